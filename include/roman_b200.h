@@ -1,0 +1,186 @@
+/*
+ * roman_b200.h — C ABI of libroman_b200.so: the B200-native (sm_100a) replacement for the
+ * CLIPPER registration hot path that roman.align drives through the `clipperpy` pybind11 module.
+ *
+ * The reference has no C ABI for this path (pybind11 is a C++ ABI); each entry point below
+ * names the reference interface it replaces (paths relative to the reference repo,
+ * clipper/ = dependencies/clipper/).  Plain pointers and sizes only — no torch, no C++ types.
+ *
+ * Conventions
+ *   - Every function returns 0 on success, a negative rb_status on error; the message is
+ *     available from rb_last_error().  Per-problem soft failures (too few inliers) are
+ *     reported in `status[b]`, never as a return code (mirrors the Python exceptions caught
+ *     per pair in roman/align/submap_align.py:179-184).
+ *   - "Device" entry points take DEVICE pointers and a cudaStream_t (passed as void*); they
+ *     only enqueue work on that stream and never synchronise.  "Host" entry points (_host
+ *     suffix) take HOST pointers, do the H2D/D2H copies themselves and return after the
+ *     results are in the host buffers.
+ *   - A batch is B independent submap-pair problems.  Problem b has n1[b], n2[b] objects and
+ *     m[b] putative associations (m = n1*n2 when all-to-all).  Per-object feature rows are
+ *     object-major: D1 is the concatenation over b of n1[b] rows of d doubles — exactly the
+ *     memory of the (d x n1) column-major Eigen matrix the reference receives
+ *     (clipper/bindings/python/py_clipper.cpp:316-318, roman/align/roman_registration.py:88-96).
+ *   - Per-association arrays (A, u0, u, nodes, sel) are the concatenation over b of m[b]
+ *     entries, problem b starting at rb_assoc_offset(h, b).
+ */
+#ifndef ROMAN_B200_H
+#define ROMAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB_MAX_RATIO_FEATURES 8
+
+typedef struct rb_handle rb_handle;
+
+typedef enum {
+  RB_OK = 0,
+  RB_ERR_ARG = -1,       /* bad argument / unsupported configuration */
+  RB_ERR_CUDA = -2,      /* CUDA runtime error */
+  RB_ERR_NOPLAN = -3,    /* stage called before rb_plan / out of order */
+  RB_ERR_TOO_LARGE = -4, /* m exceeds what the solver's shared-memory layout supports */
+  RB_ERR_ALLOC = -5
+} rb_status;
+
+/* per-problem status written by rb_arun / rb_align_batch */
+#define RB_PAIR_OK 0
+#define RB_PAIR_INSUFFICIENT 1 /* fewer than point_dim inliers: T filled with NaN
+                                  (InsufficientAssociationsException, object_registration.py:107-108) */
+
+/* Which invariant scores the pairs. */
+#define RB_INVARIANT_ROMAN 0     /* clipper::invariants::ROMAN      (pairwise + single) */
+#define RB_INVARIANT_EUCLIDEAN 1 /* clipper::invariants::EuclideanDistance (pairwise)   */
+
+/* POD mirror of clipper::invariants::ROMAN::Params (clipper/include/clipper/invariants/roman.h:27-53)
+ * and EuclideanDistance::Params (euclidean_distance.h:24-29; uses sigma, epsilon, mindist only). */
+typedef struct {
+  int32_t kind;              /* RB_INVARIANT_* */
+  int32_t point_dim;         /* 2 or 3 */
+  int32_t ratio_feature_dim; /* 0..RB_MAX_RATIO_FEATURES */
+  int32_t cos_feature_dim;   /* 0 or D */
+  int32_t fusion_method;     /* 0 GEOMETRIC_MEAN, 1 ARITHMETIC_MEAN, 2 PRODUCT (roman.h:22-26) */
+  int32_t gravity_guided;
+  int32_t drift_aware;
+  int32_t drift_scale_sigma;
+  double sigma, epsilon, mindist;
+  double distance_weight, ratio_weight, cosine_weight;
+  double ratio_epsilon[RB_MAX_RATIO_FEATURES];
+  double cosine_min, cosine_max;
+  double gravity_unc_ang_rad;
+  double drift_scale;
+} rb_invariant_params;
+
+/* POD mirror of clipper::Params (clipper/include/clipper/clipper.h:27-60). */
+typedef struct {
+  double tol_u, tol_F, tol_Fop;
+  int32_t maxiniters, maxoliters;
+  double beta;
+  int32_t maxlsiters;
+  double eps;
+  double affinityeps;
+  int32_t rescale_u0;
+  int32_t rounding; /* 0 NONZERO, 1 DSD (unsupported: RB_ERR_ARG), 2 DSD_HEU */
+} rb_solver_params;
+
+/* Fill with the reference defaults (roman.h:27-53, clipper.h:27-60). */
+void rb_default_invariant_params(rb_invariant_params* p);
+void rb_default_solver_params(rb_solver_params* p);
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+
+/* One handle per (device, stream user).  Owns only scratch: packed M storage, association
+ * records, work vectors; sized lazily by rb_plan and reused.  Not thread-safe.
+ * Replaces: construction of clipperpy.CLIPPER / CLIPPERPairwiseAndSingle
+ * (py_clipper.cpp:258-332; roman/align/roman_registration.py:82-86). */
+int rb_create(rb_handle** out, int device);
+int rb_destroy(rb_handle* h);
+const char* rb_last_error(const rb_handle* h);
+
+/* Replaces clipperpy.invariants.ROMANParams / ROMAN(...) / EuclideanDistanceParams
+ * (py_clipper.cpp:51-122) and clipperpy.Params (py_clipper.cpp:226-242). */
+int rb_set_invariant_params(rb_handle* h, const rb_invariant_params* p);
+int rb_set_solver_params(rb_handle* h, const rb_solver_params* p);
+
+/* ---- planning ------------------------------------------------------------------------- */
+
+/* Describe the batch shapes (HOST arrays of length B).  m == NULL means all-to-all
+ * (m[b] = n1[b]*n2[b], A implicit: utils::createAllToAll, clipper/include/clipper/utils.h:61-71).
+ * d = doubles per object row.  Computes offsets, (re)allocates scratch, uploads descriptors.
+ * Does not touch the compute stream; call it outside timed regions when shapes repeat. */
+int rb_plan(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const int32_t* n2,
+            const int32_t* m);
+int64_t rb_assoc_offset(const rb_handle* h, int32_t b); /* b == B gives the total */
+int64_t rb_obj1_offset(const rb_handle* h, int32_t b);  /* in objects (rows of d doubles) */
+int64_t rb_obj2_offset(const rb_handle* h, int32_t b);
+int64_t rb_packed_bytes(const rb_handle* h);            /* bytes of packed M for the batch */
+
+/* ---- device-pointer stages ---------------------------------------------------------------- */
+
+/* K1a + K1.  Replaces CLIPPER::scorePairwiseConsistency (clipper/src/clipper.cpp:29-73) and
+ * CLIPPERPairwiseAndSingle::scorePairwiseAndSingleConsistency (:77-136) with the ROMAN /
+ * EuclideanDistance invariants (clipper/src/invariants/roman.cpp, euclidean_distance.cpp).
+ * A: device int32 (sum m) x 2 row-major, or NULL when the plan is all-to-all.
+ * Result stays in the handle (packed strict-upper M in 32x32 tiles; C = pattern(M)). */
+int rb_affinity(rb_handle* h, const double* D1, const double* D2, const int32_t* A, void* stream);
+
+/* K2.  Replaces CLIPPER::solve / findDenseClique (clipper/src/clipper.cpp:140-149, 243-394),
+ * utils::findIndicesOfkLargest (clipper/src/utils.cpp:33-55) and
+ * utils::selectInlierAssociations (:101-108).
+ * u0: device (sum m) doubles — REQUIRED (the reference draws it from std::random_device,
+ *     clipper/src/utils.cpp:22-29; callers wanting that behaviour fill u0 with U[0,1)).
+ * Outputs (device; any may be NULL): nodes (sum m int32, first n_nodes[b] valid per problem,
+ * ordered as the reference: descending u), sel (sum m x 2 int32: rows of A at nodes),
+ * n_nodes (B), u (sum m), score (B), ifinal (B), n_passes (B: M passes streamed). */
+int rb_solve(rb_handle* h, const double* u0, int32_t* nodes, int32_t* sel, int32_t* n_nodes,
+             double* u, double* score, int32_t* ifinal, int32_t* n_passes, void* stream);
+
+/* K3.  Replaces ObjectRegistration.T_align (roman/align/object_registration.py:88-129):
+ * Arun/Umeyama with unit weights on the matched object centres (first point_dim entries of
+ * the rows).  sel / n_sel as produced by rb_solve (or any correspondences laid out the same).
+ * T: device B x 16 doubles, row-major 4x4 mapping frame-2 points into frame 1 (for
+ * point_dim == 2 the 2x2 rotation and translation sit in rows/cols {0,1} and column 3).
+ * status: device B int32 (RB_PAIR_*). */
+int rb_arun(rb_handle* h, const double* D1, const double* D2, const int32_t* sel,
+            const int32_t* n_sel, double* T, int32_t* status, void* stream);
+
+/* rb_affinity + rb_solve + rb_arun on one stream: one ObjectRegistration.register + T_align
+ * per problem (object_registration.py:22-29, 88-129).  Optional outputs may be NULL. */
+int rb_align_batch(rb_handle* h, const double* D1, const double* D2, const int32_t* A,
+                   const double* u0, int32_t* sel, int32_t* n_sel, double* T, int32_t* status,
+                   double* score, int32_t* n_passes, void* stream);
+
+/* Replaces CLIPPER::getAffinityMatrix / getConstraintMatrix (clipper/src/clipper.cpp:202-216):
+ * dense m x m row-major M + I and C + I of problem b into device buffers (either may be NULL). */
+int rb_get_dense(rb_handle* h, int32_t b, double* M_out, double* C_out, void* stream);
+
+/* Replaces CLIPPER::setMatrixData (clipper/src/clipper.cpp:220-229): take the strict upper
+ * triangles of dense row-major device matrices as problem b's M and C.  Entries with C != 0
+ * and M == 0 are kept (stored as -0.0); entries with M != 0 and C == 0 are unsupported. */
+int rb_set_dense(rb_handle* h, int32_t b, const double* M, const double* C, void* stream);
+
+/* Device milliseconds of the last rb_align_batch / stage calls, measured with CUDA events on
+ * the launch stream: ms[0]=prep(K1a) ms[1]=affinity(K1) ms[2]=solve(K2) ms[3]=arun(K3).
+ * Synchronises on the recorded events.  Enabled by rb_set_profiling(h, 1). */
+int rb_set_profiling(rb_handle* h, int32_t on);
+int rb_get_stage_ms(rb_handle* h, float ms[4]);
+
+/* ---- host-buffer entry point (what a cgo / ctypes / JNI binding of the reference would call) ---- */
+
+/* Same as rb_align_batch with HOST pointers: copies D1, D2, A, u0 to the device, runs the
+ * three stages, copies sel, n_sel, T, status, score, n_passes back, synchronises.  Pinned host
+ * buffers make the copies asynchronous; pageable ones work too.  Requires a prior rb_plan. */
+int rb_align_batch_host(rb_handle* h, const double* D1, const double* D2, const int32_t* A,
+                        const double* u0, int32_t* sel, int32_t* n_sel, double* T,
+                        int32_t* status, double* score, int32_t* n_passes);
+
+/* Library/build identification. */
+const char* rb_version(void);
+int rb_device_sm_count(const rb_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROMAN_B200_H */

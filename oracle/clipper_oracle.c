@@ -1,0 +1,668 @@
+/*
+ * clipper_oracle.c — CPU fp64 restatement of the roman.align / CLIPPER hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under roman_b200/ may import, link or call this
+ * file; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs use it, and only as the checker / the timed CPU baseline.
+ *
+ * Why a restatement: the reference library (dependencies/clipper, C++14) hard-requires
+ * Eigen3 (clipper/CMakeLists.txt:40), which is not installed in this image and cannot be
+ * fetched, so the reference cannot be compiled into oracle/_ref.  This file follows the
+ * reference's algorithm AND structure, Eigen-free, in plain C + OpenMP:
+ *
+ *   orc_single_similarity      <- clipper/src/invariants/roman.cpp:116-164
+ *   orc_pairwise_similarity    <- clipper/src/invariants/roman.cpp:17-85
+ *   orc_pairwise_single_fusion <- clipper/src/invariants/roman.cpp:87-114
+ *   orc_euclidean              <- clipper/src/invariants/euclidean_distance.cpp:13-31
+ *   orc_k2ij                   <- clipper/src/utils.cpp:87-97
+ *   orc_score                  <- clipper/src/clipper.cpp:29-73 and :77-136
+ *                                 (dense zero scratch, OpenMP over the pair index,
+ *                                  sparseView -> CSC strict upper, C = pattern(M))
+ *   symv_upper                 <- Eigen/src/SparseCore/SparseSelfAdjointView.h
+ *                                 sparse_selfadjoint_time_dense_product, Upper|ColMajor
+ *                                 (the accumulation ORDER of M_.selfadjointView<Upper>()*u)
+ *   orc_solve                  <- clipper/src/clipper.cpp:243-394 (findDenseClique)
+ *   orc_k_largest              <- clipper/src/utils.cpp:33-55 (findIndicesOfkLargest)
+ *   orc_arun                   <- roman/align/object_registration.py:110-129 (T_align)
+ *
+ * Parity pin status (see DESIGN.md "Oracle"): the Euclidean affinity build and the
+ * end-to-end solve are pinned by the reference's own known-answer tests
+ * (clipper/test/affinity_test.cpp:94-107, clipper/test/clipper_test.cpp:62-66,
+ * committed as tests/golden/ JSON files).  The ROMAN invariant, the solver iterates for a
+ * fixed u0, the top-k tie order and T_align have NO golden vector anywhere in the
+ * reference: for those, PARITY IS UNPINNED and this restatement (cross-checked against
+ * the independent numpy restatement oracle/clipper_np.py) is the sole pin.
+ *
+ * Compile: gcc -O3 -march=native -fopenmp -ffp-contract=off -shared -fPIC (oracle/Makefile).
+ * -ffp-contract=off keeps a*b+c as two roundings so the arithmetic is well defined.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_MAX_RATIO 8
+
+/* roman.cpp:11-12 — truncated literals, used verbatim */
+#define SQRT_TWO_THIRDS 0.81649658092
+#define SQRT_ONE_THIRD 0.57735026919
+
+typedef struct {
+  int32_t kind;              /* 0 = ROMAN (pairwise + single), 1 = EuclideanDistance */
+  int32_t point_dim;         /* roman.h:29 */
+  int32_t ratio_feature_dim; /* roman.h:30 */
+  int32_t cos_feature_dim;   /* roman.h:31 */
+  int32_t fusion_method;     /* roman.h:22-26: 0 GEOMETRIC_MEAN, 1 ARITHMETIC_MEAN, 2 PRODUCT */
+  int32_t gravity_guided;    /* roman.h:47 */
+  int32_t drift_aware;       /* roman.h:50 */
+  int32_t drift_scale_sigma; /* roman.h:51 */
+  double sigma, epsilon, mindist;                      /* roman.h:34-36 */
+  double distance_weight, ratio_weight, cosine_weight; /* roman.h:38-40 */
+  double ratio_epsilon[ORC_MAX_RATIO];                 /* roman.h:42 */
+  double cosine_min, cosine_max;                       /* roman.h:43-44 */
+  double gravity_unc_ang_rad;                          /* roman.h:48 */
+  double drift_scale;                                  /* roman.h:52 */
+} orc_invariant_params;
+
+typedef struct {
+  double tol_u, tol_F, tol_Fop; /* clipper.h:30-32 */
+  int32_t maxiniters, maxoliters; /* clipper.h:33-34 */
+  double beta;                  /* clipper.h:37 */
+  int32_t maxlsiters;           /* clipper.h:38 */
+  double eps;                   /* clipper.h:40 */
+  double affinityeps;           /* clipper.h:42 */
+  int32_t rescale_u0;           /* clipper.h:44 */
+  int32_t rounding;             /* clipper.h:50: 0 NONZERO, 1 DSD, 2 DSD_HEU */
+} orc_solver_params;
+
+/* CSC strict-upper sparse matrix (what Eigen's sparseView() of the dense scratch yields) */
+typedef struct {
+  int64_t n;
+  int64_t nnz;
+  int64_t *colptr; /* n+1 */
+  int32_t *rowidx; /* nnz, ascending inside a column, all < column */
+  double *val;     /* nnz */
+} orc_csc;
+
+void orc_csc_free(orc_csc *s) {
+  if (!s) return;
+  free(s->colptr); free(s->rowidx); free(s->val);
+  s->colptr = NULL; s->rowidx = NULL; s->val = NULL; s->nnz = 0; s->n = 0;
+}
+
+/* ---------------------------------------------------------------- invariants */
+
+static double norm_head(const double *a, const double *b, int n) {
+  double s = 0.0;
+  for (int i = 0; i < n; ++i) { const double d = a[i] - b[i]; s += d * d; }
+  return sqrt(s);
+}
+
+/* roman.cpp:116-164 */
+double orc_single_similarity(const orc_invariant_params *p, const double *ai, const double *bi) {
+  double cosine_score_scaled = 0.0;
+  double ratio_score = 0.0;
+  if (p->cos_feature_dim == 0 && p->ratio_feature_dim == 0) return 1.0;
+
+  if (p->cos_feature_dim > 0) {
+    const double *fa = ai + p->point_dim + p->ratio_feature_dim;
+    const double *fb = bi + p->point_dim + p->ratio_feature_dim;
+    double dot = 0.0, na = 0.0, nb = 0.0;
+    for (int i = 0; i < p->cos_feature_dim; ++i) {
+      dot += fa[i] * fb[i]; na += fa[i] * fa[i]; nb += fb[i] * fb[i];
+    }
+    const double cosine_score = dot / (sqrt(na) * sqrt(nb));
+    if (cosine_score >= p->cosine_max) cosine_score_scaled = 1.0;
+    else if (cosine_score <= p->cosine_min) return 0.0;
+    else cosine_score_scaled = (cosine_score - p->cosine_min) / (p->cosine_max - p->cosine_min);
+    if (p->ratio_feature_dim == 0) return cosine_score_scaled;
+  }
+
+  if (p->ratio_feature_dim > 0) {
+    double prod = 1.0;
+    int any_below = 0;
+    for (int i = 0; i < p->ratio_feature_dim; ++i) {
+      const double a = ai[p->point_dim + i], b = bi[p->point_dim + i];
+      const double r = a < b ? a / b : b / a;
+      if (r < p->ratio_epsilon[i]) any_below = 1; /* NaN < x is false, as in Eigen's array compare */
+      prod *= r;
+    }
+    if (any_below) return 0.0;
+    ratio_score = pow(prod, 1.0 / p->ratio_feature_dim);
+    if (p->cos_feature_dim == 0) return ratio_score;
+  }
+  return pow(pow(ratio_score, p->ratio_weight) * pow(cosine_score_scaled, p->cosine_weight),
+             1.0 / (p->ratio_weight + p->cosine_weight));
+}
+
+/* roman.cpp:17-85 */
+double orc_pairwise_similarity(const orc_invariant_params *p, double cos_unc, double sin_unc,
+                               const double *ai, const double *aj, const double *bi,
+                               const double *bj) {
+  const double l1 = norm_head(ai, aj, p->point_dim);
+  const double l2 = norm_head(bi, bj, p->point_dim);
+  if (p->mindist > 0 && (l1 < p->mindist || l2 < p->mindist)) return 0.0;
+
+  const double epsilon = p->drift_aware
+                             ? fmax(p->epsilon, p->epsilon * p->drift_scale * 0.5 * (l1 + l2))
+                             : p->epsilon;
+  const double sigma = (p->drift_aware && p->drift_scale_sigma)
+                           ? fmax(p->sigma, p->sigma * p->drift_scale * 0.5 * (l1 + l2))
+                           : p->sigma;
+
+  if (p->gravity_guided) {
+    const double xy_dist1 = norm_head(ai, aj, 2);
+    const double xy_dist2 = norm_head(bi, bj, 2);
+    const double z_diff1 = ai[2] - aj[2];
+    const double z_diff2 = bi[2] - bj[2];
+    const double c_xy = fabs(xy_dist1 - xy_dist2);
+    const double c_z = fabs(z_diff1 - z_diff2);
+    double sigma_xy = sigma, sigma_z = sigma, epsilon_xy = epsilon, epsilon_z = epsilon;
+    if (p->gravity_unc_ang_rad > 0.0) {
+      const double xy_dist_mean = 0.5 * (xy_dist1 + xy_dist2);
+      const double z_dist_mean = 0.5 * (fabs(z_diff1) + fabs(z_diff2));
+      sigma_xy += fabs(xy_dist_mean * cos_unc - xy_dist_mean);
+      sigma_z += fabs(z_dist_mean * sin_unc);
+      epsilon_xy += fabs(xy_dist_mean * cos_unc - xy_dist_mean);
+      epsilon_z += fabs(z_dist_mean * sin_unc);
+    }
+    if (c_xy > SQRT_TWO_THIRDS * epsilon_xy || c_z > SQRT_ONE_THIRD * epsilon_z) return 0.0;
+    return exp(-0.5 * (c_xy * c_xy / (2.0 / 3.0 * sigma_xy * sigma_xy) +
+                       c_z * c_z / (sigma_z * sigma_z / 3.0)));
+  } else {
+    const double c = fabs(l1 - l2);
+    if (c > epsilon) return 0.0;
+    return exp(-0.5 * c * c / (sigma * sigma));
+  }
+}
+
+/* roman.cpp:87-114 */
+double orc_pairwise_single_fusion(const orc_invariant_params *p, double pair_ij, double single_i,
+                                  double single_j) {
+  if (p->ratio_feature_dim > 0 || p->cos_feature_dim > 0) {
+    switch (p->fusion_method) {
+      case 0: {
+        const double dist_score_pow = pow(pair_ij, p->distance_weight);
+        return pow(dist_score_pow * single_i * single_j, 1.0 / (p->distance_weight + 2.0));
+      }
+      case 1:
+        return (p->distance_weight * pair_ij + single_i + single_j) / (p->distance_weight + 2.0);
+      case 2:
+        return pair_ij * single_i * single_j;
+      default:
+        return 0.0;
+    }
+  }
+  return pair_ij;
+}
+
+/* euclidean_distance.cpp:13-31 — norms over the WHOLE datum (all d rows) */
+double orc_euclidean(const orc_invariant_params *p, int d, const double *ai, const double *aj,
+                     const double *bi, const double *bj) {
+  const double l1 = norm_head(ai, aj, d);
+  const double l2 = norm_head(bi, bj, d);
+  if (p->mindist > 0 && (l1 < p->mindist || l2 < p->mindist)) return 0.0;
+  const double c = fabs(l1 - l2);
+  return (c < p->epsilon) ? exp(-0.5 * c * c / (p->sigma * p->sigma)) : 0;
+}
+
+/* utils.cpp:87-97 */
+void orc_k2ij(uint64_t k, uint64_t n, uint64_t *io, uint64_t *jo) {
+  k += 1;
+  const uint64_t l = n * (n - 1) / 2 - k;
+  const uint64_t o = (uint64_t)floor((sqrt((double)(1 + 8 * l)) - 1) / 2.);
+  const uint64_t p = l - o * (o + 1) / 2;
+  const uint64_t i = n - (o + 1);
+  const uint64_t j = n - p;
+  *io = i - 1;
+  *jo = j - 1;
+}
+
+/* utils.h:61-71 */
+void orc_create_all_to_all(int n1, int n2, int32_t *A /* (n1*n2) x 2 row-major */) {
+  for (int i = 0; i < n1; ++i)
+    for (int j = 0; j < n2; ++j) {
+      A[2 * (j + (int64_t)i * n2) + 0] = i;
+      A[2 * (j + (int64_t)i * n2) + 1] = j;
+    }
+}
+
+/* ---------------------------------------------------------------- affinity build */
+
+/*
+ * clipper.cpp:29-73 (kind==1) / :77-136 (kind==0).
+ * D1: n1 objects x d doubles, object-major (one Eigen column = one object = d contiguous
+ * doubles).  A: m x 2 int32 row-major.  Output: CSC strict-upper M; optionally the dense
+ * scratch (m x m row-major, zeros elsewhere) and single_sim (m) for the tests.
+ * parallelize mirrors CLIPPER::parallelize_ (clipper.h:147).
+ */
+int orc_score(const orc_invariant_params *ip, double affinityeps, int d, int n1, const double *D1,
+              int n2, const double *D2, int64_t m, const int32_t *A, int parallelize,
+              orc_csc *out, double *dense_out /* nullable, m*m */,
+              double *single_out /* nullable, m */) {
+  (void)n1; (void)n2;
+  const double cos_unc = cos(ip->gravity_unc_ang_rad); /* roman.h:57-58 */
+  const double sin_unc = sin(ip->gravity_unc_ang_rad);
+
+  double *M = (double *)calloc((size_t)m * (size_t)m, sizeof(double)); /* MatrixXd::Zero(m,m) */
+  double *single_sim = (double *)calloc((size_t)(m > 0 ? m : 1), sizeof(double));
+  if (!M || !single_sim) { free(M); free(single_sim); return -1; }
+
+  if (ip->kind == 0) {
+    for (int64_t i = 0; i < m; ++i) { /* clipper.cpp:89-93, serial */
+      const double *d1i = D1 + (int64_t)A[2 * i] * d;
+      const double *d2i = D2 + (int64_t)A[2 * i + 1] * d;
+      single_sim[i] = orc_single_similarity(ip, d1i, d2i);
+    }
+  }
+
+  const int64_t npairs = m * (m - 1) / 2;
+#pragma omp parallel for if (parallelize) schedule(static)
+  for (int64_t k = 0; k < npairs; ++k) {
+    uint64_t i, j;
+    orc_k2ij((uint64_t)k, (uint64_t)m, &i, &j);
+    if (A[2 * i] == A[2 * j] || A[2 * i + 1] == A[2 * j + 1]) continue; /* distinctness */
+    const double *d1i = D1 + (int64_t)A[2 * i] * d;
+    const double *d1j = D1 + (int64_t)A[2 * j] * d;
+    const double *d2i = D2 + (int64_t)A[2 * i + 1] * d;
+    const double *d2j = D2 + (int64_t)A[2 * j + 1] * d;
+    double scr;
+    if (ip->kind == 0) {
+      if (single_sim[i] < affinityeps || single_sim[j] < affinityeps) continue;
+      const double pw = orc_pairwise_similarity(ip, cos_unc, sin_unc, d1i, d1j, d2i, d2j);
+      scr = orc_pairwise_single_fusion(ip, pw, single_sim[i], single_sim[j]);
+    } else {
+      scr = orc_euclidean(ip, d, d1i, d1j, d2i, d2j);
+    }
+    if (scr > affinityeps) M[i * m + j] = scr; /* M(i,j), i<j */
+  }
+
+  /* M_ = M.sparseView(): column-major scan keeping coefficients != 0 */
+  int64_t nnz = 0;
+  for (int64_t i = 0; i < m; ++i)
+    for (int64_t j = i + 1; j < m; ++j)
+      if (M[i * m + j] != 0.0) ++nnz;
+  out->n = m;
+  out->nnz = nnz;
+  out->colptr = (int64_t *)malloc(sizeof(int64_t) * (size_t)(m + 1));
+  out->rowidx = (int32_t *)malloc(sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1));
+  out->val = (double *)malloc(sizeof(double) * (size_t)(nnz > 0 ? nnz : 1));
+  int64_t q = 0;
+  for (int64_t j = 0; j < m; ++j) {
+    out->colptr[j] = q;
+    for (int64_t i = 0; i < j; ++i) {
+      const double v = M[i * m + j];
+      if (v != 0.0) { out->rowidx[q] = (int32_t)i; out->val[q] = v; ++q; }
+    }
+  }
+  out->colptr[m] = q;
+
+  if (dense_out) memcpy(dense_out, M, sizeof(double) * (size_t)m * (size_t)m);
+  if (single_out) memcpy(single_out, single_sim, sizeof(double) * (size_t)m);
+  free(M);
+  free(single_sim);
+  return 0;
+}
+
+/* clipper.cpp:220-229 setMatrixData: strict upper triangle of a dense (row-major) M -> CSC.
+ * C is taken as given too; the solver below needs both. */
+int orc_csc_from_dense_upper(int64_t m, const double *dense, orc_csc *out) {
+  int64_t nnz = 0;
+  for (int64_t i = 0; i < m; ++i)
+    for (int64_t j = i + 1; j < m; ++j)
+      if (dense[i * m + j] != 0.0) ++nnz;
+  out->n = m; out->nnz = nnz;
+  out->colptr = (int64_t *)malloc(sizeof(int64_t) * (size_t)(m + 1));
+  out->rowidx = (int32_t *)malloc(sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1));
+  out->val = (double *)malloc(sizeof(double) * (size_t)(nnz > 0 ? nnz : 1));
+  int64_t q = 0;
+  for (int64_t j = 0; j < m; ++j) {
+    out->colptr[j] = q;
+    for (int64_t i = 0; i < j; ++i) {
+      const double v = dense[i * m + j];
+      if (v != 0.0) { out->rowidx[q] = (int32_t)i; out->val[q] = v; ++q; }
+    }
+  }
+  out->colptr[m] = q;
+  return 0;
+}
+
+/* ---------------------------------------------------------------- solver */
+
+/* res = selfadjointView<Upper>(S) * x, in Eigen's accumulation order.
+ * If unit_values, every stored value is taken as 1.0 (C_ = pattern(M_), clipper.cpp:71-72). */
+static void symv_upper(const orc_csc *S, int unit_values, const double *x, double *res) {
+  const int64_t n = S->n;
+  for (int64_t i = 0; i < n; ++i) res[i] = 0.0;
+  for (int64_t j = 0; j < n; ++j) {
+    const double rhs_j = x[j];
+    double res_j = 0.0;
+    for (int64_t q = S->colptr[j]; q < S->colptr[j + 1]; ++q) {
+      const int32_t i = S->rowidx[q];
+      const double v = unit_values ? 1.0 : S->val[q];
+      res_j += v * x[i];
+      res[i] += v * rhs_j;
+    }
+    res[j] += res_j;
+  }
+}
+
+static double vsum(const double *x, int64_t n) { double s = 0; for (int64_t i = 0; i < n; ++i) s += x[i]; return s; }
+static double vdot(const double *a, const double *b, int64_t n) { double s = 0; for (int64_t i = 0; i < n; ++i) s += a[i] * b[i]; return s; }
+
+typedef struct { double v; int32_t i; } hp_t;
+/* std::greater<pair<double,int>> min-heap == ordered by (v, i) ascending at the top */
+static int hp_less(hp_t a, hp_t b) { return a.v < b.v || (a.v == b.v && a.i < b.i); }
+static void hp_push(hp_t *h, int *sz, hp_t e) {
+  int c = (*sz)++; h[c] = e;
+  while (c > 0) { int p = (c - 1) / 2; if (hp_less(h[c], h[p])) { hp_t t = h[c]; h[c] = h[p]; h[p] = t; c = p; } else break; }
+}
+static void hp_pop(hp_t *h, int *sz) {
+  h[0] = h[--(*sz)];
+  int c = 0;
+  for (;;) {
+    int l = 2 * c + 1, r = l + 1, s = c;
+    if (l < *sz && hp_less(h[l], h[s])) s = l;
+    if (r < *sz && hp_less(h[r], h[s])) s = r;
+    if (s == c) break;
+    hp_t t = h[c]; h[c] = h[s]; h[s] = t; c = s;
+  }
+}
+
+/* utils.cpp:33-55.  Returns number of indices written (k, or 0 if k<1).  k is clamped to n
+ * (the reference would be UB for k>n; it cannot occur because F <= n). */
+int orc_k_largest(const double *x, int64_t n, int k, int32_t *indices) {
+  if (k < 1) return 0;
+  if (k > n) k = (int)n;
+  hp_t *h = (hp_t *)malloc(sizeof(hp_t) * (size_t)k);
+  int sz = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    if (sz < k) { hp_t e = {x[i], (int32_t)i}; hp_push(h, &sz, e); }
+    else if (h[0].v < x[i]) { hp_pop(h, &sz); hp_t e = {x[i], (int32_t)i}; hp_push(h, &sz, e); }
+  }
+  for (int i = 0; i < k; ++i) { indices[k - i - 1] = h[0].i; hp_pop(h, &sz); }
+  free(h);
+  return k;
+}
+
+/*
+ * clipper.cpp:243-394.  M, C: CSC strict upper (C values ignored when c_is_pattern).
+ * Outputs: u (n), nodes (capacity n), *n_nodes, *score, *ifinal, *n_matvec_pairs (number of
+ * times the reference evaluates a fresh (M*x, C*x) pair — the "passes" of SURVEY §8d).
+ */
+int orc_solve(const orc_solver_params *sp, const orc_csc *M, const orc_csc *C, int c_is_pattern,
+              const double *u0, double *u_out, int32_t *nodes, int32_t *n_nodes, double *score,
+              int32_t *ifinal, int32_t *n_passes) {
+  const int64_t n = M->n;
+  double *buf = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1) * 8);
+  if (!buf) return -1;
+  double *gradF = buf, *gradFnew = buf + n, *u = buf + 2 * n, *unew = buf + 3 * n;
+  double *Mu = buf + 4 * n, *Cu = buf + 5 * n, *Cbu = buf + 6 * n, *tmp = buf + 7 * n;
+  int passes = 0;
+
+  if (sp->rescale_u0) { /* :264-265  u = M*u0 + u0 */
+    symv_upper(M, 0, u0, tmp); ++passes;
+    for (int64_t i = 0; i < n; ++i) u[i] = tmp[i] + u0[i];
+  } else {
+    for (int64_t i = 0; i < n; ++i) u[i] = u0[i];
+  }
+  { const double nrm = sqrt(vdot(u, u, n)); for (int64_t i = 0; i < n; ++i) u[i] /= nrm; } /* :269 */
+
+  double d = 0; /* :272-280 */
+  {
+    const double su = vsum(u, n);
+    symv_upper(C, c_is_pattern, u, Cu); ++passes;
+    int64_t cnt = 0;
+    for (int64_t i = 0; i < n; ++i) { Cbu[i] = (su - Cu[i]) - u[i]; if (Cbu[i] > sp->eps && u[i] > sp->eps) ++cnt; }
+    if (cnt > 0) {
+      symv_upper(M, 0, u, Mu);
+      double s = 0;
+      for (int64_t i = 0; i < n; ++i) if (Cbu[i] > sp->eps && u[i] > sp->eps) s += (Mu[i] + u[i]) / Cbu[i];
+      d = s / (double)cnt;
+    }
+  }
+
+  double F = 0;
+  int64_t i_ol, j_il, k_ls;
+  for (i_ol = 0; i_ol < sp->maxoliters; ++i_ol) {
+    { /* :290 gradF = (1+d)*u - d*ones*u.sum() + M*u + C*u*d */
+      const double su = vsum(u, n);
+      symv_upper(M, 0, u, Mu); symv_upper(C, c_is_pattern, u, Cu); ++passes;
+      for (int64_t i = 0; i < n; ++i) gradF[i] = (((1 + d) * u[i] - d * su) + Mu[i]) + Cu[i] * d;
+    }
+    F = vdot(u, gradF, n);
+
+    for (j_il = 0; j_il < sp->maxiniters; ++j_il) {
+      double alpha = 1;
+      double Fnew = 0, deltaF = 0;
+      for (k_ls = 0; k_ls < sp->maxlsiters; ++k_ls) {
+        for (int64_t i = 0; i < n; ++i) { const double t = u[i] + alpha * gradF[i]; unew[i] = t > 0 ? t : 0; } /* cwiseMax(0) */
+        { const double z = vdot(unew, unew, n); if (z > 0) { const double nrm = sqrt(z); for (int64_t i = 0; i < n; ++i) unew[i] /= nrm; } } /* normalize() */
+        const double sun = vsum(unew, n);
+        symv_upper(M, 0, unew, Mu); symv_upper(C, c_is_pattern, unew, Cu); ++passes;
+        for (int64_t i = 0; i < n; ++i) gradFnew[i] = (((1 + d) * unew[i] - d * sun) + Mu[i]) + Cu[i] * d;
+        Fnew = vdot(unew, gradFnew, n);
+        deltaF = Fnew - F;
+        if (deltaF < -sp->eps) alpha = alpha * sp->beta; else break;
+      }
+      double du2 = 0;
+      for (int64_t i = 0; i < n; ++i) { const double t = unew[i] - u[i]; du2 += t * t; }
+      const double deltau = sqrt(du2);
+      F = Fnew;
+      memcpy(u, unew, sizeof(double) * (size_t)n);
+      memcpy(gradF, gradFnew, sizeof(double) * (size_t)n);
+      if (deltau < sp->tol_u || fabs(deltaF) < sp->tol_F) break;
+    }
+
+    /* :339-351 increase d */
+    const double su = vsum(u, n);
+    symv_upper(C, c_is_pattern, u, Cu); ++passes;
+    int64_t cnt = 0;
+    for (int64_t i = 0; i < n; ++i) { Cbu[i] = (su - Cu[i]) - u[i]; if (Cbu[i] > sp->eps && u[i] > sp->eps) ++cnt; }
+    if (cnt > 0) {
+      symv_upper(M, 0, u, Mu);
+      double s = 0;
+      for (int64_t i = 0; i < n; ++i) if (Cbu[i] > sp->eps && u[i] > sp->eps) s += fabs((Mu[i] + u[i]) / Cbu[i]);
+      d += s / (double)cnt;
+    } else {
+      break;
+    }
+  }
+
+  int nn = 0;
+  if (sp->rounding == 0) { /* NONZERO, utils.cpp:59-68 */
+    for (int64_t i = 0; i < n; ++i) if (u[i] > 0.0) nodes[nn++] = (int32_t)i;
+  } else if (sp->rounding == 2) { /* DSD_HEU :373-381 */
+    const int omega = (int)round(F);
+    nn = orc_k_largest(u, n, omega, nodes);
+  } else {
+    free(buf);
+    return -2; /* exact DSD (dsd.cpp) is out of scope of this path */
+  }
+  *n_nodes = nn;
+  *score = F;
+  *ifinal = (int32_t)i_ol;
+  if (n_passes) *n_passes = passes;
+  memcpy(u_out, u, sizeof(double) * (size_t)n);
+  free(buf);
+  return 0;
+}
+
+/* ---------------------------------------------------------------- Arun / Umeyama */
+
+/* Cyclic Jacobi eigen-decomposition of a symmetric 3x3 (row-major); V columns = eigenvectors */
+static void jacobi_eig3(double A[9], double V[9]) {
+  for (int i = 0; i < 9; ++i) V[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    const double off = A[1] * A[1] + A[2] * A[2] + A[5] * A[5];
+    if (off < 1e-300) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        const double apq = A[p * 3 + q];
+        if (apq == 0.0) continue;
+        const double app = A[p * 3 + p], aqq = A[q * 3 + q];
+        const double theta = (aqq - app) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 3; ++k) { /* A <- A J */
+          const double akp = A[k * 3 + p], akq = A[k * 3 + q];
+          A[k * 3 + p] = c * akp - s * akq; A[k * 3 + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < 3; ++k) { /* A <- J^T A */
+          const double apk = A[p * 3 + k], aqk = A[q * 3 + k];
+          A[p * 3 + k] = c * apk - s * aqk; A[q * 3 + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double vkp = V[k * 3 + p], vkq = V[k * 3 + q];
+          V[k * 3 + p] = c * vkp - s * vkq; V[k * 3 + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+}
+
+static double det3(const double *R) {
+  return R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
+}
+
+/*
+ * object_registration.py:110-129 with unit weights, dim = 3 only in this C form (the numpy
+ * restatement oracle/clipper_np.py keeps np.linalg.svd and dim 2).  R = U diag(1,1,s) V^T with
+ * s = +-1 chosen so det R = +1, which is what the "flip the last row of Vh" fix produces.
+ * pts: k x 3 row-major.  T: 4x4 row-major.  Returns -1 if k < 3 (InsufficientAssociations).
+ */
+int orc_arun(int k, const double *pts1, const double *pts2, double *T) {
+  if (k < 3) return -1;
+  double m1[3] = {0, 0, 0}, m2[3] = {0, 0, 0};
+  for (int i = 0; i < k; ++i) for (int a = 0; a < 3; ++a) { m1[a] += pts1[3 * i + a]; m2[a] += pts2[3 * i + a]; }
+  for (int a = 0; a < 3; ++a) { m1[a] /= k; m2[a] /= k; }
+  double H[9] = {0};
+  for (int i = 0; i < k; ++i)
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) H[a * 3 + b] += (pts1[3 * i + a] - m1[a]) * (pts2[3 * i + b] - m2[b]);
+  /* SVD via eig(H^T H) = V S^2 V^T, sorted descending; U = H V S^-1 completed by cross products */
+  double HtH[9], V[9];
+  for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { double s = 0; for (int c = 0; c < 3; ++c) s += H[c * 3 + a] * H[c * 3 + b]; HtH[a * 3 + b] = s; }
+  jacobi_eig3(HtH, V);
+  double ev[3] = {HtH[0], HtH[4], HtH[8]};
+  int ord[3] = {0, 1, 2};
+  for (int a = 0; a < 2; ++a) for (int b = a + 1; b < 3; ++b) if (ev[ord[b]] > ev[ord[a]]) { int t = ord[a]; ord[a] = ord[b]; ord[b] = t; }
+  double Vs[9], U[9];
+  for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) Vs[r * 3 + c] = V[r * 3 + ord[c]];
+  /* make V right-handed so that the cross-product completion below is consistent */
+  if (det3(Vs) < 0) for (int r = 0; r < 3; ++r) Vs[r * 3 + 2] = -Vs[r * 3 + 2];
+  double u0[3], u1[3], u2[3];
+  for (int r = 0; r < 3; ++r) { u0[r] = 0; u1[r] = 0; for (int c = 0; c < 3; ++c) { u0[r] += H[r * 3 + c] * Vs[c * 3 + 0]; u1[r] += H[r * 3 + c] * Vs[c * 3 + 1]; } }
+  double n0 = sqrt(u0[0] * u0[0] + u0[1] * u0[1] + u0[2] * u0[2]);
+  if (n0 < 1e-300) { /* H == 0: R = I by convention */
+    for (int i = 0; i < 16; ++i) T[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    for (int a = 0; a < 3; ++a) T[a * 4 + 3] = m1[a] - m2[a];
+    return 0;
+  }
+  for (int r = 0; r < 3; ++r) u0[r] /= n0;
+  { /* Gram-Schmidt u1 against u0 */
+    double dp = u0[0] * u1[0] + u0[1] * u1[1] + u0[2] * u1[2];
+    for (int r = 0; r < 3; ++r) u1[r] -= dp * u0[r];
+    double n1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+    if (n1 < 1e-13 * n0) { /* rank 1: any unit vector orthogonal to u0 */
+      int a = fabs(u0[0]) < fabs(u0[1]) ? (fabs(u0[0]) < fabs(u0[2]) ? 0 : 2) : (fabs(u0[1]) < fabs(u0[2]) ? 1 : 2);
+      double e[3] = {0, 0, 0}; e[a] = 1.0;
+      double dq = u0[a];
+      for (int r = 0; r < 3; ++r) u1[r] = e[r] - dq * u0[r];
+      n1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+    }
+    for (int r = 0; r < 3; ++r) u1[r] /= n1;
+  }
+  u2[0] = u0[1] * u1[2] - u0[2] * u1[1]; u2[1] = u0[2] * u1[0] - u0[0] * u1[2]; u2[2] = u0[0] * u1[1] - u0[1] * u1[0];
+  for (int r = 0; r < 3; ++r) { U[r * 3 + 0] = u0[r]; U[r * 3 + 1] = u1[r]; U[r * 3 + 2] = u2[r]; }
+  /* U and Vs are both proper rotations => R = U Vs^T has det +1, i.e. the reflection fix
+   * (flip the direction belonging to the smallest singular value) is already applied. */
+  double R[9];
+  for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { double s = 0; for (int c = 0; c < 3; ++c) s += U[a * 3 + c] * Vs[b * 3 + c]; R[a * 3 + b] = s; }
+  for (int a = 0; a < 3; ++a) {
+    for (int b = 0; b < 3; ++b) T[a * 4 + b] = R[a * 3 + b];
+    T[a * 4 + 3] = m1[a] - (R[a * 3 + 0] * m2[0] + R[a * 3 + 1] * m2[1] + R[a * 3 + 2] * m2[2]);
+  }
+  T[12] = 0; T[13] = 0; T[14] = 0; T[15] = 1;
+  return 0;
+}
+
+/* ---------------------------------------------------------------- whole-pair driver */
+
+/*
+ * One submap-pair alignment exactly as ObjectRegistration.register + T_align drive it
+ * (object_registration.py:22-29, 88-129): score -> solve -> selected associations -> Arun.
+ * Returns 0, or 1 if fewer than 3 inliers (T filled with NaN, as submap_align.py:179-184).
+ * sel: capacity m x 2.  This is the unit that bench.py's CPU baseline times.
+ */
+int orc_align_pair(const orc_invariant_params *ip, const orc_solver_params *sp, int d, int n1,
+                   const double *D1, int n2, const double *D2, int64_t m, const int32_t *A_in,
+                   const double *u0, int parallelize, int32_t *sel, int32_t *n_sel, double *T,
+                   double *score, int32_t *n_passes, int64_t *nnz_out) {
+  int32_t *A = NULL;
+  if (!A_in) { /* clipper.cpp:32,81: empty A => all-to-all */
+    m = (int64_t)n1 * n2;
+    A = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)(m > 0 ? m : 1));
+    orc_create_all_to_all(n1, n2, A);
+    A_in = A;
+  }
+  orc_csc M = {0};
+  int rc = orc_score(ip, sp->affinityeps, d, n1, D1, n2, D2, m, A_in, parallelize, &M, NULL, NULL);
+  if (rc) { free(A); return rc; }
+  double *u = (double *)malloc(sizeof(double) * (size_t)(m > 0 ? m : 1));
+  int32_t *nodes = (int32_t *)malloc(sizeof(int32_t) * (size_t)(m > 0 ? m : 1));
+  int32_t nn = 0, ifinal = 0;
+  rc = orc_solve(sp, &M, &M, 1, u0, u, nodes, &nn, score, &ifinal, n_passes);
+  if (nnz_out) *nnz_out = M.nnz;
+  orc_csc_free(&M);
+  if (rc) { free(u); free(nodes); free(A); return rc; }
+  for (int i = 0; i < nn; ++i) { sel[2 * i] = A_in[2 * nodes[i]]; sel[2 * i + 1] = A_in[2 * nodes[i] + 1]; }
+  *n_sel = nn;
+  int status = 0;
+  if (nn < 3) {
+    for (int i = 0; i < 16; ++i) T[i] = NAN;
+    status = 1;
+  } else {
+    double *p1 = (double *)malloc(sizeof(double) * 3 * (size_t)nn), *p2 = (double *)malloc(sizeof(double) * 3 * (size_t)nn);
+    for (int i = 0; i < nn; ++i)
+      for (int a = 0; a < 3; ++a) { p1[3 * i + a] = D1[(int64_t)sel[2 * i] * d + a]; p2[3 * i + a] = D2[(int64_t)sel[2 * i + 1] * d + a]; }
+    orc_arun(nn, p1, p2, T);
+    free(p1); free(p2);
+  }
+  free(u); free(nodes); free(A);
+  return status;
+}
+
+/*
+ * Throughput-fair CPU baseline: B independent pairs, one pair per thread (OpenMP over
+ * problems, affinity loop serial inside each).  All pairs share n1, n2, d; inputs are
+ * concatenated.  `threads` <= 0 means omp default.  Returns the thread count used.
+ */
+int orc_align_batch(const orc_invariant_params *ip, const orc_solver_params *sp, int B, int d,
+                    int n1, const double *D1, int n2, const double *D2, const double *u0,
+                    int threads, int32_t *sel /* B*m*2 */, int32_t *n_sel, double *T /* B*16 */,
+                    double *score, int32_t *n_passes, int32_t *status) {
+  const int64_t m = (int64_t)n1 * n2;
+  int used = 1;
+#ifdef _OPENMP
+  if (threads > 0) omp_set_num_threads(threads);
+  used = omp_get_max_threads();
+#endif
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int b = 0; b < B; ++b) {
+    status[b] = orc_align_pair(ip, sp, d, n1, D1 + (int64_t)b * n1 * d, n2, D2 + (int64_t)b * n2 * d,
+                               m, NULL, u0 + (int64_t)b * m, 0, sel + (int64_t)b * m * 2, n_sel + b,
+                               T + (int64_t)b * 16, score + b, n_passes + b, NULL);
+  }
+  return used;
+}
+
+int orc_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}

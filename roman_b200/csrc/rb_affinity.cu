@@ -1,0 +1,357 @@
+// rb_affinity.cu — K1a (association records + single scores) and K1 (pairwise affinity tiles).
+//
+// Replaces, for a batch of problems at once:
+//   CLIPPERPairwiseAndSingle::scorePairwiseAndSingleConsistency  clipper/src/clipper.cpp:77-136
+//   CLIPPER::scorePairwiseConsistency                            clipper/src/clipper.cpp:29-73
+//   ROMAN::{single_similarity,pairwise_similarity,pairwise_single_fusion}
+//                                                                clipper/src/invariants/roman.cpp
+//   EuclideanDistance::operator()                                clipper/src/invariants/euclidean_distance.cpp:13-31
+//   CLIPPER::getAffinityMatrix/getConstraintMatrix/setMatrixData clipper/src/clipper.cpp:202-229
+//
+// Arithmetic notes: the translation unit is compiled with -fmad=false so that a*b+c keeps two
+// roundings, like the reference's plain C++ expressions; sqrt and division are IEEE; exp/pow
+// are CUDA's (<= 2 ulp from libm).  All gates (distinctness, single-score, mindist, epsilon,
+// affinityeps) are evaluated exactly as written in the reference, in the same order.
+#include "rb_kernels.cuh"
+
+namespace {
+
+// roman.cpp:11-12 — truncated literals, verbatim
+constexpr double kSqrtTwoThirds = 0.81649658092;
+constexpr double kSqrtOneThird = 0.57735026919;
+
+struct Rec {
+  double ax, ay, az, bx, by, bz, s;
+  int32_t i1, i2;
+};
+
+__device__ __forceinline__ double norm3(double dx, double dy, double dz) {
+  return sqrt((dx * dx + dy * dy) + dz * dz);
+}
+
+// roman.cpp:17-85
+__device__ __forceinline__ double pairwise_roman(const RbDevParams& P, const Rec& i, const Rec& j) {
+  const rb_invariant_params& p = P.inv;
+  const double dax = i.ax - j.ax, day = i.ay - j.ay, daz = i.az - j.az;
+  const double dbx = i.bx - j.bx, dby = i.by - j.by, dbz = i.bz - j.bz;
+  const double l1 = norm3(dax, day, daz);
+  const double l2 = norm3(dbx, dby, dbz);
+  if (p.mindist > 0 && (l1 < p.mindist || l2 < p.mindist)) return 0.0;
+
+  double epsilon = p.epsilon, sigma = p.sigma;
+  if (p.drift_aware) {
+    const double e2 = p.epsilon * p.drift_scale * 0.5 * (l1 + l2);
+    epsilon = (p.epsilon < e2) ? e2 : p.epsilon;  // std::max
+    if (p.drift_scale_sigma) {
+      const double s2 = p.sigma * p.drift_scale * 0.5 * (l1 + l2);
+      sigma = (p.sigma < s2) ? s2 : p.sigma;
+    }
+  }
+
+  if (p.gravity_guided) {
+    const double xy1 = sqrt(dax * dax + day * day);
+    const double xy2 = sqrt(dbx * dbx + dby * dby);
+    const double z1 = daz, z2 = dbz;
+    const double c_xy = fabs(xy1 - xy2);
+    const double c_z = fabs(z1 - z2);
+    double sigma_xy = sigma, sigma_z = sigma, eps_xy = epsilon, eps_z = epsilon;
+    if (p.gravity_unc_ang_rad > 0.0) {
+      const double xym = 0.5 * (xy1 + xy2);
+      const double zm = 0.5 * (fabs(z1) + fabs(z2));
+      const double dxy = fabs(xym * P.cos_unc - xym);
+      const double dz = fabs(zm * P.sin_unc);
+      sigma_xy += dxy;
+      sigma_z += dz;
+      eps_xy += dxy;
+      eps_z += dz;
+    }
+    if (c_xy > kSqrtTwoThirds * eps_xy || c_z > kSqrtOneThird * eps_z) return 0.0;
+    return exp(-0.5 * (c_xy * c_xy / (2.0 / 3.0 * sigma_xy * sigma_xy) +
+                       c_z * c_z / (sigma_z * sigma_z / 3.0)));
+  } else {
+    const double c = fabs(l1 - l2);
+    if (c > epsilon) return 0.0;
+    return exp(-0.5 * c * c / (sigma * sigma));
+  }
+}
+
+// euclidean_distance.cpp:13-31 (strict c < epsilon)
+__device__ __forceinline__ double pairwise_euclid(const RbDevParams& P, const Rec& i, const Rec& j) {
+  const rb_invariant_params& p = P.inv;
+  const double l1 = norm3(i.ax - j.ax, i.ay - j.ay, i.az - j.az);
+  const double l2 = norm3(i.bx - j.bx, i.by - j.by, i.bz - j.bz);
+  if (p.mindist > 0 && (l1 < p.mindist || l2 < p.mindist)) return 0.0;
+  const double c = fabs(l1 - l2);
+  return (c < p.epsilon) ? exp(-0.5 * c * c / (p.sigma * p.sigma)) : 0.0;
+}
+
+// roman.cpp:87-114
+__device__ __forceinline__ double fusion(const RbDevParams& P, double pair_ij, double si, double sj) {
+  const rb_invariant_params& p = P.inv;
+  if (p.ratio_feature_dim > 0 || p.cos_feature_dim > 0) {
+    switch (p.fusion_method) {
+      case 0: {
+        const double dsp = pow(pair_ij, p.distance_weight);
+        return pow(dsp * si * sj, 1.0 / (p.distance_weight + 2.0));
+      }
+      case 1:
+        return (p.distance_weight * pair_ij + si + sj) / (p.distance_weight + 2.0);
+      case 2:
+        return pair_ij * si * sj;
+      default:
+        return 0.0;
+    }
+  }
+  return pair_ij;
+}
+
+// One entry M(i,j) with i < j in association order (clipper.cpp:96-127 / :40-64).
+__device__ __forceinline__ double pair_score(const RbDevParams& P, const Rec& i, const Rec& j) {
+  if (i.i1 < 0 || j.i1 < 0) return 0.0;                  // padding
+  if (i.i1 == j.i1 || i.i2 == j.i2) return 0.0;          // distinctness constraint
+  double scr;
+  if (P.inv.kind == RB_INVARIANT_ROMAN) {
+    if (i.s < P.affinityeps || j.s < P.affinityeps) return 0.0;
+    const double pw = pairwise_roman(P, i, j);
+    scr = fusion(P, pw, i.s, j.s);
+  } else {
+    scr = pairwise_euclid(P, i, j);
+  }
+  return (scr > P.affinityeps) ? scr : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1a: one warp per association — gathers the two object centres and evaluates
+// ROMAN::single_similarity (roman.cpp:116-164); descriptor dot products are warp-strided
+// fp64 sums reduced with a fixed xor tree.
+__global__ void __launch_bounds__(256) rb_prep_kernel(const RbProblem* __restrict__ probs, RbAssocSoA rec,
+                                                      const double* __restrict__ D1, const double* __restrict__ D2,
+                                                      const int32_t* __restrict__ A, RbDevParams P) {
+  const RbProblem pr = probs[blockIdx.y];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int mp = pr.nb * RB_TILE;
+  const rb_invariant_params& p = P.inv;
+  for (int k = blockIdx.x * 8 + warp; k < mp; k += gridDim.x * 8) {
+    const int64_t o = pr.off_pad + k;
+    if (k >= pr.m) {
+      if (lane == 0) {
+        rec.ax[o] = rec.ay[o] = rec.az[o] = rec.bx[o] = rec.by[o] = rec.bz[o] = 0.0;
+        rec.single[o] = 0.0;
+        rec.i1[o] = -1;
+        rec.i2[o] = -1;
+      }
+      continue;
+    }
+    int i1, i2;
+    if (pr.all_to_all) {  // utils::createAllToAll, utils.h:61-71
+      i1 = k / pr.n2;
+      i2 = k - i1 * pr.n2;
+    } else {
+      i1 = A[2 * (pr.off_assoc + k)];
+      i2 = A[2 * (pr.off_assoc + k) + 1];
+    }
+    const double* a = D1 + (pr.off_obj1 + i1) * (int64_t)pr.d;
+    const double* b = D2 + (pr.off_obj2 + i2) * (int64_t)pr.d;
+
+    double single = 1.0;
+    if (p.kind == RB_INVARIANT_ROMAN && (p.cos_feature_dim > 0 || p.ratio_feature_dim > 0)) {
+      bool zero = false;
+      double cos_scaled = 0.0, ratio_score = 0.0;
+      if (p.cos_feature_dim > 0) {
+        const double* fa = a + p.point_dim + p.ratio_feature_dim;
+        const double* fb = b + p.point_dim + p.ratio_feature_dim;
+        double dot = 0.0, na = 0.0, nb = 0.0;
+        for (int t = lane; t < p.cos_feature_dim; t += 32) {
+          const double x = fa[t], y = fb[t];
+          dot += x * y;
+          na += x * x;
+          nb += y * y;
+        }
+        dot = rb_warp_sum(dot);
+        na = rb_warp_sum(na);
+        nb = rb_warp_sum(nb);
+        const double c = dot / (sqrt(na) * sqrt(nb));
+        if (c >= p.cosine_max) cos_scaled = 1.0;
+        else if (c <= p.cosine_min) zero = true;
+        else cos_scaled = (c - p.cosine_min) / (p.cosine_max - p.cosine_min);
+      }
+      if (!zero && p.ratio_feature_dim > 0) {
+        double prod = 1.0;
+        bool below = false;
+        for (int t = 0; t < p.ratio_feature_dim; ++t) {
+          const double x = a[p.point_dim + t], y = b[p.point_dim + t];
+          const double r = x < y ? x / y : y / x;
+          if (r < p.ratio_epsilon[t]) below = true;
+          prod *= r;
+        }
+        if (below) zero = true;
+        else ratio_score = pow(prod, 1.0 / p.ratio_feature_dim);
+      }
+      if (zero) single = 0.0;
+      else if (p.ratio_feature_dim == 0) single = cos_scaled;
+      else if (p.cos_feature_dim == 0) single = ratio_score;
+      else
+        single = pow(pow(ratio_score, p.ratio_weight) * pow(cos_scaled, p.cosine_weight),
+                     1.0 / (p.ratio_weight + p.cosine_weight));
+    }
+    if (lane == 0) {
+      const int pd = (p.kind == RB_INVARIANT_ROMAN) ? p.point_dim : (pr.d < 3 ? pr.d : 3);
+      rec.ax[o] = a[0];
+      rec.ay[o] = pd > 1 ? a[1] : 0.0;
+      rec.az[o] = pd > 2 ? a[2] : 0.0;
+      rec.bx[o] = b[0];
+      rec.by[o] = pd > 1 ? b[1] : 0.0;
+      rec.bz[o] = pd > 2 ? b[2] : 0.0;
+      rec.single[o] = single;
+      rec.i1[o] = i1;
+      rec.i2[o] = i2;
+    }
+  }
+}
+
+__device__ __forceinline__ Rec load_rec(const RbAssocSoA& rec, int64_t o) {
+  Rec r;
+  r.ax = rec.ax[o]; r.ay = rec.ay[o]; r.az = rec.az[o];
+  r.bx = rec.bx[o]; r.by = rec.by[o]; r.bz = rec.bz[o];
+  r.s = rec.single[o];
+  r.i1 = rec.i1[o]; r.i2 = rec.i2[o];
+  return r;
+}
+
+// tile q of a problem with nb tile-rows -> (I, J), I <= J
+__device__ __forceinline__ void tile_coords(int64_t q, int nb, int& I, int& J) {
+  const double t = 2.0 * nb + 1.0;
+  int i = (int)floor((t - sqrt(t * t - 8.0 * (double)q)) * 0.5);
+  if (i < 0) i = 0;
+  if (i > nb - 1) i = nb - 1;
+  while (i > 0 && rb_tile_index(i, i, nb) > q) --i;
+  while (i + 1 < nb && rb_tile_index(i + 1, i + 1, nb) <= q) ++i;
+  I = i;
+  J = i + (int)(q - rb_tile_index(i, i, nb));
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: one warp per 32x32 tile, lane = tile column; 32 coalesced 256-byte row stores per tile.
+// Work list = all stored tiles of all problems (flat), grid-strided by a persistent grid.
+__global__ void __launch_bounds__(256) rb_affinity_kernel(const RbProblem* __restrict__ probs, int B,
+                                                          const int64_t* __restrict__ tile_prefix,
+                                                          int64_t total_tiles, RbAssocSoA rec,
+                                                          double* __restrict__ Mp, RbDevParams P) {
+  __shared__ Rec s_row[8][RB_TILE];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t t = (int64_t)blockIdx.x * 8 + warp; t < total_tiles; t += (int64_t)gridDim.x * 8) {
+    int lo = 0, hi = B;  // largest b with tile_prefix[b] <= t
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (tile_prefix[mid] <= t) lo = mid; else hi = mid;
+    }
+    const RbProblem pr = probs[lo];
+    const int64_t q = t - tile_prefix[lo];
+    int I, J;
+    tile_coords(q, pr.nb, I, J);
+    const Rec col = load_rec(rec, pr.off_pad + (int64_t)J * RB_TILE + lane);
+    __syncwarp();
+    s_row[warp][lane] = load_rec(rec, pr.off_pad + (int64_t)I * RB_TILE + lane);
+    __syncwarp();
+    double* out = Mp + (pr.off_tile + q) * RB_TILE_ELEMS;
+    const bool diag = (I == J);
+#pragma unroll 4
+    for (int r = 0; r < RB_TILE; ++r) {
+      const Rec row = s_row[warp][r];
+      double v;
+      if (!diag || r < lane) v = pair_score(P, row, col);       // i = row index < j = column index
+      else if (r > lane) v = pair_score(P, col, row);           // mirrored entry of the diagonal tile
+      else v = 0.0;                                             // identity is implicit (clipper.cpp:129-130)
+      out[r * RB_TILE + lane] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dense <-> packed conversions (clipper.cpp:202-229).
+__global__ void rb_unpack_kernel(RbProblem pr, const double* __restrict__ Mp, double* __restrict__ Mout,
+                                 double* __restrict__ Cout) {
+  const int m = pr.m;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < (int64_t)m * m;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / m), j = (int)(e - (int64_t)i * m);
+    double mv, cv;
+    if (i == j) {
+      mv = 1.0;
+      cv = 1.0;
+    } else {
+      const int a = i < j ? i : j, b = i < j ? j : i;
+      const int I = a / RB_TILE, J = b / RB_TILE;
+      const double v = Mp[(pr.off_tile + rb_tile_index(I, J, pr.nb)) * RB_TILE_ELEMS + (a % RB_TILE) * RB_TILE + (b % RB_TILE)];
+      cv = (__double_as_longlong(v) != 0ll) ? 1.0 : 0.0;
+      mv = (cv != 0.0) ? fabs(v) : 0.0;  // -0.0 (constraint-only entry) reads back as 0
+    }
+    if (Mout) Mout[e] = mv;
+    if (Cout) Cout[e] = cv;
+  }
+}
+
+__global__ void rb_pack_kernel(RbProblem pr, const double* __restrict__ Min, const double* __restrict__ Cin,
+                               double* __restrict__ Mp, int* __restrict__ bad) {
+  const int m = pr.m;
+  const int64_t total = pr.n_tiles * RB_TILE_ELEMS;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t q = e / RB_TILE_ELEMS;
+    const int w = (int)(e - q * RB_TILE_ELEMS);
+    int I, J;
+    tile_coords(q, pr.nb, I, J);
+    const int i = I * RB_TILE + w / RB_TILE, j = J * RB_TILE + w % RB_TILE;
+    double v = 0.0;
+    if (i < m && j < m && i != j) {
+      const int a = i < j ? i : j, b = i < j ? j : i;  // strict upper triangle of the inputs
+      const double mv = Min[(int64_t)a * m + b];
+      const double cv = Cin ? Cin[(int64_t)a * m + b] : (mv != 0.0 ? 1.0 : 0.0);
+      if (mv != 0.0) {
+        v = mv;
+        if (cv == 0.0) *bad = 1;
+      } else if (cv != 0.0) {
+        v = -0.0;
+      }
+    }
+    Mp[pr.off_tile * RB_TILE_ELEMS + e] = v;
+  }
+}
+
+}  // namespace
+
+cudaError_t rb_launch_prep(const RbProblem* probs, int B, int max_mp, const RbAssocSoA& rec, const double* D1,
+                           const double* D2, const int32_t* A, const RbDevParams& P, cudaStream_t st) {
+  if (B == 0 || max_mp == 0) return cudaSuccess;
+  dim3 grid((max_mp + 7) / 8, B);
+  if (grid.x > 512) grid.x = 512;
+  rb_prep_kernel<<<grid, 256, 0, st>>>(probs, rec, D1, D2, A, P);
+  return cudaGetLastError();
+}
+
+cudaError_t rb_launch_affinity(const RbProblem* probs, int B, const int64_t* tile_prefix, int64_t total_tiles,
+                               const RbAssocSoA& rec, double* Mp, const RbDevParams& P, int sm_count,
+                               cudaStream_t st) {
+  if (total_tiles == 0) return cudaSuccess;
+  int64_t want = (total_tiles + 7) / 8;
+  const int64_t cap = (int64_t)sm_count * 8;  // 8 CTAs of 256 threads per SM, persistent
+  const int grid = (int)(want < cap ? want : cap);
+  rb_affinity_kernel<<<grid, 256, 0, st>>>(probs, B, tile_prefix, total_tiles, rec, Mp, P);
+  return cudaGetLastError();
+}
+
+cudaError_t rb_launch_unpack(const RbProblem& pr, const double* Mp, double* Mout, double* Cout, cudaStream_t st) {
+  if (pr.m == 0) return cudaSuccess;
+  const int64_t n = (int64_t)pr.m * pr.m;
+  const int grid = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  rb_unpack_kernel<<<grid, 256, 0, st>>>(pr, Mp, Mout, Cout);
+  return cudaGetLastError();
+}
+
+cudaError_t rb_launch_pack(const RbProblem& pr, const double* Min, const double* Cin, double* Mp, int* bad,
+                           cudaStream_t st) {
+  if (pr.m == 0) return cudaSuccess;
+  const int64_t n = pr.n_tiles * RB_TILE_ELEMS;
+  const int grid = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  rb_pack_kernel<<<grid, 256, 0, st>>>(pr, Min, Cin, Mp, bad);
+  return cudaGetLastError();
+}

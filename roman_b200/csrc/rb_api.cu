@@ -1,0 +1,472 @@
+// rb_api.cu — handle, batch planning and the extern "C" entry points of include/roman_b200.h.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "rb_kernels.cuh"
+
+#define RB_VERSION_STR "roman_b200 0.1.0 (sm_100a)"
+
+struct rb_handle {
+  int device = 0;
+  int sm_count = 0;
+  std::string err;
+  rb_invariant_params inv;
+  rb_solver_params sol;
+
+  // plan (host copies)
+  bool planned = false;
+  int32_t B = 0, d = 0;
+  bool all_to_all = true;
+  std::vector<RbProblem> probs;
+  std::vector<int64_t> tile_prefix;  // B+1
+  int64_t total_assoc = 0, total_pad = 0, total_tiles = 0, total_obj1 = 0, total_obj2 = 0;
+  int32_t max_mp = 0;
+
+  // device scratch
+  RbProblem* d_probs = nullptr; size_t cap_probs = 0;
+  int64_t* d_tile_prefix = nullptr; size_t cap_prefix = 0;
+  double* d_M = nullptr; size_t cap_M = 0;            // packed tiles
+  double* d_pad_f64 = nullptr; size_t cap_pad = 0;    // 9 padded double arrays (7 record + u + g)
+  int32_t* d_pad_i32 = nullptr;                       // 2 padded int arrays
+  int32_t* d_counter = nullptr;
+  int* d_bad = nullptr;
+  // internal outputs used when the caller passes NULL
+  int32_t* d_nodes = nullptr; int32_t* d_sel = nullptr; size_t cap_assoc = 0;
+  int32_t* d_nsel = nullptr; double* d_score = nullptr; int32_t* d_ifinal = nullptr; int32_t* d_npass = nullptr;
+  int32_t* d_status = nullptr; double* d_T = nullptr; size_t cap_B = 0;
+  // staging for the host entry point
+  double* s_D1 = nullptr; double* s_D2 = nullptr; size_t cap_sD1 = 0, cap_sD2 = 0;
+  int32_t* s_A = nullptr; double* s_u0 = nullptr; size_t cap_sA = 0, cap_su0 = 0;
+  cudaStream_t own_stream = nullptr;
+
+  bool affinity_done = false;
+  bool profiling = false;
+  // e0 prep start, e1 prep end = affinity start, e2 affinity end, e3/e4 solve, e5/e6 arun
+  cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool ev_valid[7] = {false, false, false, false, false, false, false};
+};
+
+namespace {
+
+int fail(rb_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+int cuda_fail(rb_handle* h, cudaError_t e, const char* what) {
+  char buf[256];
+  snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+  return fail(h, RB_ERR_CUDA, buf);
+}
+#define RB_CUDA(h, call)                                   \
+  do {                                                     \
+    cudaError_t _e = (call);                               \
+    if (_e != cudaSuccess) return cuda_fail(h, _e, #call); \
+  } while (0)
+
+template <typename T>
+int ensure(rb_handle* h, T** p, size_t* cap, size_t need) {
+  if (need <= *cap && *p) return 0;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  size_t n = need ? need : 1;
+  cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+  if (e != cudaSuccess) return cuda_fail(h, e, "cudaMalloc");
+  *cap = n;
+  return 0;
+}
+
+RbAssocSoA soa_of(rb_handle* h) {
+  RbAssocSoA r;
+  const size_t n = (size_t)h->total_pad;
+  double* f = h->d_pad_f64;
+  r.ax = f; r.ay = f + n; r.az = f + 2 * n; r.bx = f + 3 * n; r.by = f + 4 * n; r.bz = f + 5 * n;
+  r.single = f + 6 * n;
+  r.i1 = h->d_pad_i32;
+  r.i2 = h->d_pad_i32 + n;
+  return r;
+}
+double* u_work(rb_handle* h) { return h->d_pad_f64 + 7 * (size_t)h->total_pad; }
+double* g_work(rb_handle* h) { return h->d_pad_f64 + 8 * (size_t)h->total_pad; }
+
+RbDevParams dev_params(const rb_handle* h) {
+  RbDevParams P;
+  P.inv = h->inv;
+  P.cos_unc = cos(h->inv.gravity_unc_ang_rad);  // roman.h:57-58
+  P.sin_unc = sin(h->inv.gravity_unc_ang_rad);
+  P.affinityeps = h->sol.affinityeps;
+  return P;
+}
+
+void record(rb_handle* h, int i, cudaStream_t st) {
+  if (!h->profiling) return;
+  if (!h->ev[i]) cudaEventCreate(&h->ev[i]);
+  cudaEventRecord(h->ev[i], st);
+  h->ev_valid[i] = true;
+}
+
+}  // namespace
+
+extern "C" {
+
+void rb_default_invariant_params(rb_invariant_params* p) {
+  memset(p, 0, sizeof *p);
+  p->kind = RB_INVARIANT_ROMAN;
+  p->point_dim = 3;
+  p->fusion_method = 0;
+  p->sigma = 0.01;
+  p->epsilon = 0.06;
+  p->mindist = 0.0;
+  p->distance_weight = p->ratio_weight = p->cosine_weight = 1.0;
+  p->cosine_min = 0.85;
+  p->cosine_max = 0.95;
+  p->drift_scale = 0.1;
+}
+
+void rb_default_solver_params(rb_solver_params* p) {
+  p->tol_u = 1e-8; p->tol_F = 1e-9; p->tol_Fop = 1e-10;
+  p->maxiniters = 200; p->maxoliters = 1000;
+  p->beta = 0.25; p->maxlsiters = 99;
+  p->eps = 1e-9; p->affinityeps = 1e-4;
+  p->rescale_u0 = 1; p->rounding = 2;
+}
+
+const char* rb_version(void) { return RB_VERSION_STR; }
+
+int rb_create(rb_handle** out, int device) {
+  if (!out) return RB_ERR_ARG;
+  *out = nullptr;
+  rb_handle* h = new rb_handle();
+  h->device = device;
+  rb_default_invariant_params(&h->inv);
+  rb_default_solver_params(&h->sol);
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { delete h; return RB_ERR_CUDA; }
+  int sm = 0;
+  e = cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
+  if (e != cudaSuccess) { delete h; return RB_ERR_CUDA; }
+  h->sm_count = sm;
+  e = rb_solver_prepare(device);
+  if (e != cudaSuccess) { delete h; return RB_ERR_CUDA; }
+  if (cudaMalloc((void**)&h->d_counter, sizeof(int32_t)) != cudaSuccess ||
+      cudaMalloc((void**)&h->d_bad, sizeof(int)) != cudaSuccess) {
+    delete h;
+    return RB_ERR_ALLOC;
+  }
+  *out = h;
+  return RB_OK;
+}
+
+int rb_destroy(rb_handle* h) {
+  if (!h) return RB_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_probs); cudaFree(h->d_tile_prefix); cudaFree(h->d_M); cudaFree(h->d_pad_f64);
+  cudaFree(h->d_pad_i32); cudaFree(h->d_counter); cudaFree(h->d_bad); cudaFree(h->d_nodes); cudaFree(h->d_sel);
+  cudaFree(h->d_nsel); cudaFree(h->d_score); cudaFree(h->d_ifinal); cudaFree(h->d_npass);
+  cudaFree(h->d_status); cudaFree(h->d_T);
+  cudaFree(h->s_D1); cudaFree(h->s_D2); cudaFree(h->s_A); cudaFree(h->s_u0);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return RB_OK;
+}
+
+const char* rb_last_error(const rb_handle* h) { return h ? h->err.c_str() : "null handle"; }
+int rb_device_sm_count(const rb_handle* h) { return h ? h->sm_count : 0; }
+
+int rb_set_invariant_params(rb_handle* h, const rb_invariant_params* p) {
+  if (!h || !p) return RB_ERR_ARG;
+  if (p->kind != RB_INVARIANT_ROMAN && p->kind != RB_INVARIANT_EUCLIDEAN) return fail(h, RB_ERR_ARG, "unknown invariant kind");
+  if (p->kind == RB_INVARIANT_ROMAN) {
+    if (p->point_dim != 2 && p->point_dim != 3) return fail(h, RB_ERR_ARG, "point_dim must be 2 or 3");
+    if (p->gravity_guided && p->point_dim != 3) return fail(h, RB_ERR_ARG, "gravity_guided requires point_dim == 3");
+    if (p->ratio_feature_dim < 0 || p->ratio_feature_dim > RB_MAX_RATIO_FEATURES)
+      return fail(h, RB_ERR_ARG, "ratio_feature_dim out of range");
+    if (p->cos_feature_dim < 0) return fail(h, RB_ERR_ARG, "cos_feature_dim < 0");
+    if (p->fusion_method < 0 || p->fusion_method > 2) return fail(h, RB_ERR_ARG, "unknown fusion_method");
+  }
+  h->inv = *p;
+  return RB_OK;
+}
+
+int rb_set_solver_params(rb_handle* h, const rb_solver_params* p) {
+  if (!h || !p) return RB_ERR_ARG;
+  if (p->rounding == 1) return fail(h, RB_ERR_ARG, "Rounding::DSD (exact densest subgraph) is not implemented on this path");
+  if (p->rounding != 0 && p->rounding != 2) return fail(h, RB_ERR_ARG, "unknown rounding");
+  h->sol = *p;
+  return RB_OK;
+}
+
+int rb_set_profiling(rb_handle* h, int32_t on) {
+  if (!h) return RB_ERR_ARG;
+  h->profiling = on != 0;
+  return RB_OK;
+}
+
+int rb_get_stage_ms(rb_handle* h, float ms[4]) {
+  if (!h || !ms) return RB_ERR_ARG;
+  static const int beg[4] = {0, 1, 3, 5}, end[4] = {1, 2, 4, 6};
+  for (int i = 0; i < 4; ++i) {
+    ms[i] = 0.f;
+    if (h->ev_valid[beg[i]] && h->ev_valid[end[i]]) {
+      RB_CUDA(h, cudaEventSynchronize(h->ev[end[i]]));
+      RB_CUDA(h, cudaEventElapsedTime(&ms[i], h->ev[beg[i]], h->ev[end[i]]));
+    }
+  }
+  return RB_OK;
+}
+
+int rb_plan(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const int32_t* n2, const int32_t* m) {
+  if (!h) return RB_ERR_ARG;
+  if (B < 0 || d < 1 || (B > 0 && (!n1 || !n2))) return fail(h, RB_ERR_ARG, "rb_plan: bad arguments");
+  RB_CUDA(h, cudaSetDevice(h->device));
+  h->planned = false;
+  h->affinity_done = false;
+  h->probs.assign((size_t)B, RbProblem());
+  h->tile_prefix.assign((size_t)B + 1, 0);
+  int64_t oa = 0, op = 0, ot = 0, o1 = 0, o2 = 0;
+  int32_t max_mp = 0;
+  for (int b = 0; b < B; ++b) {
+    if (n1[b] < 0 || n2[b] < 0) return fail(h, RB_ERR_ARG, "rb_plan: negative object count");
+    const int64_t mm = m ? (int64_t)m[b] : (int64_t)n1[b] * n2[b];
+    if (mm < 0 || mm > (int64_t)1 << 24) return fail(h, RB_ERR_ARG, "rb_plan: association count out of range");
+    RbProblem& p = h->probs[(size_t)b];
+    p.n1 = n1[b]; p.n2 = n2[b]; p.m = (int32_t)mm; p.nb = (int32_t)((mm + RB_TILE - 1) / RB_TILE);
+    p.d = d; p.all_to_all = m ? 0 : 1;
+    p.off_obj1 = o1; p.off_obj2 = o2; p.off_assoc = oa; p.off_pad = op; p.off_tile = ot;
+    p.n_tiles = (int64_t)p.nb * (p.nb + 1) / 2;
+    h->tile_prefix[(size_t)b] = ot;
+    o1 += n1[b]; o2 += n2[b]; oa += mm; op += (int64_t)p.nb * RB_TILE; ot += p.n_tiles;
+    if (p.nb * RB_TILE > max_mp) max_mp = p.nb * RB_TILE;
+  }
+  h->tile_prefix[(size_t)B] = ot;
+  const size_t smem = rb_solver_smem_bytes(max_mp, 2);
+  int optin = 0;
+  RB_CUDA(h, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  if (smem > (size_t)optin) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "rb_plan: m (padded %d) needs %zu B of shared memory in the solver, device offers %d", max_mp, smem, optin);
+    return fail(h, RB_ERR_TOO_LARGE, buf);
+  }
+  h->B = B; h->d = d; h->all_to_all = (m == nullptr);
+  h->total_assoc = oa; h->total_pad = op; h->total_tiles = ot; h->total_obj1 = o1; h->total_obj2 = o2;
+  h->max_mp = max_mp;
+
+  int rc;
+  if ((rc = ensure(h, &h->d_probs, &h->cap_probs, (size_t)B))) return rc;
+  if ((rc = ensure(h, &h->d_tile_prefix, &h->cap_prefix, (size_t)B + 1))) return rc;
+  if ((rc = ensure(h, &h->d_M, &h->cap_M, (size_t)ot * RB_TILE_ELEMS))) return rc;
+  {
+    const size_t need = (size_t)op;
+    if (need > h->cap_pad || !h->d_pad_f64) {
+      if (h->d_pad_f64) cudaFree(h->d_pad_f64);
+      if (h->d_pad_i32) cudaFree(h->d_pad_i32);
+      h->d_pad_f64 = nullptr; h->d_pad_i32 = nullptr; h->cap_pad = 0;
+      const size_t n = need ? need : 1;
+      RB_CUDA(h, cudaMalloc((void**)&h->d_pad_f64, 9 * n * sizeof(double)));
+      RB_CUDA(h, cudaMalloc((void**)&h->d_pad_i32, 2 * n * sizeof(int32_t)));
+      h->cap_pad = n;
+    }
+  }
+  {
+    const size_t need = (size_t)oa;
+    if (need > h->cap_assoc || !h->d_nodes) {
+      if (h->d_nodes) cudaFree(h->d_nodes);
+      if (h->d_sel) cudaFree(h->d_sel);
+      h->d_nodes = nullptr; h->d_sel = nullptr; h->cap_assoc = 0;
+      const size_t n = need ? need : 1;
+      RB_CUDA(h, cudaMalloc((void**)&h->d_nodes, n * sizeof(int32_t)));
+      RB_CUDA(h, cudaMalloc((void**)&h->d_sel, 2 * n * sizeof(int32_t)));
+      h->cap_assoc = n;
+    }
+  }
+  if ((size_t)B > h->cap_B || !h->d_nsel) {
+    cudaFree(h->d_nsel); cudaFree(h->d_score); cudaFree(h->d_ifinal); cudaFree(h->d_npass); cudaFree(h->d_status); cudaFree(h->d_T);
+    h->d_nsel = h->d_ifinal = h->d_npass = h->d_status = nullptr; h->d_score = h->d_T = nullptr; h->cap_B = 0;
+    const size_t n = B ? (size_t)B : 1;
+    RB_CUDA(h, cudaMalloc((void**)&h->d_nsel, n * sizeof(int32_t)));
+    RB_CUDA(h, cudaMalloc((void**)&h->d_score, n * sizeof(double)));
+    RB_CUDA(h, cudaMalloc((void**)&h->d_ifinal, n * sizeof(int32_t)));
+    RB_CUDA(h, cudaMalloc((void**)&h->d_npass, n * sizeof(int32_t)));
+    RB_CUDA(h, cudaMalloc((void**)&h->d_status, n * sizeof(int32_t)));
+    RB_CUDA(h, cudaMalloc((void**)&h->d_T, n * 16 * sizeof(double)));
+    h->cap_B = n;
+  }
+  // Descriptor upload is synchronous on the legacy stream: plan is not part of any timed region.
+  if (B > 0) {
+    RB_CUDA(h, cudaMemcpy(h->d_probs, h->probs.data(), (size_t)B * sizeof(RbProblem), cudaMemcpyHostToDevice));
+  }
+  RB_CUDA(h, cudaMemcpy(h->d_tile_prefix, h->tile_prefix.data(), ((size_t)B + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+  RB_CUDA(h, cudaDeviceSynchronize());
+  h->planned = true;
+  return RB_OK;
+}
+
+int64_t rb_assoc_offset(const rb_handle* h, int32_t b) {
+  if (!h || !h->planned || b < 0 || b > h->B) return -1;
+  return b == h->B ? h->total_assoc : h->probs[(size_t)b].off_assoc;
+}
+int64_t rb_obj1_offset(const rb_handle* h, int32_t b) {
+  if (!h || !h->planned || b < 0 || b > h->B) return -1;
+  return b == h->B ? h->total_obj1 : h->probs[(size_t)b].off_obj1;
+}
+int64_t rb_obj2_offset(const rb_handle* h, int32_t b) {
+  if (!h || !h->planned || b < 0 || b > h->B) return -1;
+  return b == h->B ? h->total_obj2 : h->probs[(size_t)b].off_obj2;
+}
+int64_t rb_packed_bytes(const rb_handle* h) {
+  if (!h || !h->planned) return -1;
+  return h->total_tiles * (int64_t)RB_TILE_BYTES;
+}
+
+int rb_affinity(rb_handle* h, const double* D1, const double* D2, const int32_t* A, void* stream) {
+  if (!h) return RB_ERR_ARG;
+  if (!h->planned) return fail(h, RB_ERR_NOPLAN, "rb_affinity before rb_plan");
+  if (h->B == 0) { h->affinity_done = true; return RB_OK; }
+  if (!D1 || !D2) return fail(h, RB_ERR_ARG, "rb_affinity: null feature table");
+  if (!h->all_to_all && !A) return fail(h, RB_ERR_ARG, "rb_affinity: plan has explicit associations but A is null");
+  const rb_invariant_params& p = h->inv;
+  if (p.kind == RB_INVARIANT_ROMAN) {
+    if (h->d < p.point_dim + p.ratio_feature_dim + p.cos_feature_dim)
+      return fail(h, RB_ERR_ARG, "rb_affinity: row length d smaller than point_dim + ratio_feature_dim + cos_feature_dim");
+  } else if (h->d > 3) {
+    return fail(h, RB_ERR_ARG, "rb_affinity: EuclideanDistance invariant supports d <= 3");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const RbDevParams P = dev_params(h);
+  const RbAssocSoA rec = soa_of(h);
+  record(h, 0, st);
+  RB_CUDA(h, rb_launch_prep(h->d_probs, h->B, h->max_mp, rec, D1, D2, h->all_to_all ? nullptr : A, P, st));
+  record(h, 1, st);
+  RB_CUDA(h, rb_launch_affinity(h->d_probs, h->B, h->d_tile_prefix, h->total_tiles, rec, h->d_M, P, h->sm_count, st));
+  record(h, 2, st);
+  h->affinity_done = true;
+  return RB_OK;
+}
+
+int rb_solve(rb_handle* h, const double* u0, int32_t* nodes, int32_t* sel, int32_t* n_nodes, double* u,
+             double* score, int32_t* ifinal, int32_t* n_passes, void* stream) {
+  if (!h) return RB_ERR_ARG;
+  if (!h->planned) return fail(h, RB_ERR_NOPLAN, "rb_solve before rb_plan");
+  if (!h->affinity_done) return fail(h, RB_ERR_NOPLAN, "rb_solve before rb_affinity / rb_set_dense");
+  if (h->B == 0) return RB_OK;
+  if (!u0 && h->total_assoc > 0) return fail(h, RB_ERR_ARG, "rb_solve: u0 is required");
+  cudaStream_t st = (cudaStream_t)stream;
+  RbSolveArgs a;
+  a.probs = h->d_probs; a.B = h->B; a.counter = h->d_counter; a.Mp = h->d_M;
+  a.i1 = h->d_pad_i32; a.i2 = h->d_pad_i32 + (size_t)h->total_pad;
+  a.u0 = u0; a.u_work = u_work(h); a.g_work = g_work(h);
+  a.nodes = nodes ? nodes : h->d_nodes;
+  a.sel = sel ? sel : h->d_sel;
+  a.n_nodes = n_nodes ? n_nodes : h->d_nsel;
+  a.u_out = u;
+  a.score = score ? score : h->d_score;
+  a.ifinal = ifinal ? ifinal : h->d_ifinal;
+  a.n_passes = n_passes ? n_passes : h->d_npass;
+  a.sp = h->sol;
+  a.mp_max = h->max_mp;
+  RB_CUDA(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int32_t), st));
+  record(h, 3, st);
+  RB_CUDA(h, rb_launch_solver(a, h->sm_count, st));
+  record(h, 4, st);
+  return RB_OK;
+}
+
+int rb_arun(rb_handle* h, const double* D1, const double* D2, const int32_t* sel, const int32_t* n_sel, double* T,
+            int32_t* status, void* stream) {
+  if (!h) return RB_ERR_ARG;
+  if (!h->planned) return fail(h, RB_ERR_NOPLAN, "rb_arun before rb_plan");
+  if (h->B == 0) return RB_OK;
+  if (!D1 || !D2 || !sel || !n_sel) return fail(h, RB_ERR_ARG, "rb_arun: null input");
+  cudaStream_t st = (cudaStream_t)stream;
+  int pd = h->inv.kind == RB_INVARIANT_ROMAN ? h->inv.point_dim : (h->d < 3 ? h->d : 3);
+  if (pd < 2) return fail(h, RB_ERR_ARG, "rb_arun: point dimension must be 2 or 3");
+  record(h, 5, st);
+  RB_CUDA(h, rb_launch_arun(h->d_probs, h->B, pd, D1, D2, sel, n_sel, T ? T : h->d_T, status ? status : h->d_status, st));
+  record(h, 6, st);
+  return RB_OK;
+}
+
+int rb_align_batch(rb_handle* h, const double* D1, const double* D2, const int32_t* A, const double* u0,
+                   int32_t* sel, int32_t* n_sel, double* T, int32_t* status, double* score, int32_t* n_passes,
+                   void* stream) {
+  if (!h) return RB_ERR_ARG;
+  int rc = rb_affinity(h, D1, D2, A, stream);
+  if (rc) return rc;
+  int32_t* sel_p = sel ? sel : h->d_sel;
+  int32_t* nsel_p = n_sel ? n_sel : h->d_nsel;
+  rc = rb_solve(h, u0, nullptr, sel_p, nsel_p, nullptr, score, nullptr, n_passes, stream);
+  if (rc) return rc;
+  return rb_arun(h, D1, D2, sel_p, nsel_p, T, status, stream);
+}
+
+int rb_get_dense(rb_handle* h, int32_t b, double* M_out, double* C_out, void* stream) {
+  if (!h) return RB_ERR_ARG;
+  if (!h->planned || !h->affinity_done) return fail(h, RB_ERR_NOPLAN, "rb_get_dense before rb_affinity / rb_set_dense");
+  if (b < 0 || b >= h->B) return fail(h, RB_ERR_ARG, "rb_get_dense: problem index out of range");
+  RB_CUDA(h, rb_launch_unpack(h->probs[(size_t)b], h->d_M, M_out, C_out, (cudaStream_t)stream));
+  return RB_OK;
+}
+
+int rb_set_dense(rb_handle* h, int32_t b, const double* M, const double* C, void* stream) {
+  if (!h) return RB_ERR_ARG;
+  if (!h->planned) return fail(h, RB_ERR_NOPLAN, "rb_set_dense before rb_plan");
+  if (b < 0 || b >= h->B || !M) return fail(h, RB_ERR_ARG, "rb_set_dense: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const RbProblem& pr = h->probs[(size_t)b];
+  RB_CUDA(h, cudaMemsetAsync(h->d_bad, 0, sizeof(int), st));
+  // set_matrix_data carries no association table: nodes map to themselves (sel = (node, 0))
+  const size_t n = (size_t)pr.nb * RB_TILE;
+  RB_CUDA(h, cudaMemsetAsync(h->d_pad_i32 + pr.off_pad, 0, n * sizeof(int32_t), st));
+  RB_CUDA(h, cudaMemsetAsync(h->d_pad_i32 + (size_t)h->total_pad + pr.off_pad, 0, n * sizeof(int32_t), st));
+  RB_CUDA(h, rb_launch_pack(pr, M, C, h->d_M, h->d_bad, st));
+  int bad = 0;
+  RB_CUDA(h, cudaMemcpyAsync(&bad, h->d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+  RB_CUDA(h, cudaStreamSynchronize(st));
+  if (bad) return fail(h, RB_ERR_ARG, "rb_set_dense: M has a non-zero entry where C is zero (unsupported)");
+  h->affinity_done = true;
+  return RB_OK;
+}
+
+int rb_align_batch_host(rb_handle* h, const double* D1, const double* D2, const int32_t* A, const double* u0,
+                        int32_t* sel, int32_t* n_sel, double* T, int32_t* status, double* score,
+                        int32_t* n_passes) {
+  if (!h) return RB_ERR_ARG;
+  if (!h->planned) return fail(h, RB_ERR_NOPLAN, "rb_align_batch_host before rb_plan");
+  if (h->B == 0) return RB_OK;
+  RB_CUDA(h, cudaSetDevice(h->device));
+  if (!h->own_stream) RB_CUDA(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  cudaStream_t st = h->own_stream;
+  const size_t nD1 = (size_t)h->total_obj1 * h->d, nD2 = (size_t)h->total_obj2 * h->d, nA = (size_t)h->total_assoc;
+  int rc;
+  if ((rc = ensure(h, &h->s_D1, &h->cap_sD1, nD1))) return rc;
+  if ((rc = ensure(h, &h->s_D2, &h->cap_sD2, nD2))) return rc;
+  if ((rc = ensure(h, &h->s_u0, &h->cap_su0, nA))) return rc;
+  if (!h->all_to_all && (rc = ensure(h, &h->s_A, &h->cap_sA, 2 * nA))) return rc;
+  if (!D1 || !D2 || !u0) return fail(h, RB_ERR_ARG, "rb_align_batch_host: null input");
+  RB_CUDA(h, cudaMemcpyAsync(h->s_D1, D1, nD1 * sizeof(double), cudaMemcpyHostToDevice, st));
+  RB_CUDA(h, cudaMemcpyAsync(h->s_D2, D2, nD2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  RB_CUDA(h, cudaMemcpyAsync(h->s_u0, u0, nA * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (!h->all_to_all) {
+    if (!A) return fail(h, RB_ERR_ARG, "rb_align_batch_host: A required");
+    RB_CUDA(h, cudaMemcpyAsync(h->s_A, A, 2 * nA * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  }
+  rc = rb_align_batch(h, h->s_D1, h->s_D2, h->all_to_all ? nullptr : h->s_A, h->s_u0, nullptr, nullptr, nullptr,
+                      nullptr, nullptr, nullptr, st);
+  if (rc) return rc;
+  const size_t B = (size_t)h->B;
+  if (sel) RB_CUDA(h, cudaMemcpyAsync(sel, h->d_sel, 2 * nA * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (n_sel) RB_CUDA(h, cudaMemcpyAsync(n_sel, h->d_nsel, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (T) RB_CUDA(h, cudaMemcpyAsync(T, h->d_T, B * 16 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (status) RB_CUDA(h, cudaMemcpyAsync(status, h->d_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (score) RB_CUDA(h, cudaMemcpyAsync(score, h->d_score, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (n_passes) RB_CUDA(h, cudaMemcpyAsync(n_passes, h->d_npass, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  RB_CUDA(h, cudaStreamSynchronize(st));
+  return RB_OK;
+}
+
+}  // extern "C"

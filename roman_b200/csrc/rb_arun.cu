@@ -1,0 +1,169 @@
+// rb_arun.cu — K3: batched Arun / Umeyama rigid registration on the surviving inliers.
+//
+// Replaces ObjectRegistration.T_align (roman/align/object_registration.py:88-129): unit weights,
+// means, H = (P1 - mu1)^T (P2 - mu2), SVD, reflection fix, t = mu1 - R mu2.  One warp per problem;
+// sums are lane-strided with a fixed xor tree.  The 3x3 SVD is done as a Jacobi eigen-decomposition
+// of H^T H (V, sorted), U completed from H V by Gram-Schmidt and a cross product, which directly
+// yields the proper rotation U diag(1,1,det(U V^T)) V^T that numpy's "flip the last row of Vh"
+// branch (object_registration.py:123-126) produces.
+#include "rb_kernels.cuh"
+
+namespace {
+
+__device__ void jacobi_eig3(double A[9], double V[9]) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) V[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    const double off = A[1] * A[1] + A[2] * A[2] + A[5] * A[5];
+    if (off < 1e-300) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        const double apq = A[p * 3 + q];
+        if (apq == 0.0) continue;
+        const double app = A[p * 3 + p], aqq = A[q * 3 + q];
+        const double theta = (aqq - app) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 3; ++k) {
+          const double akp = A[k * 3 + p], akq = A[k * 3 + q];
+          A[k * 3 + p] = c * akp - s * akq;
+          A[k * 3 + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double apk = A[p * 3 + k], aqk = A[q * 3 + k];
+          A[p * 3 + k] = c * apk - s * aqk;
+          A[q * 3 + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double vkp = V[k * 3 + p], vkq = V[k * 3 + q];
+          V[k * 3 + p] = c * vkp - s * vkq;
+          V[k * 3 + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+}
+
+__device__ double det3(const double* R) {
+  return R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
+}
+
+// R (row-major 3x3) from H for point_dim 3
+__device__ void rotation_from_H3(const double H[9], double R[9]) {
+  double HtH[9], V[9];
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) {
+      double s = 0;
+      for (int c = 0; c < 3; ++c) s += H[c * 3 + a] * H[c * 3 + b];
+      HtH[a * 3 + b] = s;
+    }
+  jacobi_eig3(HtH, V);
+  const double ev[3] = {HtH[0], HtH[4], HtH[8]};
+  int ord[3] = {0, 1, 2};
+  for (int a = 0; a < 2; ++a)
+    for (int b = a + 1; b < 3; ++b)
+      if (ev[ord[b]] > ev[ord[a]]) { const int t = ord[a]; ord[a] = ord[b]; ord[b] = t; }
+  double Vs[9];
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 3; ++r) Vs[r * 3 + c] = V[r * 3 + ord[c]];
+  if (det3(Vs) < 0)
+    for (int r = 0; r < 3; ++r) Vs[r * 3 + 2] = -Vs[r * 3 + 2];
+  double u0[3], u1[3], u2[3];
+  for (int r = 0; r < 3; ++r) {
+    u0[r] = 0; u1[r] = 0;
+    for (int c = 0; c < 3; ++c) { u0[r] += H[r * 3 + c] * Vs[c * 3 + 0]; u1[r] += H[r * 3 + c] * Vs[c * 3 + 1]; }
+  }
+  const double n0 = sqrt(u0[0] * u0[0] + u0[1] * u0[1] + u0[2] * u0[2]);
+  if (n0 < 1e-300) {  // H == 0
+    for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    return;
+  }
+  for (int r = 0; r < 3; ++r) u0[r] /= n0;
+  const double dp = u0[0] * u1[0] + u0[1] * u1[1] + u0[2] * u1[2];
+  for (int r = 0; r < 3; ++r) u1[r] -= dp * u0[r];
+  double n1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+  if (n1 < 1e-13 * n0) {  // rank 1: any unit vector orthogonal to u0
+    const int a = fabs(u0[0]) < fabs(u0[1]) ? (fabs(u0[0]) < fabs(u0[2]) ? 0 : 2) : (fabs(u0[1]) < fabs(u0[2]) ? 1 : 2);
+    double e[3] = {0, 0, 0};
+    e[a] = 1.0;
+    const double dq = u0[a];
+    for (int r = 0; r < 3; ++r) u1[r] = e[r] - dq * u0[r];
+    n1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+  }
+  for (int r = 0; r < 3; ++r) u1[r] /= n1;
+  u2[0] = u0[1] * u1[2] - u0[2] * u1[1];
+  u2[1] = u0[2] * u1[0] - u0[0] * u1[2];
+  u2[2] = u0[0] * u1[1] - u0[1] * u1[0];
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) R[a * 3 + b] = u0[a] * Vs[b * 3 + 0] + u1[a] * Vs[b * 3 + 1] + u2[a] * Vs[b * 3 + 2];
+}
+
+__global__ void __launch_bounds__(128) rb_arun_kernel(const RbProblem* __restrict__ probs, int B, int pd,
+                                                      const double* __restrict__ D1, const double* __restrict__ D2,
+                                                      const int32_t* __restrict__ sel, const int32_t* __restrict__ n_sel,
+                                                      double* __restrict__ T, int32_t* __restrict__ status) {
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const RbProblem pr = probs[b];
+  const int k = n_sel[b];
+  double* Tb = T + (int64_t)b * 16;
+  if (pr.n1 == 0 || pr.n2 == 0 || k < pd) {  // object_registration.py:102-108
+    if (lane < 16) Tb[lane] = __longlong_as_double(0x7ff8000000000000ll);
+    if (lane == 0) status[b] = RB_PAIR_INSUFFICIENT;
+    return;
+  }
+  const int32_t* s = sel + 2 * pr.off_assoc;
+  const double* P1 = D1 + pr.off_obj1 * (int64_t)pr.d;
+  const double* P2 = D2 + pr.off_obj2 * (int64_t)pr.d;
+  double m1[3] = {0, 0, 0}, m2[3] = {0, 0, 0};
+  for (int i = lane; i < k; i += 32) {
+    const double* a = P1 + (int64_t)s[2 * i] * pr.d;
+    const double* c = P2 + (int64_t)s[2 * i + 1] * pr.d;
+    for (int t = 0; t < 3; ++t) {
+      m1[t] += (t < pd) ? a[t] : 0.0;
+      m2[t] += (t < pd) ? c[t] : 0.0;
+    }
+  }
+  for (int t = 0; t < 3; ++t) {
+    m1[t] = rb_warp_sum(m1[t]) / (double)k;
+    m2[t] = rb_warp_sum(m2[t]) / (double)k;
+  }
+  double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = lane; i < k; i += 32) {
+    const double* a = P1 + (int64_t)s[2 * i] * pr.d;
+    const double* c = P2 + (int64_t)s[2 * i + 1] * pr.d;
+    double da[3], dc[3];
+    for (int t = 0; t < 3; ++t) {
+      da[t] = (t < pd) ? a[t] - m1[t] : 0.0;
+      dc[t] = (t < pd) ? c[t] - m2[t] : 0.0;
+    }
+    for (int x = 0; x < 3; ++x)
+      for (int y = 0; y < 3; ++y) H[x * 3 + y] += da[x] * dc[y];
+  }
+  for (int e = 0; e < 9; ++e) H[e] = rb_warp_sum(H[e]);
+  if (lane == 0) {
+    double R[9];
+    if (pd == 3) {
+      rotation_from_H3(H, R);
+    } else {  // 2-D: closed-form proper rotation maximising tr(R H^T)
+      const double th = atan2(H[3] - H[1], H[0] + H[4]);
+      const double c = cos(th), sn = sin(th);
+      R[0] = c; R[1] = -sn; R[2] = 0; R[3] = sn; R[4] = c; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+    }
+    for (int a = 0; a < 3; ++a) {
+      for (int c = 0; c < 3; ++c) Tb[a * 4 + c] = R[a * 3 + c];
+      Tb[a * 4 + 3] = m1[a] - (R[a * 3 + 0] * m2[0] + R[a * 3 + 1] * m2[1] + R[a * 3 + 2] * m2[2]);
+    }
+    Tb[12] = 0; Tb[13] = 0; Tb[14] = 0; Tb[15] = 1;
+    status[b] = RB_PAIR_OK;
+  }
+}
+
+}  // namespace
+
+cudaError_t rb_launch_arun(const RbProblem* probs, int B, int point_dim, const double* D1, const double* D2,
+                           const int32_t* sel, const int32_t* n_sel, double* T, int32_t* status, cudaStream_t st) {
+  if (B == 0) return cudaSuccess;
+  rb_arun_kernel<<<(B + 3) / 4, 128, 0, st>>>(probs, B, point_dim, D1, D2, sel, n_sel, T, status);
+  return cudaGetLastError();
+}

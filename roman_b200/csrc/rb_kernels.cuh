@@ -1,0 +1,52 @@
+// rb_kernels.cuh — launch wrappers shared between the kernel translation units and rb_api.cu.
+#pragma once
+#include "rb_common.cuh"
+
+// Invariant parameters as the kernels see them (roman.h:55-60 caches cos/sin of the angle).
+struct RbDevParams {
+  rb_invariant_params inv;
+  double cos_unc, sin_unc;
+  double affinityeps;
+};
+
+// Everything the persistent solver kernel needs.
+struct RbSolveArgs {
+  const RbProblem* probs;
+  int32_t B;
+  int32_t* counter;        // dynamic problem queue (zeroed before launch)
+  const double* Mp;        // packed tiles
+  const int32_t* i1;       // association object indices (padded arrays), for `sel`
+  const int32_t* i2;
+  const double* u0;        // user layout (off_assoc)
+  double* u_work;          // padded scratch (off_pad): current iterate u
+  double* g_work;          // padded scratch: gradient at u
+  // outputs, user layout (off_assoc); rb_api substitutes handle scratch for NULL user pointers,
+  // so only u_out may be null here
+  int32_t* nodes;
+  int32_t* sel;
+  int32_t* n_nodes;
+  double* u_out;
+  double* score;
+  int32_t* ifinal;
+  int32_t* n_passes;
+  rb_solver_params sp;
+  int32_t mp_max;          // max padded m over the batch (sizes the shared-memory vectors)
+};
+
+cudaError_t rb_launch_prep(const RbProblem* probs, int B, int max_mp, const RbAssocSoA& rec, const double* D1,
+                           const double* D2, const int32_t* A, const RbDevParams& P, cudaStream_t st);
+cudaError_t rb_launch_affinity(const RbProblem* probs, int B, const int64_t* tile_prefix, int64_t total_tiles,
+                               const RbAssocSoA& rec, double* Mp, const RbDevParams& P, int sm_count,
+                               cudaStream_t st);
+cudaError_t rb_launch_unpack(const RbProblem& pr, const double* Mp, double* Mout, double* Cout, cudaStream_t st);
+cudaError_t rb_launch_pack(const RbProblem& pr, const double* Min, const double* Cin, double* Mp, int* bad,
+                           cudaStream_t st);
+
+// Returns cudaErrorInvalidValue if mp_max does not fit the shared-memory layout.
+size_t rb_solver_smem_bytes(int mp_max, int slots);
+cudaError_t rb_solver_prepare(int device);  // opt in to the large dynamic shared-memory carve-out
+cudaError_t rb_launch_solver(const RbSolveArgs& a, int sm_count, cudaStream_t st);
+
+cudaError_t rb_launch_arun(const RbProblem* probs, int B, int point_dim, const double* D1, const double* D2,
+                           const int32_t* sel, const int32_t* n_sel, double* T, int32_t* status,
+                           cudaStream_t st);

@@ -1,0 +1,505 @@
+// rb_solver.cu — K2: persistent CLIPPER dense-clique solver, one CTA per problem.
+//
+// Replaces CLIPPER::findDenseClique (clipper/src/clipper.cpp:243-394), utils::findIndicesOfkLargest
+// (clipper/src/utils.cpp:33-55) and utils::selectInlierAssociations (utils.cpp:101-108).
+//
+// Shape of the kernel
+//   - grid = min(B, #SM) CTAs of 8 warps; CTAs pull problems from an atomic queue, so every SM
+//     streams a different problem's packed affinity matrix from HBM: the working set is far
+//     larger than L2 and the kernel is HBM-bound by construction.
+//   - one "pass" = one fused evaluation of (M x, C x) for the current trial vector x:
+//     every 32x32 tile (8 KB, contiguous) of the packed upper triangle is brought into shared
+//     memory by one cp.async.bulk (TMA) and used twice — tile * x_J feeds the row sums of block
+//     I, tile^T * x_I feeds the column sums of block J — so each byte of M is read once per pass.
+//     C is never stored: C_ij = [stored word != +0.0].
+//   - each warp runs its own 2-slot TMA ring (issue by lane 0, completion on an mbarrier) over
+//     the tiles (I, J) with J mod 8 == warp, which makes warp (K mod 8) the only writer of the
+//     output block K: no atomics, fixed summation order, bit-reproducible results.
+//     Row partial sums live in registers across a tile-row and are combined once per tile-row.
+//   - all scalar control flow of the reference (line search, convergence tests, the d update)
+//     is resolved on the device from block-wide reductions with a fixed tree.
+//   - M x and C x of the accepted iterate are kept, so the d update and the new gradient need
+//     no extra pass (the reference recomputes them; the values are identical).
+#include "rb_kernels.cuh"
+
+namespace {
+
+constexpr int NW = 8;         // warps per CTA (all are consumers; each runs its own TMA ring)
+constexpr int NT = NW * 32;   // threads per CTA
+constexpr int SLOTS = 2;      // ring slots per warp (8 KB each)
+constexpr int RED_DOUBLES = 64;   // [0,32): double-buffered reduction scratch; [40]: broadcast slot
+constexpr int MISC_INTS = 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_tile(void* dst, const void* src, uint64_t* bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // order prior generic reads of dst
+  mbar_expect_tx(bar, RB_TILE_BYTES);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"((uint32_t)RB_TILE_BYTES), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// first tile column of tile-row I that belongs to warp w
+__device__ __forceinline__ int first_col(int I, int w) { return I + ((w - I) % NW + NW) % NW; }
+
+struct Smem {
+  double* x;     // trial vector (mp)
+  double* accM;  // M x (strict), then reused as int scratch in rounding
+  double* accC;  // C x (strict)
+  double* part;  // [2][NW][2][32] row partials, double buffered over tile-rows
+  double* red;   // [2][2*NW] reduction scratch, double buffered
+  uint64_t* bar; // [NW][SLOTS]
+  double* ring;  // [NW][SLOTS][1024]
+  int* misc;     // small ints / broadcast slots
+};
+
+struct Reducer {
+  double* red;
+  int flip;
+  // sum of (a, b) over the CTA, same value in every thread, fixed order; one barrier.
+  __device__ __forceinline__ void sum2(double& a, double& b) {
+    a = rb_warp_sum(a);
+    b = rb_warp_sum(b);
+    double* r = red + flip * (2 * NW);
+    if ((threadIdx.x & 31) == 0) {
+      r[threadIdx.x >> 5] = a;
+      r[NW + (threadIdx.x >> 5)] = b;
+    }
+    __syncthreads();
+    double sa = 0.0, sb = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      sa += r[w];
+      sb += r[NW + w];
+    }
+    a = sa;
+    b = sb;
+    flip ^= 1;
+  }
+  __device__ __forceinline__ double sum1(double a) {
+    double b = 0.0;
+    sum2(a, b);
+    return a;
+  }
+};
+
+// One fused pass: accM += M x, accC += C x over the packed upper triangle of one problem.
+// Preconditions: x complete, accM/accC zeroed, all threads past a __syncthreads.
+__device__ __forceinline__ void matvec_pass(const Smem& S, const double* __restrict__ tiles, int nb,
+                                            uint32_t& phase_bits) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint64_t* bar = S.bar + w * SLOTS;
+  double* ring = S.ring + (size_t)w * SLOTS * RB_TILE_ELEMS;
+
+  // prefetch iterator over this warp's tile sequence
+  int pfI = 0, pfJ = 0;
+  bool pf_ok = false;
+  for (pfI = 0; pfI < nb; ++pfI) {
+    pfJ = first_col(pfI, w);
+    if (pfJ < nb) { pf_ok = true; break; }
+  }
+  auto pf_issue = [&](int slot) {
+    if (lane == 0)
+      tma_load_tile(ring + slot * RB_TILE_ELEMS, tiles + rb_tile_index(pfI, pfJ, nb) * RB_TILE_ELEMS, bar + slot);
+    pfJ += NW;
+    while (pfJ >= nb) {
+      ++pfI;
+      if (pfI >= nb) { pf_ok = false; break; }
+      pfJ = first_col(pfI, w);
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s)
+    if (pf_ok) pf_issue(s);
+
+  int slot = 0;
+  for (int I = 0; I < nb; ++I) {
+    double rowM[RB_TILE], rowC[RB_TILE];
+#pragma unroll
+    for (int r = 0; r < RB_TILE; ++r) { rowM[r] = 0.0; rowC[r] = 0.0; }
+    const double* xI = S.x + I * RB_TILE;
+
+    for (int J = first_col(I, w); J < nb; J += NW) {
+      mbar_wait(bar + slot, (phase_bits >> slot) & 1u);
+      phase_bits ^= (1u << slot);
+      const double* buf = ring + slot * RB_TILE_ELEMS;
+      const double xJ = S.x[J * RB_TILE + lane];
+      if (J != I) {
+        double colM = 0.0, colC = 0.0;
+#pragma unroll
+        for (int r = 0; r < RB_TILE; ++r) {
+          const double v = buf[r * RB_TILE + lane];
+          const double xi = xI[r];
+          const bool nz = (__double_as_longlong(v) != 0ll);  // +0.0 <=> no edge (-0.0: constraint-only entry)
+          rowM[r] = fma(v, xJ, rowM[r]);
+          colM = fma(v, xi, colM);
+          if (nz) { rowC[r] += xJ; colC += xi; }
+        }
+        // this warp is the only writer of output block J
+        S.accM[J * RB_TILE + lane] += colM;
+        S.accC[J * RB_TILE + lane] += colC;
+      } else {
+        // diagonal tile holds both triangles: row sums only
+#pragma unroll
+        for (int r = 0; r < RB_TILE; ++r) {
+          const double v = buf[r * RB_TILE + lane];
+          const bool nz = (__double_as_longlong(v) != 0ll);
+          rowM[r] = fma(v, xJ, rowM[r]);
+          if (nz) rowC[r] += xJ;
+        }
+      }
+      __syncwarp();
+      if (pf_ok) pf_issue(slot);  // refill the slot just drained
+      slot = (slot + 1 == SLOTS) ? 0 : slot + 1;
+    }
+
+    // Lane-transpose reduction: afterwards lane r holds this warp's total for row r of block I.
+#pragma unroll
+    for (int h = 16; h >= 1; h >>= 1) {
+#pragma unroll
+      for (int i = 0; i < h; ++i) {
+        const bool up = (lane & h) != 0;
+        const double sendM = up ? rowM[i] : rowM[i + h];
+        const double keepM = up ? rowM[i + h] : rowM[i];
+        rowM[i] = keepM + __shfl_xor_sync(0xffffffffu, sendM, h);
+        const double sendC = up ? rowC[i] : rowC[i + h];
+        const double keepC = up ? rowC[i + h] : rowC[i];
+        rowC[i] = keepC + __shfl_xor_sync(0xffffffffu, sendC, h);
+      }
+    }
+    double* part = S.part + (size_t)(I & 1) * (NW * 2 * RB_TILE);
+    part[(w * 2 + 0) * RB_TILE + lane] = rowM[0];
+    part[(w * 2 + 1) * RB_TILE + lane] = rowC[0];
+    named_bar_sync(1, NT);
+    if ((I % NW) == w) {  // owner of output block I combines the 8 warps in fixed order
+      double sm = 0.0, sc = 0.0;
+#pragma unroll
+      for (int ww = 0; ww < NW; ++ww) {
+        sm += part[(ww * 2 + 0) * RB_TILE + lane];
+        sc += part[(ww * 2 + 1) * RB_TILE + lane];
+      }
+      S.accM[I * RB_TILE + lane] += sm;
+      S.accC[I * RB_TILE + lane] += sc;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Smem S;
+  {
+    const size_t mp = (size_t)A.mp_max;
+    unsigned char* p = smem_raw;
+    S.ring = (double*)p; p += (size_t)NW * SLOTS * RB_TILE_BYTES;
+    S.x = (double*)p; p += mp * 8;
+    S.accM = (double*)p; p += mp * 8;
+    S.accC = (double*)p; p += mp * 8;
+    S.part = (double*)p; p += (size_t)2 * NW * 2 * RB_TILE * 8;
+    S.red = (double*)p; p += (size_t)RED_DOUBLES * 8;
+    S.bar = (uint64_t*)p; p += (size_t)NW * SLOTS * 8;
+    S.misc = (int*)p;
+  }
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int i = 0; i < NW * SLOTS; ++i) mbar_init(S.bar + i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t phase = 0u;  // bit s = parity the next wait on ring slot s must see
+  Reducer R{S.red, 0};
+  const rb_solver_params sp = A.sp;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) S.misc[0] = atomicAdd(A.counter, 1);
+    __syncthreads();
+    const int b = S.misc[0];
+    if (b >= A.B) break;
+    const RbProblem pr = A.probs[b];
+    const int m = pr.m, nb = pr.nb, mp = nb * RB_TILE;
+    const double* tiles = A.Mp + pr.off_tile * RB_TILE_ELEMS;
+    double* u = A.u_work + pr.off_pad;
+    double* g = A.g_work + pr.off_pad;
+    const double* u0 = A.u0 + pr.off_assoc;
+    int passes = 0;
+
+    if (m == 0) {
+      if (tid == 0) {
+        A.n_nodes[b] = 0; A.score[b] = 0.0; A.ifinal[b] = 0; A.n_passes[b] = 0;
+      }
+      continue;
+    }
+
+    // ---- init (clipper.cpp:263-269): u = M u0 + u0 (optional), u /= ||u||
+    for (int i = tid; i < mp; i += NT) {
+      S.x[i] = (i < m) ? u0[i] : 0.0;
+      S.accM[i] = 0.0;
+      S.accC[i] = 0.0;
+    }
+    __syncthreads();
+    if (sp.rescale_u0) {
+      matvec_pass(S, tiles, nb, phase);
+      ++passes;
+      __syncthreads();
+    }
+    double nrm2 = 0.0;
+    for (int i = tid; i < mp; i += NT) {
+      const double v = sp.rescale_u0 ? (S.accM[i] + S.x[i]) : S.x[i];
+      S.x[i] = v;
+      nrm2 += v * v;
+    }
+    nrm2 = R.sum1(nrm2);
+    double sum_u = 0.0;
+    {
+      const double nrm = sqrt(nrm2);
+      for (int i = tid; i < mp; i += NT) {
+        const double v = (i < m) ? S.x[i] / nrm : 0.0;
+        S.x[i] = v;
+        u[i] = v;
+        sum_u += v;
+        S.accM[i] = 0.0;
+        S.accC[i] = 0.0;
+      }
+    }
+    sum_u = R.sum1(sum_u);
+    matvec_pass(S, tiles, nb, phase);  // (M u, C u) of the normalised start vector
+    ++passes;
+    __syncthreads();
+
+    // ---- initial d (clipper.cpp:271-280)
+    double d = 0.0;
+    {
+      double cnt = 0.0, s = 0.0;
+      for (int i = tid; i < m; i += NT) {
+        const double ui = S.x[i];
+        const double cbu = (sum_u - S.accC[i]) - ui;
+        if (cbu > sp.eps && ui > sp.eps) { cnt += 1.0; s += (S.accM[i] + ui) / cbu; }
+      }
+      R.sum2(cnt, s);
+      if (cnt > 0.0) d = s / cnt;
+    }
+
+    // ---- graduated projected gradient ascent (clipper.cpp:286-352)
+    double F = 0.0;
+    int i_ol;
+    for (i_ol = 0; i_ol < sp.maxoliters; ++i_ol) {
+      {  // gradF and F at (u, d) from the kept M u, C u  (clipper.cpp:290-291)
+        double f = 0.0;
+        for (int i = tid; i < m; i += NT) {
+          const double ui = S.x[i];
+          const double gi = (((1.0 + d) * ui - d * sum_u) + S.accM[i]) + S.accC[i] * d;
+          g[i] = gi;
+          f += ui * gi;
+        }
+        F = R.sum1(f);
+      }
+      for (int j_il = 0; j_il < sp.maxiniters; ++j_il) {
+        double alpha = 1.0, Fnew = 0.0, deltaF = 0.0, du2 = 0.0, sum_un = 0.0;
+        for (int k_ls = 0; k_ls < sp.maxlsiters; ++k_ls) {
+          // unew = normalize(max(u + alpha*gradF, 0))   (clipper.cpp:306-308)
+          double z = 0.0;
+          for (int i = tid; i < m; i += NT) {
+            const double t = u[i] + alpha * g[i];
+            const double r = t > 0.0 ? t : 0.0;
+            S.x[i] = r;
+            z += r * r;
+          }
+          z = R.sum1(z);
+          double su = 0.0;
+          const double nrm = sqrt(z);
+          for (int i = tid; i < mp; i += NT) {
+            double v = S.x[i];
+            if (z > 0.0 && i < m) { v = v / nrm; S.x[i] = v; }
+            su += (i < m) ? v : 0.0;
+            S.accM[i] = 0.0;
+            S.accC[i] = 0.0;
+          }
+          sum_un = R.sum1(su);
+          matvec_pass(S, tiles, nb, phase);
+          ++passes;
+          __syncthreads();
+          // gradFnew, Fnew (clipper.cpp:309-315) and, speculatively, ||unew - u||^2
+          double f = 0.0, dd = 0.0;
+          for (int i = tid; i < m; i += NT) {
+            const double xi = S.x[i];
+            const double gi = (((1.0 + d) * xi - d * sum_un) + S.accM[i]) + S.accC[i] * d;
+            f += xi * gi;
+            const double t = xi - u[i];
+            dd += t * t;
+          }
+          R.sum2(f, dd);
+          Fnew = f;
+          du2 = dd;
+          deltaF = Fnew - F;
+          if (deltaF < -sp.eps) alpha = alpha * sp.beta;
+          else break;
+        }
+        // accept (also after an exhausted line search, clipper.cpp:324-329)
+        const double deltau = sqrt(du2);
+        F = Fnew;
+        sum_u = sum_un;
+        for (int i = tid; i < m; i += NT) {
+          const double xi = S.x[i];
+          u[i] = xi;
+          g[i] = (((1.0 + d) * xi - d * sum_un) + S.accM[i]) + S.accC[i] * d;
+        }
+        if (deltau < sp.tol_u || fabs(deltaF) < sp.tol_F) break;
+      }
+      // ---- increase d (clipper.cpp:339-351), from the kept M u, C u
+      double cnt = 0.0, s = 0.0;
+      for (int i = tid; i < m; i += NT) {
+        const double ui = S.x[i];
+        const double cbu = (sum_u - S.accC[i]) - ui;
+        if (cbu > sp.eps && ui > sp.eps) { cnt += 1.0; s += fabs((S.accM[i] + ui) / cbu); }
+      }
+      R.sum2(cnt, s);
+      if (cnt > 0.0) d += s / cnt;
+      else break;
+    }
+
+    // ---- rounding (clipper.cpp:358-381) + selected associations (utils.cpp:101-108)
+    __syncthreads();
+    int32_t* nodes = A.nodes + pr.off_assoc;
+    int* rank = (int*)S.accM;  // accM is dead from here on
+    int n_sel = 0;
+    if (sp.rounding == 0) {  // NONZERO: utils::findIndicesWhereAboveThreshold(u, 0.0)
+      if (tid == 0) {
+        int n = 0;
+        for (int i = 0; i < m; ++i)
+          if (S.x[i] > 0.0) nodes[n++] = i;
+        S.misc[1] = n;
+      }
+      __syncthreads();
+      n_sel = S.misc[1];
+    } else {  // DSD_HEU: omega = round(F); k largest of u with the reference's heap semantics
+      const double Fr = round(F);  // half away from zero, like std::round
+      int k = !(Fr >= 1.0) ? 0 : (Fr > (double)m ? m : (int)Fr);
+      if (k >= 1) {
+        double npos = 0.0;
+        for (int i = tid; i < m; i += NT) npos += (S.x[i] > 0.0) ? 1.0 : 0.0;
+        npos = R.sum1(npos);
+        const bool only_pos = ((double)k <= npos);  // then no zero can be among the k largest
+        // rank_i = #{j : (x_j, j) > (x_i, i)}  == position in "descending value, larger index first"
+        for (int i = tid; i < m; i += NT) {
+          const double xi = S.x[i];
+          int rk = m;  // sentinel: not ranked
+          if (!only_pos || xi > 0.0) {
+            rk = 0;
+            for (int j = 0; j < m; ++j) {
+              const double xj = S.x[j];
+              rk += (xj > xi || (xj == xi && j > i)) ? 1 : 0;
+            }
+            if (rk == k - 1) S.red[40] = xi;  // value of the k-th largest (unique writer)
+          }
+          rank[i] = rk;
+        }
+        __syncthreads();
+        const double vstar = S.red[40];
+        double a = 0.0, bcnt = 0.0;
+        for (int i = tid; i < m; i += NT) {
+          const double xi = S.x[i];
+          a += (xi > vstar) ? 1.0 : 0.0;
+          bcnt += (xi == vstar) ? 1.0 : 0.0;
+        }
+        R.sum2(a, bcnt);
+        const int na = (int)a, nbq = (int)bcnt;
+        if (na + nbq == k) {
+          for (int i = tid; i < m; i += NT)
+            if (rank[i] < k) nodes[rank[i]] = i;
+        } else {
+          // ties at the boundary value: reproduce the heap's choice (see DESIGN.md "top-k ties")
+          for (int i = tid; i < m; i += NT)
+            if (S.x[i] > vstar) nodes[rank[i]] = i;
+          if (tid == 0) {
+            int cnt_ge = 0, g_le = 0, istar = m - 1;
+            for (int i = 0; i < m; ++i) {
+              const double xi = S.x[i];
+              if (xi >= vstar) {
+                ++cnt_ge;
+                if (xi > vstar) ++g_le;
+                if (cnt_ge == k) { istar = i; break; }
+              }
+            }
+            const int skip = na - g_le, t = k - na;
+            int pos = 0, q = 0;
+            for (int i = 0; i <= istar && q < t; ++i) {
+              if (S.x[i] == vstar) {
+                if (pos >= skip) { nodes[na + (t - 1 - q)] = i; ++q; }
+                ++pos;
+              }
+            }
+          }
+        }
+        __syncthreads();
+      }
+      n_sel = k;
+    }
+    // outputs
+    int32_t* sel = A.sel + 2 * pr.off_assoc;
+    for (int p = tid; p < n_sel; p += NT) {
+      const int nd = nodes[p];
+      sel[2 * p] = A.i1[pr.off_pad + nd];
+      sel[2 * p + 1] = A.i2[pr.off_pad + nd];
+    }
+    if (A.u_out) {
+      double* uo = A.u_out + pr.off_assoc;
+      for (int i = tid; i < m; i += NT) uo[i] = S.x[i];
+    }
+    if (tid == 0) {
+      A.n_nodes[b] = n_sel;
+      A.score[b] = F;
+      A.ifinal[b] = i_ol;
+      A.n_passes[b] = passes;
+    }
+  }
+}
+
+}  // namespace
+
+size_t rb_solver_smem_bytes(int mp_max, int /*slots*/) {
+  return (size_t)NW * SLOTS * RB_TILE_BYTES + (size_t)3 * mp_max * 8 + (size_t)2 * NW * 2 * RB_TILE * 8 +
+         (size_t)RED_DOUBLES * 8 + (size_t)NW * SLOTS * 8 + (size_t)MISC_INTS * 4;
+}
+
+static size_t g_max_optin = 0;
+
+cudaError_t rb_solver_prepare(int device) {
+  int v = 0;
+  cudaError_t e = cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  if (e != cudaSuccess) return e;
+  g_max_optin = (size_t)v;
+  return cudaFuncSetAttribute(rb_solver_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+}
+
+cudaError_t rb_launch_solver(const RbSolveArgs& a, int sm_count, cudaStream_t st) {
+  if (a.B == 0) return cudaSuccess;
+  const size_t smem = rb_solver_smem_bytes(a.mp_max, SLOTS);
+  if (g_max_optin && smem > g_max_optin) return cudaErrorInvalidValue;
+  const int grid = a.B < sm_count ? a.B : sm_count;
+  rb_solver_kernel<<<grid, NT, smem, st>>>(a);
+  return cudaGetLastError();
+}
