@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""
+bench.py — submap-pair alignments/sec on the BASELINE.json workload.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B]
+
+One "step" = one pass of the hot path (K1a + K1 + K2 + K3) over one batch of B synthetic submap
+pairs per GPU.  Workload at every N (weak scaling, B pairs per GPU): n1=40, n2=50 objects
+(m = 2000 all-to-all correspondences), method 'roman' (gravity + PCA + volume + 768-d semantics),
+SubmapAlignParams defaults — the configuration BASELINE.json's metric is quoted on.
+Printed JSON line: see the task contract; `roofline` is for the dominant kernel (K2, the
+solver's streaming pass over the packed affinity matrix), `kernels` lists K1 and K2 separately.
+
+--impl reference times the reference algorithm's CPU restatement (oracle/, kind "port": the
+reference itself needs Eigen3 and cannot be compiled in this image) on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N1, N2, SEM_DIM, METHOD = 40, 50, 768, "roman"
+M_ASSOC = N1 * N2
+WORKLOAD = "synthetic submap pairs n1=40 n2=50 (m=2000 all-to-all), method roman, D=768, SubmapAlignParams defaults"
+METRIC = "submap-pair alignments/sec at N=2000 correspondences"
+UNIT = "alignments/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_inputs(seed0, B):
+    from roman_b200 import synth
+    D1, D2, u0, _ = synth.make_batch(seed0, B, N1, N2, method=METHOD, semantics_dim=SEM_DIM)
+    return np.ascontiguousarray(D1), np.ascontiguousarray(D2), np.ascontiguousarray(u0)
+
+
+def oracle_params():
+    from oracle import clipper_np as cn
+    from roman_b200.engine import method_invariant_kwargs
+    kw = method_invariant_kwargs(METHOD, semantics_dim=SEM_DIM)
+    return cn.InvariantParams(**kw), cn.SolverParams()
+
+
+def cpu_baseline(rounds=16, threads=0, seed0=10_000):
+    """
+    Time the CPU restatement, one pair per thread on all host threads (throughput-fair mode of
+    BASELINE.md §3): `rounds` sweeps over 2*cores distinct pairs (~1 s of wall, cores x ~1 s of CPU work).
+    """
+    import oracle
+    O = oracle.COracle()
+    ip, sp = oracle_params()
+    cores = O.max_threads() if threads <= 0 else threads
+    nd = 2 * cores
+    D1, D2, u0 = make_inputs(seed0, nd)
+    O.align_batch(ip, sp, D1[:cores], D2[:cores], u0[:cores], threads=threads)  # warm the library / thread pool
+    t0 = time.perf_counter()
+    for _ in range(rounds):
+        r = O.align_batch(ip, sp, D1, D2, u0, threads=threads)
+    dt = time.perf_counter() - t0
+    n = rounds * nd
+    return {"value": n / dt, "unit": UNIT, "cores": int(r["threads"]), "kind": "port",
+            "sample": f"{n} alignments ({rounds} sweeps over {nd} distinct pairs of the same workload), one pair per "
+                      f"thread (OpenMP over pairs), {dt:.2f} s wall",
+            "host_cpus": os.cpu_count(), "pairs": n, "seconds": dt}, r
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rounds = 8
+    times = []
+    last = None
+    for s in range(args.warmup + args.steps):
+        cb, _ = cpu_baseline(rounds, seed0=20_000)
+        if s >= args.warmup:
+            times.append(cb["seconds"])
+            last = cb
+    sample = last["pairs"]
+    t = float(np.mean(times))
+    v = sample / t
+    cb = dict(last)
+    cb["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_step": sample, "note": "CPU restatement of the reference "
+                       "(oracle/clipper_oracle.c, kind=port: the reference needs Eigen3 which is absent); one pair per host thread"},
+            "cpu_baseline": cb,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from roman_b200.engine import Engine, make_invariant_params, method_invariant_kwargs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    K, W = args.steps, args.warmup
+
+    eng = Engine(local)
+    eng.set_invariant_params(make_invariant_params(**method_invariant_kwargs(METHOD, semantics_dim=SEM_DIM)))
+    eng.plan(N1 * 0 + (3 + 3 + 1 + SEM_DIM), [N1] * B, [N2] * B)
+    # problems are partitioned round-robin over ranks: global pair g = b*world + rank
+    D1h, D2h, u0h = make_inputs(1000 + rank * B, B)
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    D1p, D2p, u0p = pin(D1h.reshape(-1)), pin(D2h.reshape(-1)), pin(u0h.reshape(-1))
+    D1d, D2d, u0d = D1p.to(dev), D2p.to(dev), u0p.to(dev)
+    res = eng.alloc_result()
+    rec = torch.zeros((B, 20), dtype=torch.float64, device=dev)       # status, n_inliers, F, pad, T[16]
+    gathered = torch.zeros((world * B, 20), dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step():
+        eng.align_batch(D1d, D2d, u0d, out=res)
+        if world > 1:  # the path's only exchange: all-gather of fixed-size per-pair records
+            rec[:, 0] = res.status.to(torch.float64)
+            rec[:, 1] = res.n_sel.to(torch.float64)
+            rec[:, 2] = res.score
+            rec[:, 4:] = res.T.reshape(B, 16)
+            dist.all_gather_into_tensor(gathered, rec)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng.set_profiling(True)
+    for _ in range(W):
+        step()
+    sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage = {"prep": 0.0, "affinity": 0.0, "solve": 0.0, "arun": 0.0}
+    sync()
+    ev0.record()
+    for _ in range(K):
+        step()
+        for k, v in eng.stage_ms().items():  # CUDA events on the launch stream (syncs on the step's last event)
+            stage[k] += v
+    ev1.record()
+    sync()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * K / (ms * 1e-3)
+
+    # ---- end-to-end through the host-buffer C ABI: pinned host inputs, H2D + kernels + D2H inside the timed region
+    out_h = None
+    sync()
+    for _ in range(max(1, min(W, 2))):
+        out_h = eng.align_batch_host(D1p, D2p, u0p, out=out_h)
+    sync()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(K):
+        out_h = eng.align_batch_host(D1p, D2p, u0p, out=out_h)
+    wall = time.perf_counter() - t0
+    te = torch.tensor([wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * K / float(te.item())
+    h2d = (D1p.numel() + D2p.numel() + u0p.numel()) * 8
+    d2h = sum(v.nbytes for v in out_h.values())
+
+    if rank == 0:
+        peaks, which = measured_peaks()
+        passes = res.n_passes.cpu().numpy().astype(np.int64)
+        m = M_ASSOC
+        # algorithmic bytes (packed-upper layout, s = 8):
+        k2_bytes = float(passes.sum()) * (8.0 * m * (m - 1) / 2 + 24.0 * m)
+        d_row = 3 + 3 + 1 + SEM_DIM
+        k1_bytes = B * (8.0 * m * (m - 1) / 2 + 8.0 * d_row * (N1 + N2) + 8.0 * m)
+        k2_ms, k1_ms = stage["solve"] / K, (stage["prep"] + stage["affinity"]) / K
+        k2_gbs = k2_bytes / (k2_ms * 1e-3) / 1e9
+        k1_gbs = k1_bytes / (k1_ms * 1e-3) / 1e9
+        peak = float(peaks["hbm_gbs"])
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "parallelism": f"round-robin pairs over {world} GPU(s)",
+                       "l2": f"inputs larger than L2: packed affinity working set {eng.packed_bytes / 1e9:.2f} GB per GPU per step",
+                       "layout": "packed upper triangle, 32x32 fp64 tiles", "mean_passes": float(passes.mean())},
+            "roofline": {"kernel": "rb_solver_kernel (K2)", "bound": "hbm", "achieved": k2_gbs, "peak": peak, "unit": "GB/s",
+                         "frac": k2_gbs / peak, "traffic": None, "peak_source": which,
+                         "algorithmic_bytes_per_launch": k2_bytes, "ms_per_launch": k2_ms},
+            "kernels": {"K1_affinity": {"achieved": k1_gbs, "frac": k1_gbs / peak, "ms_per_launch": k1_ms,
+                                        "algorithmic_bytes_per_launch": k1_bytes},
+                        "K2_solver": {"achieved": k2_gbs, "frac": k2_gbs / peak, "ms_per_launch": k2_ms},
+                        "K3_arun_ms": stage["arun"] / K},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "api": "rb_align_batch_host (pinned host buffers; H2D + K1a/K1/K2/K3 + D2H per step)"},
+            "gpu_launches": 4 * K,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            cb, _ = cpu_baseline(16)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=592, help="submap pairs per GPU per step (4 x 148 SMs)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
