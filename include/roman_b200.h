@@ -161,6 +161,12 @@ int rb_get_dense(rb_handle* h, int32_t b, double* M_out, double* C_out, void* st
  * and M == 0 are kept (stored as -0.0); entries with M != 0 and C == 0 are unsupported. */
 int rb_set_dense(rb_handle* h, int32_t b, const double* M, const double* C, void* stream);
 
+/* Tuning knob of K2: how many CTAs (SMs) of one thread-block cluster share one problem
+ * (0 = auto, else 1, 2, 4 or 8).  Takes effect at the next rb_plan.  Results do not depend on
+ * it beyond the last bits of u (different summation tree). */
+int rb_set_solver_cluster(rb_handle* h, int32_t ctas_per_problem);
+int rb_get_solver_cluster(const rb_handle* h);
+
 /* Device milliseconds of the last rb_align_batch / stage calls, measured with CUDA events on
  * the launch stream: ms[0]=prep(K1a) ms[1]=affinity(K1) ms[2]=solve(K2) ms[3]=arun(K3).
  * Synchronises on the recorded events.  Enabled by rb_set_profiling(h, 1). */

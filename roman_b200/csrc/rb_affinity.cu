@@ -209,6 +209,138 @@ __global__ void __launch_bounds__(256) rb_prep_kernel(const RbProblem* __restric
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// K1a for all-to-all plans: the n1 x n2 cosine table is a small dense contraction
+// (descriptors^T * descriptors), so it is tiled through shared memory instead of re-reading two
+// D-vectors per association: one CTA per 64x64 block of (object of map 1, object of map 2), 4x4
+// outputs per thread, descriptors streamed once in chunks of 32 columns.  Each dot product and
+// squared norm is accumulated sequentially over the descriptor index with separate multiply and
+// add (the translation unit is built with -fmad=false), i.e. in the same order as the scalar loop
+// of the reference's restatement.
+constexpr int PT = 64;   // objects per tile edge
+constexpr int PK = 32;   // descriptor columns per chunk
+__global__ void __launch_bounds__(256) rb_prep_table_kernel(const RbProblem* __restrict__ probs, RbAssocSoA rec,
+                                                            const double* __restrict__ D1,
+                                                            const double* __restrict__ D2, RbDevParams P,
+                                                            int tiles2_max) {
+  __shared__ double As[PT][PK + 1];
+  __shared__ double Bs[PT][PK + 1];
+  __shared__ double s_na[PT], s_nb[PT];
+  const RbProblem pr = probs[blockIdx.y];
+  const rb_invariant_params& p = P.inv;
+  const int t1 = blockIdx.x / tiles2_max, t2 = blockIdx.x % tiles2_max;
+  const int i1_0 = t1 * PT, i2_0 = t2 * PT;
+  const int tid = threadIdx.x;
+  if (blockIdx.x == 0) {  // padding records of this problem
+    for (int k = pr.m + tid; k < pr.nb * RB_TILE; k += 256) {
+      const int64_t o = pr.off_pad + k;
+      rec.ax[o] = rec.ay[o] = rec.az[o] = rec.bx[o] = rec.by[o] = rec.bz[o] = 0.0;
+      rec.single[o] = 0.0;
+      rec.i1[o] = -1;
+      rec.i2[o] = -1;
+    }
+  }
+  if (i1_0 >= pr.n1 || i2_0 >= pr.n2) return;
+  const int tx = tid & 15, ty = tid >> 4;
+  const double* A0 = D1 + pr.off_obj1 * (int64_t)pr.d;
+  const double* B0 = D2 + pr.off_obj2 * (int64_t)pr.d;
+  const int foff = p.point_dim + p.ratio_feature_dim;
+  const int Dc = (p.kind == RB_INVARIANT_ROMAN) ? p.cos_feature_dim : 0;
+
+  double acc[4][4];
+  double na[4] = {0, 0, 0, 0}, nb[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+
+  for (int k0 = 0; k0 < Dc; k0 += PK) {
+    __syncthreads();
+    for (int e = tid; e < PT * PK; e += 256) {  // coalesced along the descriptor index
+      const int o = e / PK, k = e % PK;
+      const bool kin = (k0 + k) < Dc;
+      As[o][k] = (kin && i1_0 + o < pr.n1) ? A0[(int64_t)(i1_0 + o) * pr.d + foff + k0 + k] : 0.0;
+      Bs[o][k] = (kin && i2_0 + o < pr.n2) ? B0[(int64_t)(i2_0 + o) * pr.d + foff + k0 + k] : 0.0;
+    }
+    __syncthreads();
+    const int kend = (Dc - k0) < PK ? (Dc - k0) : PK;
+    for (int k = 0; k < kend; ++k) {
+      double a[4], b[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[r] = As[ty * 4 + r][k];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) b[c] = Bs[tx * 4 + c][k];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] += a[r] * b[c];
+        na[r] += a[r] * a[r];
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) nb[c] += b[c] * b[c];
+    }
+  }
+  __syncthreads();
+  if (tx == 0)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) s_na[ty * 4 + r] = na[r];
+  if (ty == 0)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) s_nb[tx * 4 + c] = nb[c];
+  __syncthreads();
+
+  const int pd = (p.kind == RB_INVARIANT_ROMAN) ? p.point_dim : (pr.d < 3 ? pr.d : 3);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i1 = i1_0 + ty * 4 + r;
+    if (i1 >= pr.n1) continue;
+    const double* a = A0 + (int64_t)i1 * pr.d;
+    const double a0 = a[0], a1 = pd > 1 ? a[1] : 0.0, a2 = pd > 2 ? a[2] : 0.0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int i2 = i2_0 + tx * 4 + c;
+      if (i2 >= pr.n2) continue;
+      const double* b = B0 + (int64_t)i2 * pr.d;
+      double single = 1.0;
+      if (p.kind == RB_INVARIANT_ROMAN && (p.cos_feature_dim > 0 || p.ratio_feature_dim > 0)) {  // roman.cpp:116-164
+        bool zero = false;
+        double cos_scaled = 0.0, ratio_score = 0.0;
+        if (p.cos_feature_dim > 0) {
+          const double cs = acc[r][c] / (sqrt(s_na[ty * 4 + r]) * sqrt(s_nb[tx * 4 + c]));
+          if (cs >= p.cosine_max) cos_scaled = 1.0;
+          else if (cs <= p.cosine_min) zero = true;
+          else cos_scaled = (cs - p.cosine_min) / (p.cosine_max - p.cosine_min);
+        }
+        if (!zero && p.ratio_feature_dim > 0) {
+          double prod = 1.0;
+          bool below = false;
+          for (int t = 0; t < p.ratio_feature_dim; ++t) {
+            const double x = a[p.point_dim + t], y = b[p.point_dim + t];
+            const double q = x < y ? x / y : y / x;
+            if (q < p.ratio_epsilon[t]) below = true;
+            prod *= q;
+          }
+          if (below) zero = true;
+          else ratio_score = pow(prod, 1.0 / p.ratio_feature_dim);
+        }
+        if (zero) single = 0.0;
+        else if (p.ratio_feature_dim == 0) single = cos_scaled;
+        else if (p.cos_feature_dim == 0) single = ratio_score;
+        else
+          single = pow(pow(ratio_score, p.ratio_weight) * pow(cos_scaled, p.cosine_weight),
+                       1.0 / (p.ratio_weight + p.cosine_weight));
+      }
+      const int64_t o = pr.off_pad + (int64_t)i1 * pr.n2 + i2;  // utils::createAllToAll order
+      rec.ax[o] = a0; rec.ay[o] = a1; rec.az[o] = a2;
+      rec.bx[o] = b[0]; rec.by[o] = pd > 1 ? b[1] : 0.0; rec.bz[o] = pd > 2 ? b[2] : 0.0;
+      rec.single[o] = single;
+      rec.i1[o] = i1;
+      rec.i2[o] = i2;
+    }
+  }
+}
+
 __device__ __forceinline__ Rec load_rec(const RbAssocSoA& rec, int64_t o) {
   Rec r;
   r.ax = rec.ax[o]; r.ay = rec.ay[o]; r.az = rec.az[o];
@@ -250,18 +382,33 @@ __global__ void __launch_bounds__(256) rb_affinity_kernel(const RbProblem* __res
     int I, J;
     tile_coords(q, pr.nb, I, J);
     const Rec col = load_rec(rec, pr.off_pad + (int64_t)J * RB_TILE + lane);
-    __syncwarp();
-    s_row[warp][lane] = load_rec(rec, pr.off_pad + (int64_t)I * RB_TILE + lane);
-    __syncwarp();
+    const Rec myrow = load_rec(rec, pr.off_pad + (int64_t)I * RB_TILE + lane);
     double* out = Mp + (pr.off_tile + q) * RB_TILE_ELEMS;
+    // An association whose single score is below affinityeps (clipper.cpp:104-108), or padding,
+    // can have no edge at all: rows/columns made only of such associations are written as zeros
+    // without evaluating anything.  (NaN scores are "live", exactly as the reference's `<` test.)
+    const bool roman = (P.inv.kind == RB_INVARIANT_ROMAN);
+    const unsigned col_live = __ballot_sync(0xffffffffu, col.i1 >= 0 && !(roman && col.s < P.affinityeps));
+    const unsigned row_live = __ballot_sync(0xffffffffu, myrow.i1 >= 0 && !(roman && myrow.s < P.affinityeps));
+    if (col_live == 0u || row_live == 0u) {
+      double2* o2 = reinterpret_cast<double2*>(out);
+#pragma unroll
+      for (int t = 0; t < RB_TILE_ELEMS / 2 / 32; ++t) o2[t * 32 + lane] = make_double2(0.0, 0.0);
+      continue;
+    }
+    __syncwarp();
+    s_row[warp][lane] = myrow;
+    __syncwarp();
     const bool diag = (I == J);
 #pragma unroll 4
     for (int r = 0; r < RB_TILE; ++r) {
-      const Rec row = s_row[warp][r];
-      double v;
-      if (!diag || r < lane) v = pair_score(P, row, col);       // i = row index < j = column index
-      else if (r > lane) v = pair_score(P, col, row);           // mirrored entry of the diagonal tile
-      else v = 0.0;                                             // identity is implicit (clipper.cpp:129-130)
+      double v = 0.0;
+      if ((row_live >> r) & 1u) {
+        const Rec row = s_row[warp][r];
+        if (!diag || r < lane) v = pair_score(P, row, col);       // i = row index < j = column index
+        else if (r > lane) v = pair_score(P, col, row);           // mirrored entry of the diagonal tile
+        // r == lane: identity is implicit (clipper.cpp:129-130)
+      }
       out[r * RB_TILE + lane] = v;
     }
   }
@@ -319,9 +466,18 @@ __global__ void rb_pack_kernel(RbProblem pr, const double* __restrict__ Min, con
 
 }  // namespace
 
-cudaError_t rb_launch_prep(const RbProblem* probs, int B, int max_mp, const RbAssocSoA& rec, const double* D1,
-                           const double* D2, const int32_t* A, const RbDevParams& P, cudaStream_t st) {
+cudaError_t rb_launch_prep(const RbProblem* probs, int B, int max_mp, int max_n1, int max_n2, bool all_to_all,
+                           const RbAssocSoA& rec, const double* D1, const double* D2, const int32_t* A,
+                           const RbDevParams& P, cudaStream_t st) {
   if (B == 0 || max_mp == 0) return cudaSuccess;
+  if (all_to_all) {
+    const int t1 = (max_n1 + PT - 1) / PT, t2 = (max_n2 + PT - 1) / PT;
+    if ((int64_t)t1 * t2 <= 65535 * 32) {
+      dim3 grid((unsigned)(t1 * t2), B);
+      rb_prep_table_kernel<<<grid, 256, 0, st>>>(probs, rec, D1, D2, P, t2);
+      return cudaGetLastError();
+    }
+  }
   dim3 grid((max_mp + 7) / 8, B);
   if (grid.x > 512) grid.x = 512;
   rb_prep_kernel<<<grid, 256, 0, st>>>(probs, rec, D1, D2, A, P);

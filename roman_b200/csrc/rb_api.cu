@@ -24,13 +24,16 @@ struct rb_handle {
   std::vector<RbProblem> probs;
   std::vector<int64_t> tile_prefix;  // B+1
   int64_t total_assoc = 0, total_pad = 0, total_tiles = 0, total_obj1 = 0, total_obj2 = 0;
-  int32_t max_mp = 0;
+  int32_t max_mp = 0, max_n1 = 0, max_n2 = 0;
+  int32_t cluster_req = 0;   // 0 = auto
+  int32_t cluster = 1;       // resolved at plan time
+  int32_t max_clusters = 1;  // co-resident clusters of that size
 
   // device scratch
   RbProblem* d_probs = nullptr; size_t cap_probs = 0;
   int64_t* d_tile_prefix = nullptr; size_t cap_prefix = 0;
   double* d_M = nullptr; size_t cap_M = 0;            // packed tiles
-  double* d_pad_f64 = nullptr; size_t cap_pad = 0;    // 9 padded double arrays (7 record + u + g)
+  double* d_pad_f64 = nullptr; size_t cap_pad = 0;    // padded double arrays (7 record + u, g per cluster CTA)
   int32_t* d_pad_i32 = nullptr;                       // 2 padded int arrays
   int32_t* d_counter = nullptr;
   int* d_bad = nullptr;
@@ -90,8 +93,10 @@ RbAssocSoA soa_of(rb_handle* h) {
   r.i2 = h->d_pad_i32 + n;
   return r;
 }
+constexpr int kMaxCluster = 8;
+constexpr int kPadArrays = 7 + 2 * kMaxCluster;  // 7 record arrays + per-CTA copies of u and g
 double* u_work(rb_handle* h) { return h->d_pad_f64 + 7 * (size_t)h->total_pad; }
-double* g_work(rb_handle* h) { return h->d_pad_f64 + 8 * (size_t)h->total_pad; }
+double* g_work(rb_handle* h) { return h->d_pad_f64 + (7 + kMaxCluster) * (size_t)h->total_pad; }
 
 RbDevParams dev_params(const rb_handle* h) {
   RbDevParams P;
@@ -201,6 +206,18 @@ int rb_set_solver_params(rb_handle* h, const rb_solver_params* p) {
   return RB_OK;
 }
 
+int rb_set_solver_cluster(rb_handle* h, int32_t ctas_per_problem) {
+  if (!h) return RB_ERR_ARG;
+  if (ctas_per_problem != 0 && ctas_per_problem != 1 && ctas_per_problem != 2 && ctas_per_problem != 4 &&
+      ctas_per_problem != 8)
+    return fail(h, RB_ERR_ARG, "rb_set_solver_cluster: must be 0 (auto), 1, 2, 4 or 8");
+  h->cluster_req = ctas_per_problem;
+  h->planned = false;  // takes effect at the next rb_plan
+  return RB_OK;
+}
+
+int rb_get_solver_cluster(const rb_handle* h) { return h ? h->cluster : 0; }
+
 int rb_set_profiling(rb_handle* h, int32_t on) {
   if (!h) return RB_ERR_ARG;
   h->profiling = on != 0;
@@ -229,7 +246,7 @@ int rb_plan(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const int32_t
   h->probs.assign((size_t)B, RbProblem());
   h->tile_prefix.assign((size_t)B + 1, 0);
   int64_t oa = 0, op = 0, ot = 0, o1 = 0, o2 = 0;
-  int32_t max_mp = 0;
+  int32_t max_mp = 0, mx1 = 0, mx2 = 0;
   for (int b = 0; b < B; ++b) {
     if (n1[b] < 0 || n2[b] < 0) return fail(h, RB_ERR_ARG, "rb_plan: negative object count");
     const int64_t mm = m ? (int64_t)m[b] : (int64_t)n1[b] * n2[b];
@@ -242,6 +259,8 @@ int rb_plan(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const int32_t
     h->tile_prefix[(size_t)b] = ot;
     o1 += n1[b]; o2 += n2[b]; oa += mm; op += (int64_t)p.nb * RB_TILE; ot += p.n_tiles;
     if (p.nb * RB_TILE > max_mp) max_mp = p.nb * RB_TILE;
+    if (n1[b] > mx1) mx1 = n1[b];
+    if (n2[b] > mx2) mx2 = n2[b];
   }
   h->tile_prefix[(size_t)B] = ot;
   const size_t smem = rb_solver_smem_bytes(max_mp, 2);
@@ -255,6 +274,29 @@ int rb_plan(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const int32_t
   h->B = B; h->d = d; h->all_to_all = (m == nullptr);
   h->total_assoc = oa; h->total_pad = op; h->total_tiles = ot; h->total_obj1 = o1; h->total_obj2 = o2;
   h->max_mp = max_mp;
+  h->max_n1 = mx1;
+  h->max_n2 = mx2;
+  {
+    // CTAs per problem.  Auto: spread a problem over enough SMs that a slow-converging problem
+    // cannot leave a long single-SM tail, but never more clusters' worth than there are problems.
+    int c = h->cluster_req;
+    if (c == 0) {
+      c = 4;
+      if ((int64_t)B * 8 <= h->sm_count) c = 8;
+      if (max_mp <= 256) c = 1;
+      else if (max_mp <= 1024 && c > 2) c = 2;
+    }
+    int mc = 0;
+    for (;;) {
+      cudaError_t e = rb_solver_max_clusters(max_mp, c, &mc);
+      if (e == cudaSuccess && mc >= 1) break;
+      cudaGetLastError();
+      if (c == 1) return fail(h, RB_ERR_CUDA, "rb_plan: solver kernel cannot be resident on this device");
+      c >>= 1;
+    }
+    h->cluster = c;
+    h->max_clusters = mc;
+  }
 
   int rc;
   if ((rc = ensure(h, &h->d_probs, &h->cap_probs, (size_t)B))) return rc;
@@ -267,7 +309,7 @@ int rb_plan(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const int32_t
       if (h->d_pad_i32) cudaFree(h->d_pad_i32);
       h->d_pad_f64 = nullptr; h->d_pad_i32 = nullptr; h->cap_pad = 0;
       const size_t n = need ? need : 1;
-      RB_CUDA(h, cudaMalloc((void**)&h->d_pad_f64, 9 * n * sizeof(double)));
+      RB_CUDA(h, cudaMalloc((void**)&h->d_pad_f64, (size_t)kPadArrays * n * sizeof(double)));
       RB_CUDA(h, cudaMalloc((void**)&h->d_pad_i32, 2 * n * sizeof(int32_t)));
       h->cap_pad = n;
     }
@@ -340,7 +382,8 @@ int rb_affinity(rb_handle* h, const double* D1, const double* D2, const int32_t*
   const RbDevParams P = dev_params(h);
   const RbAssocSoA rec = soa_of(h);
   record(h, 0, st);
-  RB_CUDA(h, rb_launch_prep(h->d_probs, h->B, h->max_mp, rec, D1, D2, h->all_to_all ? nullptr : A, P, st));
+  RB_CUDA(h, rb_launch_prep(h->d_probs, h->B, h->max_mp, h->max_n1, h->max_n2, h->all_to_all, rec, D1, D2,
+                            h->all_to_all ? nullptr : A, P, st));
   record(h, 1, st);
   RB_CUDA(h, rb_launch_affinity(h->d_probs, h->B, h->d_tile_prefix, h->total_tiles, rec, h->d_M, P, h->sm_count, st));
   record(h, 2, st);
@@ -369,9 +412,11 @@ int rb_solve(rb_handle* h, const double* u0, int32_t* nodes, int32_t* sel, int32
   a.n_passes = n_passes ? n_passes : h->d_npass;
   a.sp = h->sol;
   a.mp_max = h->max_mp;
+  a.pad_stride = h->total_pad;
+  a.cluster = h->cluster;
   RB_CUDA(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int32_t), st));
   record(h, 3, st);
-  RB_CUDA(h, rb_launch_solver(a, h->sm_count, st));
+  RB_CUDA(h, rb_launch_solver(a, h->max_clusters, st));
   record(h, 4, st);
   return RB_OK;
 }

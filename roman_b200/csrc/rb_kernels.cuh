@@ -20,6 +20,8 @@ struct RbSolveArgs {
   const double* u0;        // user layout (off_assoc)
   double* u_work;          // padded scratch (off_pad): current iterate u
   double* g_work;          // padded scratch: gradient at u
+  int64_t pad_stride;      // u_work/g_work hold `cluster` private copies, this many doubles apart
+  int32_t cluster;         // CTAs per problem (1, 2, 4, 8)
   // outputs, user layout (off_assoc); rb_api substitutes handle scratch for NULL user pointers,
   // so only u_out may be null here
   int32_t* nodes;
@@ -33,8 +35,9 @@ struct RbSolveArgs {
   int32_t mp_max;          // max padded m over the batch (sizes the shared-memory vectors)
 };
 
-cudaError_t rb_launch_prep(const RbProblem* probs, int B, int max_mp, const RbAssocSoA& rec, const double* D1,
-                           const double* D2, const int32_t* A, const RbDevParams& P, cudaStream_t st);
+cudaError_t rb_launch_prep(const RbProblem* probs, int B, int max_mp, int max_n1, int max_n2, bool all_to_all,
+                           const RbAssocSoA& rec, const double* D1, const double* D2, const int32_t* A,
+                           const RbDevParams& P, cudaStream_t st);
 cudaError_t rb_launch_affinity(const RbProblem* probs, int B, const int64_t* tile_prefix, int64_t total_tiles,
                                const RbAssocSoA& rec, double* Mp, const RbDevParams& P, int sm_count,
                                cudaStream_t st);
@@ -45,7 +48,8 @@ cudaError_t rb_launch_pack(const RbProblem& pr, const double* Min, const double*
 // Returns cudaErrorInvalidValue if mp_max does not fit the shared-memory layout.
 size_t rb_solver_smem_bytes(int mp_max, int slots);
 cudaError_t rb_solver_prepare(int device);  // opt in to the large dynamic shared-memory carve-out
-cudaError_t rb_launch_solver(const RbSolveArgs& a, int sm_count, cudaStream_t st);
+cudaError_t rb_solver_max_clusters(int mp_max, int cluster, int* out);
+cudaError_t rb_launch_solver(const RbSolveArgs& a, int max_clusters, cudaStream_t st);
 
 cudaError_t rb_launch_arun(const RbProblem* probs, int B, int point_dim, const double* D1, const double* D2,
                            const int32_t* sel, const int32_t* n_sel, double* T, int32_t* status,

@@ -1,12 +1,18 @@
-// rb_solver.cu — K2: persistent CLIPPER dense-clique solver, one CTA per problem.
+// rb_solver.cu — K2: persistent CLIPPER dense-clique solver, one thread-block cluster per problem.
 //
 // Replaces CLIPPER::findDenseClique (clipper/src/clipper.cpp:243-394), utils::findIndicesOfkLargest
 // (clipper/src/utils.cpp:33-55) and utils::selectInlierAssociations (utils.cpp:101-108).
 //
 // Shape of the kernel
-//   - grid = min(B, #SM) CTAs of 8 warps; CTAs pull problems from an atomic queue, so every SM
-//     streams a different problem's packed affinity matrix from HBM: the working set is far
-//     larger than L2 and the kernel is HBM-bound by construction.
+//   - the grid is a set of thread-block clusters of C CTAs (C = 1, 2, 4 or 8; 8 warps per CTA, one
+//     CTA per SM); clusters pull problems from an atomic queue, so the SMs stream different
+//     problems' packed affinity matrices from HBM: the working set is far larger than L2 and
+//     the kernel is HBM-bound by construction.  C > 1 splits the tiles of one problem over the
+//     CTAs of its cluster (tile column J goes to CTA J mod C) and combines the per-CTA partial
+//     (M x, C x) vectors through distributed shared memory once per pass; it exists to shorten
+//     the tail that a slow-converging problem would otherwise leave on a single SM.
+//     Every CTA of a cluster then runs the (cheap) vector phases redundantly on identical data,
+//     so all scalar decisions agree without any further exchange.
 //   - one "pass" = one fused evaluation of (M x, C x) for the current trial vector x:
 //     every 32x32 tile (8 KB, contiguous) of the packed upper triangle is brought into shared
 //     memory by one cp.async.bulk (TMA) and used twice — tile * x_J feeds the row sums of block
@@ -20,7 +26,11 @@
 //     is resolved on the device from block-wide reductions with a fixed tree.
 //   - M x and C x of the accepted iterate are kept, so the d update and the new gradient need
 //     no extra pass (the reference recomputes them; the values are identical).
+#include <cooperative_groups.h>
+
 #include "rb_kernels.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -29,6 +39,7 @@ constexpr int NT = NW * 32;   // threads per CTA
 constexpr int SLOTS = 2;      // ring slots per warp (8 KB each)
 constexpr int RED_DOUBLES = 64;   // [0,32): double-buffered reduction scratch; [40]: broadcast slot
 constexpr int MISC_INTS = 16;
+constexpr int EPT_MAX = 20;       // max vector elements per thread (mp_max <= EPT_MAX * NT)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -63,8 +74,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// first tile column of tile-row I that belongs to warp w
-__device__ __forceinline__ int first_col(int I, int w) { return I + ((w - I) % NW + NW) % NW; }
+// first tile column J >= I with J mod stride == gw (gw = global warp id inside the cluster)
+__device__ __forceinline__ int first_col(int I, int gw, int stride) { return I + ((gw - I) % stride + stride) % stride; }
 
 struct Smem {
   double* x;     // trial vector (mp)
@@ -109,9 +120,12 @@ struct Reducer {
 
 // One fused pass: accM += M x, accC += C x over the packed upper triangle of one problem.
 // Preconditions: x complete, accM/accC zeroed, all threads past a __syncthreads.
+// With a cluster of C CTAs, tile column J belongs to CTA (J mod C), warp ((J / C) mod NW); the
+// results are this CTA's PARTIAL sums (combined by cluster_combine afterwards).
 __device__ __forceinline__ void matvec_pass(const Smem& S, const double* __restrict__ tiles, int nb,
-                                            uint32_t& phase_bits) {
+                                            uint32_t& phase_bits, int C, int crank) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int gw = w * C + crank, stride = NW * C;
   uint64_t* bar = S.bar + w * SLOTS;
   double* ring = S.ring + (size_t)w * SLOTS * RB_TILE_ELEMS;
 
@@ -119,17 +133,17 @@ __device__ __forceinline__ void matvec_pass(const Smem& S, const double* __restr
   int pfI = 0, pfJ = 0;
   bool pf_ok = false;
   for (pfI = 0; pfI < nb; ++pfI) {
-    pfJ = first_col(pfI, w);
+    pfJ = first_col(pfI, gw, stride);
     if (pfJ < nb) { pf_ok = true; break; }
   }
   auto pf_issue = [&](int slot) {
     if (lane == 0)
       tma_load_tile(ring + slot * RB_TILE_ELEMS, tiles + rb_tile_index(pfI, pfJ, nb) * RB_TILE_ELEMS, bar + slot);
-    pfJ += NW;
+    pfJ += stride;
     while (pfJ >= nb) {
       ++pfI;
       if (pfI >= nb) { pf_ok = false; break; }
-      pfJ = first_col(pfI, w);
+      pfJ = first_col(pfI, gw, stride);
     }
   };
 #pragma unroll
@@ -143,7 +157,7 @@ __device__ __forceinline__ void matvec_pass(const Smem& S, const double* __restr
     for (int r = 0; r < RB_TILE; ++r) { rowM[r] = 0.0; rowC[r] = 0.0; }
     const double* xI = S.x + I * RB_TILE;
 
-    for (int J = first_col(I, w); J < nb; J += NW) {
+    for (int J = first_col(I, gw, stride); J < nb; J += stride) {
       mbar_wait(bar + slot, (phase_bits >> slot) & 1u);
       phase_bits ^= (1u << slot);
       const double* buf = ring + slot * RB_TILE_ELEMS;
@@ -159,7 +173,7 @@ __device__ __forceinline__ void matvec_pass(const Smem& S, const double* __restr
           colM = fma(v, xi, colM);
           if (nz) { rowC[r] += xJ; colC += xi; }
         }
-        // this warp is the only writer of output block J
+        // this warp is the only writer of output block J in this CTA
         S.accM[J * RB_TILE + lane] += colM;
         S.accC[J * RB_TILE + lane] += colC;
       } else {
@@ -195,7 +209,7 @@ __device__ __forceinline__ void matvec_pass(const Smem& S, const double* __restr
     part[(w * 2 + 0) * RB_TILE + lane] = rowM[0];
     part[(w * 2 + 1) * RB_TILE + lane] = rowC[0];
     named_bar_sync(1, NT);
-    if ((I % NW) == w) {  // owner of output block I combines the 8 warps in fixed order
+    if (((I / C) % NW) == w) {  // this CTA's writer of output block I combines the 8 warps in fixed order
       double sm = 0.0, sc = 0.0;
 #pragma unroll
       for (int ww = 0; ww < NW; ++ww) {
@@ -206,6 +220,34 @@ __device__ __forceinline__ void matvec_pass(const Smem& S, const double* __restr
       S.accC[I * RB_TILE + lane] += sc;
     }
   }
+}
+
+// Combine the per-CTA partial (accM, accC) of a cluster: every CTA sums all C partial vectors
+// in rank order (bitwise identical result everywhere) and overwrites its own copy with the
+// total.  Two cluster barriers: partials complete -> read; all reads done -> overwrite.
+__device__ __forceinline__ void cluster_combine(const Smem& S, int mp, int C) {
+  if (C == 1) { __syncthreads(); return; }
+  cg::cluster_group cluster = cg::this_cluster();
+  cluster.sync();
+  double sm[EPT_MAX], sc[EPT_MAX];
+#pragma unroll
+  for (int k = 0; k < EPT_MAX; ++k) { sm[k] = 0.0; sc[k] = 0.0; }
+  for (int r = 0; r < C; ++r) {
+    const double* rm = cluster.map_shared_rank(S.accM, r);
+    const double* rc = cluster.map_shared_rank(S.accC, r);
+#pragma unroll
+    for (int k = 0; k < EPT_MAX; ++k) {
+      const int i = threadIdx.x + k * NT;
+      if (i < mp) { sm[k] += rm[i]; sc[k] += rc[i]; }
+    }
+  }
+  cluster.sync();
+#pragma unroll
+  for (int k = 0; k < EPT_MAX; ++k) {
+    const int i = threadIdx.x + k * NT;
+    if (i < mp) { S.accM[i] = sm[k]; S.accC[i] = sc[k]; }
+  }
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
@@ -232,23 +274,31 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
   uint32_t phase = 0u;  // bit s = parity the next wait on ring slot s must see
   Reducer R{S.red, 0};
   const rb_solver_params sp = A.sp;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = (int)cluster.num_blocks();
+  const int crank = (int)cluster.block_rank();
+  const bool lead = (crank == 0);
 
   for (;;) {
-    __syncthreads();
-    if (tid == 0) S.misc[0] = atomicAdd(A.counter, 1);
-    __syncthreads();
+    // one problem per cluster: rank 0 pulls from the queue and posts the index to every CTA
+    cluster.sync();
+    if (lead && tid == 0) {
+      const int nxt = atomicAdd(A.counter, 1);
+      for (int r = 0; r < C; ++r) *cluster.map_shared_rank(S.misc, r) = nxt;
+    }
+    cluster.sync();
     const int b = S.misc[0];
     if (b >= A.B) break;
     const RbProblem pr = A.probs[b];
     const int m = pr.m, nb = pr.nb, mp = nb * RB_TILE;
     const double* tiles = A.Mp + pr.off_tile * RB_TILE_ELEMS;
-    double* u = A.u_work + pr.off_pad;
-    double* g = A.g_work + pr.off_pad;
+    double* u = A.u_work + (size_t)crank * A.pad_stride + pr.off_pad;  // per-CTA private copies
+    double* g = A.g_work + (size_t)crank * A.pad_stride + pr.off_pad;
     const double* u0 = A.u0 + pr.off_assoc;
     int passes = 0;
 
     if (m == 0) {
-      if (tid == 0) {
+      if (lead && tid == 0) {
         A.n_nodes[b] = 0; A.score[b] = 0.0; A.ifinal[b] = 0; A.n_passes[b] = 0;
       }
       continue;
@@ -262,9 +312,9 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
     }
     __syncthreads();
     if (sp.rescale_u0) {
-      matvec_pass(S, tiles, nb, phase);
+      matvec_pass(S, tiles, nb, phase, C, crank);
       ++passes;
-      __syncthreads();
+      cluster_combine(S, mp, C);
     }
     double nrm2 = 0.0;
     for (int i = tid; i < mp; i += NT) {
@@ -286,9 +336,9 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
       }
     }
     sum_u = R.sum1(sum_u);
-    matvec_pass(S, tiles, nb, phase);  // (M u, C u) of the normalised start vector
+    matvec_pass(S, tiles, nb, phase, C, crank);  // (M u, C u) of the normalised start vector
     ++passes;
-    __syncthreads();
+    cluster_combine(S, mp, C);
 
     // ---- initial d (clipper.cpp:271-280)
     double d = 0.0;
@@ -339,9 +389,9 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
             S.accC[i] = 0.0;
           }
           sum_un = R.sum1(su);
-          matvec_pass(S, tiles, nb, phase);
+          matvec_pass(S, tiles, nb, phase, C, crank);
           ++passes;
-          __syncthreads();
+          cluster_combine(S, mp, C);
           // gradFnew, Fnew (clipper.cpp:309-315) and, speculatively, ||unew - u||^2
           double f = 0.0, dd = 0.0;
           for (int i = tid; i < m; i += NT) {
@@ -383,6 +433,8 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
 
     // ---- rounding (clipper.cpp:358-381) + selected associations (utils.cpp:101-108)
     __syncthreads();
+    // every CTA of the cluster holds identical data; rank 0 alone produces the outputs
+    if (!lead) continue;
     int32_t* nodes = A.nodes + pr.off_assoc;
     int* rank = (int*)S.accM;  // accM is dead from here on
     int n_sel = 0;
@@ -495,11 +547,38 @@ cudaError_t rb_solver_prepare(int device) {
   return cudaFuncSetAttribute(rb_solver_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
 }
 
-cudaError_t rb_launch_solver(const RbSolveArgs& a, int sm_count, cudaStream_t st) {
+static void fill_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int grid, int cluster, size_t smem,
+                        cudaStream_t st) {
+  cfg = cudaLaunchConfig_t();
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(NT, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+}
+
+// How many clusters of `cluster` CTAs can be co-resident (one CTA per SM at this smem size).
+cudaError_t rb_solver_max_clusters(int mp_max, int cluster, int* out) {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  fill_config(cfg, attr, cluster, cluster, rb_solver_smem_bytes(mp_max, SLOTS), nullptr);
+  return cudaOccupancyMaxActiveClusters(out, rb_solver_kernel, &cfg);
+}
+
+cudaError_t rb_launch_solver(const RbSolveArgs& a, int max_clusters, cudaStream_t st) {
   if (a.B == 0) return cudaSuccess;
   const size_t smem = rb_solver_smem_bytes(a.mp_max, SLOTS);
   if (g_max_optin && smem > g_max_optin) return cudaErrorInvalidValue;
-  const int grid = a.B < sm_count ? a.B : sm_count;
-  rb_solver_kernel<<<grid, NT, smem, st>>>(a);
-  return cudaGetLastError();
+  if (a.mp_max > EPT_MAX * NT) return cudaErrorInvalidValue;
+  int nclusters = a.B < max_clusters ? a.B : max_clusters;
+  if (nclusters < 1) nclusters = 1;
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  fill_config(cfg, attr, nclusters * a.cluster, a.cluster, smem, st);
+  return cudaLaunchKernelEx(&cfg, rb_solver_kernel, a);
 }

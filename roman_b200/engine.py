@@ -103,6 +103,14 @@ class Engine:
     def set_solver_params(self, p: RbSolverParams):
         self._check(self._lib.rb_set_solver_params(self._h, C.byref(p)))
 
+    def set_solver_cluster(self, ctas_per_problem: int):
+        """CTAs (SMs) per problem in the solver: 0 auto, 1, 2, 4, 8; applies at the next plan()."""
+        self._check(self._lib.rb_set_solver_cluster(self._h, int(ctas_per_problem)))
+
+    @property
+    def solver_cluster(self) -> int:
+        return int(self._lib.rb_get_solver_cluster(self._h))
+
     def set_profiling(self, on: bool):
         self._check(self._lib.rb_set_profiling(self._h, int(on)))
 

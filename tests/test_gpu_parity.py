@@ -94,3 +94,108 @@ def test_host_entry_point_matches_device_path(engine):
         o = int(engine.offsets[b])
         assert np.array_equal(host["sel"][o:o + host["n_sel"][b]], dev.associations(b))
     assert np.array_equal(host["T"], dev.T.cpu().numpy(), equal_nan=True)
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8])
+def test_solver_cluster_sizes_agree_with_oracle(engine, coracle, cluster):
+    """K2 with 1/2/4/8 CTAs per problem: same ordered inliers as the oracle, F within 1e-9."""
+    ip_o, ip_g = params_for_method("gravity")
+    sp = cn.SolverParams()
+    shapes = [(30, 30), (40, 50), (13, 9), (40, 40)]
+    pairs = [synth.make_pair(300 + i, a, b, method="gravity") for i, (a, b) in enumerate(shapes)]
+    engine.set_solver_cluster(cluster)
+    try:
+        engine.set_invariant_params(ip_g)
+        engine.plan(3, [s[0] for s in shapes], [s[1] for s in shapes])
+        assert engine.solver_cluster == cluster
+        D1 = np.concatenate([p.D1.reshape(-1) for p in pairs])
+        D2 = np.concatenate([p.D2.reshape(-1) for p in pairs])
+        u0 = np.concatenate([p.u0 for p in pairs])
+        engine.affinity(D1, D2)
+        sol = engine.solve(u0, want_u=True)
+        for b, p in enumerate(pairs):
+            Mo, _, A, _ = coracle.score(ip_o, sp.affinityeps, p.D1, p.D2)
+            ref = coracle.solve(sp, Mo, p.u0)
+            o = int(engine.offsets[b])
+            k = int(sol["n_nodes"][b])
+            assert sol["nodes"][o:o + k].cpu().numpy().tolist() == ref["nodes"]
+            assert abs(float(sol["score"][b]) - ref["score"]) <= F_TOL
+            assert np.array_equal(sol["sel"][o:o + k].cpu().numpy(), A[ref["nodes"]])
+    finally:
+        engine.set_solver_cluster(0)
+
+
+def test_explicit_associations_euclidean(engine, coracle):
+    """clipper+prune style: EuclideanDistance invariant on an arbitrary (pruned) association list."""
+    rng = np.random.default_rng(5)
+    ip_o, ip_g = None, None
+    from tests.helpers import oracle_invariant
+    from roman_b200.engine import make_invariant_params
+    kw = dict(kind=1, sigma=0.4, epsilon=0.6, mindist=0.2)
+    ip_o, ip_g = oracle_invariant(**kw), make_invariant_params(**kw)
+    sp = cn.SolverParams()
+    probs = []
+    for s in range(3):
+        p = synth.make_pair(900 + s, 25, 28, method="clipper")
+        A_all = cn.create_all_to_all(25, 28)
+        keep = rng.uniform(size=len(A_all)) < 0.35
+        keep[[i * 28 + i for i in range(12)]] = True  # keep the planted matches
+        A = np.ascontiguousarray(A_all[keep])
+        probs.append((p, A, rng.uniform(0, 1, len(A))))
+    engine.set_invariant_params(ip_g)
+    engine.plan(3, [25] * 3, [28] * 3, m=[len(A) for _, A, _ in probs])
+    D1 = np.concatenate([p.D1.reshape(-1) for p, _, _ in probs])
+    D2 = np.concatenate([p.D2.reshape(-1) for p, _, _ in probs])
+    A_cat = np.concatenate([A for _, A, _ in probs]).astype(np.int32)
+    u0 = np.concatenate([u for _, _, u in probs])
+    res = engine.align_batch(D1, D2, u0, A=A_cat)
+    for b, (p, A, u) in enumerate(probs):
+        ref = coracle.align_pair(ip_o, sp, p.D1, p.D2, u, A=A)
+        assert np.array_equal(res.associations(b), ref["sel"])
+        refT = cn.T_align(p.D1[ref["sel"][:, 0], :3], p.D2[ref["sel"][:, 1], :3])
+        assert rel_fro(res.T[b].cpu().numpy(), refT) <= T_TOL
+
+
+def test_set_dense_get_dense_and_constraint_only_entries(engine, coracle):
+    """set_matrix_data / get_affinity_matrix round trip, incl. C != pattern(M) as mno_clipper makes it."""
+    rng = np.random.default_rng(11)
+    m = 75
+    W = np.triu(rng.uniform(0.2, 1.0, (m, m)) * (rng.uniform(size=(m, m)) < 0.15), 1)
+    W[:8, :8] = np.triu(np.full((8, 8), 0.95), 1)  # planted clique
+    M = W + W.T + np.eye(m)
+    Cfull = (M != 0).astype(float)
+    M2 = M.copy()
+    idx = np.arange(8)
+    M2[np.ix_(idx, idx)] = 0.0  # mno_clipper zeroes solved rows/cols of M but keeps C
+    engine.plan(1, [m], [1], m=[m])
+    engine.set_dense(0, M2, Cfull)
+    Mg, Cg = engine.get_dense(0)
+    M2_expect = M2.copy()
+    np.fill_diagonal(M2_expect, 1.0)
+    assert np.array_equal(Mg.cpu().numpy(), M2_expect)
+    assert np.array_equal(Cg.cpu().numpy(), Cfull)
+    u0 = rng.uniform(0, 1, m)
+    sol = engine.solve(u0, want_u=True)
+    sp = cn.SolverParams()
+    ref = coracle.solve(sp, np.triu(M2, 1), u0, Cupper=np.triu(Cfull, 1))
+    k = int(sol["n_nodes"][0])
+    assert sol["nodes"][:k].cpu().numpy().tolist() == ref["nodes"]
+    assert abs(float(sol["score"][0]) - ref["score"]) <= F_TOL
+
+
+def test_topk_tie_semantics_match_heap(engine, coracle):
+    """findIndicesOfkLargest (utils.cpp:33-55) tie order, exercised through exact ties in u:
+    a graph made of disjoint identical cliques gives exactly equal u entries."""
+    m = 40
+    M = np.eye(m)
+    for c0 in (0, 10, 20):  # three disjoint 4-cliques with identical weights
+        idx = np.arange(c0, c0 + 4)
+        M[np.ix_(idx, idx)] = 1.0
+    engine.plan(1, [m], [1], m=[m])
+    engine.set_dense(0, M, None)
+    sp = cn.SolverParams()
+    for u0 in (np.ones(m), np.linspace(1, 2, m) * 0 + 0.5):
+        sol = engine.solve(u0, want_u=True)
+        ref = coracle.solve(sp, np.triu(M, 1), u0)
+        k = int(sol["n_nodes"][0])
+        assert sol["nodes"][:k].cpu().numpy().tolist() == ref["nodes"]
