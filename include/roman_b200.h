@@ -166,6 +166,7 @@ int rb_set_dense(rb_handle* h, int32_t b, const double* M, const double* C, void
  * it beyond the last bits of u (different summation tree). */
 int rb_set_solver_cluster(rb_handle* h, int32_t ctas_per_problem);
 int rb_get_solver_cluster(const rb_handle* h);
+int rb_get_solver_max_clusters(const rb_handle* h); /* co-resident clusters of that size (after rb_plan) */
 
 /* Device milliseconds of the last rb_align_batch / stage calls, measured with CUDA events on
  * the launch stream: ms[0]=prep(K1a) ms[1]=affinity(K1) ms[2]=solve(K2) ms[3]=arun(K3).

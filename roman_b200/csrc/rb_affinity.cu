@@ -363,7 +363,8 @@ __device__ __forceinline__ void tile_coords(int64_t q, int nb, int& I, int& J) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1: one warp per 32x32 tile, lane = tile column; 32 coalesced 256-byte row stores per tile.
+// K1: one warp per 32x32 tile, lane = tile column; 32 coalesced 256-byte row stores per tile
+// (each row is written as a permutation of itself: the XOR swizzle of rb_common.cuh).
 // Work list = all stored tiles of all problems (flat), grid-strided by a persistent grid.
 __global__ void __launch_bounds__(256) rb_affinity_kernel(const RbProblem* __restrict__ probs, int B,
                                                           const int64_t* __restrict__ tile_prefix,
@@ -409,7 +410,7 @@ __global__ void __launch_bounds__(256) rb_affinity_kernel(const RbProblem* __res
         else if (r > lane) v = pair_score(P, col, row);           // mirrored entry of the diagonal tile
         // r == lane: identity is implicit (clipper.cpp:129-130)
       }
-      out[r * RB_TILE + lane] = v;
+      out[rb_tile_elem(r, lane)] = v;
     }
   }
 }
@@ -429,7 +430,7 @@ __global__ void rb_unpack_kernel(RbProblem pr, const double* __restrict__ Mp, do
     } else {
       const int a = i < j ? i : j, b = i < j ? j : i;
       const int I = a / RB_TILE, J = b / RB_TILE;
-      const double v = Mp[(pr.off_tile + rb_tile_index(I, J, pr.nb)) * RB_TILE_ELEMS + (a % RB_TILE) * RB_TILE + (b % RB_TILE)];
+      const double v = Mp[(pr.off_tile + rb_tile_index(I, J, pr.nb)) * RB_TILE_ELEMS + rb_tile_elem(a % RB_TILE, b % RB_TILE)];
       cv = (__double_as_longlong(v) != 0ll) ? 1.0 : 0.0;
       mv = (cv != 0.0) ? fabs(v) : 0.0;  // -0.0 (constraint-only entry) reads back as 0
     }
@@ -447,7 +448,8 @@ __global__ void rb_pack_kernel(RbProblem pr, const double* __restrict__ Min, con
     const int w = (int)(e - q * RB_TILE_ELEMS);
     int I, J;
     tile_coords(q, pr.nb, I, J);
-    const int i = I * RB_TILE + w / RB_TILE, j = J * RB_TILE + w % RB_TILE;
+    const int wr = w / RB_TILE, wc = (w % RB_TILE) ^ wr;  // inverse of rb_tile_elem
+    const int i = I * RB_TILE + wr, j = J * RB_TILE + wc;
     double v = 0.0;
     if (i < m && j < m && i != j) {
       const int a = i < j ? i : j, b = i < j ? j : i;  // strict upper triangle of the inputs

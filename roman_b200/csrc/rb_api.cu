@@ -26,6 +26,7 @@ struct rb_handle {
   int64_t total_assoc = 0, total_pad = 0, total_tiles = 0, total_obj1 = 0, total_obj2 = 0;
   int32_t max_mp = 0, max_n1 = 0, max_n2 = 0;
   int32_t cluster_req = 0;   // 0 = auto
+  int32_t slots = 2, depth = 8;  // solver shared-memory configuration (rb_solver_config)
   int32_t cluster = 1;       // resolved at plan time
   int32_t max_clusters = 1;  // co-resident clusters of that size
 
@@ -37,6 +38,7 @@ struct rb_handle {
   int32_t* d_pad_i32 = nullptr;                       // 2 padded int arrays
   int32_t* d_counter = nullptr;
   int* d_bad = nullptr;
+  long long* d_debug = nullptr;  // dev builds: per-CTA cycle counters of the solver
   // internal outputs used when the caller passes NULL
   int32_t* d_nodes = nullptr; int32_t* d_sel = nullptr; size_t cap_assoc = 0;
   int32_t* d_nsel = nullptr; double* d_score = nullptr; int32_t* d_ifinal = nullptr; int32_t* d_npass = nullptr;
@@ -45,6 +47,9 @@ struct rb_handle {
   double* s_D1 = nullptr; double* s_D2 = nullptr; size_t cap_sD1 = 0, cap_sD2 = 0;
   int32_t* s_A = nullptr; double* s_u0 = nullptr; size_t cap_sA = 0, cap_su0 = 0;
   cudaStream_t own_stream = nullptr;
+  cudaStream_t last_stream = nullptr;  // stream of the most recent device-pointer stage call
+  bool last_valid = false;
+  cudaEvent_t order_ev = nullptr;
 
   bool affinity_done = false;
   bool profiling = false;
@@ -175,6 +180,7 @@ int rb_destroy(rb_handle* h) {
   cudaFree(h->d_status); cudaFree(h->d_T);
   cudaFree(h->s_D1); cudaFree(h->s_D2); cudaFree(h->s_A); cudaFree(h->s_u0);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->order_ev) cudaEventDestroy(h->order_ev);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return RB_OK;
@@ -217,6 +223,19 @@ int rb_set_solver_cluster(rb_handle* h, int32_t ctas_per_problem) {
 }
 
 int rb_get_solver_cluster(const rb_handle* h) { return h ? h->cluster : 0; }
+int rb_get_solver_max_clusters(const rb_handle* h) { return h ? h->max_clusters : 0; }
+
+/* dev: enable per-CTA cycle counters of the solver and read them back (8 x int64 per CTA, up to 1024 CTAs) */
+int rb_debug_solver_cycles(rb_handle* h, long long* out, int n_ctas) {
+  if (!h) return RB_ERR_ARG;
+  if (!h->d_debug) {
+    RB_CUDA(h, cudaMalloc((void**)&h->d_debug, 1024 * 8 * sizeof(long long)));
+    RB_CUDA(h, cudaMemset(h->d_debug, 0, 1024 * 8 * sizeof(long long)));
+    return RB_OK;
+  }
+  if (out && n_ctas > 0) RB_CUDA(h, cudaMemcpy(out, h->d_debug, (size_t)(n_ctas > 1024 ? 1024 : n_ctas) * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return RB_OK;
+}
 
 int rb_set_profiling(rb_handle* h, int32_t on) {
   if (!h) return RB_ERR_ARG;
@@ -263,14 +282,17 @@ int rb_plan(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const int32_t
     if (n2[b] > mx2) mx2 = n2[b];
   }
   h->tile_prefix[(size_t)B] = ot;
-  const size_t smem = rb_solver_smem_bytes(max_mp, 2);
   int optin = 0;
   RB_CUDA(h, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-  if (smem > (size_t)optin) {
-    char buf[160];
-    snprintf(buf, sizeof buf, "rb_plan: m (padded %d) needs %zu B of shared memory in the solver, device offers %d", max_mp, smem, optin);
+  int slots = 1, depth = 2;
+  if (!rb_solver_config(max_mp, (size_t)optin, &slots, &depth)) {
+    char buf[200];
+    snprintf(buf, sizeof buf, "rb_plan: m (padded %d) does not fit the solver's shared-memory layout (%zu B needed at minimum, device offers %d)",
+             max_mp, rb_solver_smem_bytes(max_mp, 1, 2), optin);
     return fail(h, RB_ERR_TOO_LARGE, buf);
   }
+  h->slots = slots;
+  h->depth = depth;
   h->B = B; h->d = d; h->all_to_all = (m == nullptr);
   h->total_assoc = oa; h->total_pad = op; h->total_tiles = ot; h->total_obj1 = o1; h->total_obj2 = o2;
   h->max_mp = max_mp;
@@ -281,10 +303,13 @@ int rb_plan(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const int32_t
     // cannot leave a long single-SM tail, but never more clusters' worth than there are problems.
     int c = h->cluster_req;
     if (c == 0) {
-      c = 4;
+      // Measured on B200 (profiles/r1_cluster_sweep.txt): 2 CTAs per problem keeps a slow-converging
+      // problem from leaving a long single-SM tail and still uses all 148 SMs (74 clusters);
+      // larger clusters only pay when there are too few problems to fill the chip otherwise.
+      c = 2;
+      if ((int64_t)B * 4 <= h->sm_count) c = 4;
       if ((int64_t)B * 8 <= h->sm_count) c = 8;
       if (max_mp <= 256) c = 1;
-      else if (max_mp <= 1024 && c > 2) c = 2;
     }
     int mc = 0;
     for (;;) {
@@ -379,6 +404,7 @@ int rb_affinity(rb_handle* h, const double* D1, const double* D2, const int32_t*
     return fail(h, RB_ERR_ARG, "rb_affinity: EuclideanDistance invariant supports d <= 3");
   }
   cudaStream_t st = (cudaStream_t)stream;
+  h->last_stream = st; h->last_valid = true;
   const RbDevParams P = dev_params(h);
   const RbAssocSoA rec = soa_of(h);
   record(h, 0, st);
@@ -399,6 +425,7 @@ int rb_solve(rb_handle* h, const double* u0, int32_t* nodes, int32_t* sel, int32
   if (h->B == 0) return RB_OK;
   if (!u0 && h->total_assoc > 0) return fail(h, RB_ERR_ARG, "rb_solve: u0 is required");
   cudaStream_t st = (cudaStream_t)stream;
+  h->last_stream = st; h->last_valid = true;
   RbSolveArgs a;
   a.probs = h->d_probs; a.B = h->B; a.counter = h->d_counter; a.Mp = h->d_M;
   a.i1 = h->d_pad_i32; a.i2 = h->d_pad_i32 + (size_t)h->total_pad;
@@ -414,6 +441,9 @@ int rb_solve(rb_handle* h, const double* u0, int32_t* nodes, int32_t* sel, int32
   a.mp_max = h->max_mp;
   a.pad_stride = h->total_pad;
   a.cluster = h->cluster;
+  a.debug = h->d_debug;
+  a.slots = h->slots;
+  a.depth = h->depth;
   RB_CUDA(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int32_t), st));
   record(h, 3, st);
   RB_CUDA(h, rb_launch_solver(a, h->max_clusters, st));
@@ -486,6 +516,11 @@ int rb_align_batch_host(rb_handle* h, const double* D1, const double* D2, const 
   RB_CUDA(h, cudaSetDevice(h->device));
   if (!h->own_stream) RB_CUDA(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   cudaStream_t st = h->own_stream;
+  if (h->last_valid && h->last_stream != st) {  // scratch may still be in use by work queued on the caller's stream
+    if (!h->order_ev) RB_CUDA(h, cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
+    RB_CUDA(h, cudaEventRecord(h->order_ev, h->last_stream));
+    RB_CUDA(h, cudaStreamWaitEvent(st, h->order_ev, 0));
+  }
   const size_t nD1 = (size_t)h->total_obj1 * h->d, nD2 = (size_t)h->total_obj2 * h->d, nA = (size_t)h->total_assoc;
   int rc;
   if ((rc = ensure(h, &h->s_D1, &h->cap_sD1, nD1))) return rc;

@@ -1,8 +1,11 @@
 // rb_common.cuh — shared types, packed-M layout and small device helpers.
 //
 // Packed affinity layout (one per problem, in HBM):
-//   the m x m symmetric affinity matrix is cut into 32x32 tiles of doubles (8 KB, contiguous,
-//   row-major inside the tile).  Only tiles (I, J) with I <= J are stored, panel by panel:
+//   the m x m symmetric affinity matrix is cut into 32x32 tiles of doubles (8 KB, contiguous).
+//   Inside a tile, element (r, c) sits at word r*32 + (c ^ r): rows stay contiguous 256-byte
+//   segments (coalesced stores in K1), and once the tile is in shared memory both "lane = row"
+//   and "lane = column" sweeps are bank-conflict free, which lets the solver form row sums and
+//   column sums of a tile without any cross-lane reduction.  Only tiles (I, J) with I <= J are stored, panel by panel:
 //   panel I = tiles (I,I), (I,I+1) ... (I,nb-1).  Diagonal tiles hold the full symmetric
 //   tile (both triangles, zero diagonal); everything beyond m is +0.0 padding.
 //   tile_index(I,J) = I*nb - I*(I-1)/2 + (J-I);  n_tiles = nb*(nb+1)/2;  nb = ceil(m/32).
@@ -37,6 +40,9 @@ struct RbAssocSoA {
   double* single;        // single-association score (ROMAN::single_similarity), 1.0 for Euclidean
   int32_t *i1, *i2;      // object indices (A[k,0], A[k,1]); -1 in padding
 };
+
+// word offset of element (r, c) inside a tile (XOR swizzle, see above)
+__host__ __device__ __forceinline__ int rb_tile_elem(int r, int c) { return r * RB_TILE + (c ^ r); }
 
 __host__ __device__ __forceinline__ int64_t rb_tile_index(int I, int J, int nb) {
   return (int64_t)I * nb - ((int64_t)I * (I - 1)) / 2 + (J - I);

@@ -22,6 +22,8 @@ struct RbSolveArgs {
   double* g_work;          // padded scratch: gradient at u
   int64_t pad_stride;      // u_work/g_work hold `cluster` private copies, this many doubles apart
   int32_t cluster;         // CTAs per problem (1, 2, 4, 8)
+  int32_t slots, depth;    // shared-memory configuration chosen by rb_solver_config
+  long long* debug;        // optional per-CTA cycle counters (8 per CTA), or null
   // outputs, user layout (off_assoc); rb_api substitutes handle scratch for NULL user pointers,
   // so only u_out may be null here
   int32_t* nodes;
@@ -46,7 +48,8 @@ cudaError_t rb_launch_pack(const RbProblem& pr, const double* Min, const double*
                            cudaStream_t st);
 
 // Returns cudaErrorInvalidValue if mp_max does not fit the shared-memory layout.
-size_t rb_solver_smem_bytes(int mp_max, int slots);
+size_t rb_solver_smem_bytes(int mp_max, int slots, int depth);
+bool rb_solver_config(int mp_max, size_t optin, int* slots, int* depth);
 cudaError_t rb_solver_prepare(int device);  // opt in to the large dynamic shared-memory carve-out
 cudaError_t rb_solver_max_clusters(int mp_max, int cluster, int* out);
 cudaError_t rb_launch_solver(const RbSolveArgs& a, int max_clusters, cudaStream_t st);

@@ -8,7 +8,7 @@
 //     CTA per SM); clusters pull problems from an atomic queue, so the SMs stream different
 //     problems' packed affinity matrices from HBM: the working set is far larger than L2 and
 //     the kernel is HBM-bound by construction.  C > 1 splits the tiles of one problem over the
-//     CTAs of its cluster (tile column J goes to CTA J mod C) and combines the per-CTA partial
+//     CTAs of its cluster (balanced pairs of tile-rows per CTA) and combines the per-CTA partial
 //     (M x, C x) vectors through distributed shared memory once per pass; it exists to shorten
 //     the tail that a slow-converging problem would otherwise leave on a single SM.
 //     Every CTA of a cluster then runs the (cheap) vector phases redundantly on identical data,
@@ -21,7 +21,9 @@
 //   - each warp runs its own 2-slot TMA ring (issue by lane 0, completion on an mbarrier) over
 //     the tiles (I, J) with J mod 8 == warp, which makes warp (K mod 8) the only writer of the
 //     output block K: no atomics, fixed summation order, bit-reproducible results.
-//     Row partial sums live in registers across a tile-row and are combined once per tile-row.
+//     Tiles are stored XOR-swizzled, so a warp forms a tile's row sums (lane = row) and column
+//     sums (lane = column) straight from shared memory; the 8 warps' row partials of a tile-row
+//     are combined once per tile-row through a small ring, on arrive-only named barriers.
 //   - all scalar control flow of the reference (line search, convergence tests, the d update)
 //     is resolved on the device from block-wide reductions with a fixed tree.
 //   - M x and C x of the accepted iterate are kept, so the d update and the new gradient need
@@ -36,7 +38,8 @@ namespace {
 
 constexpr int NW = 8;         // warps per CTA (all are consumers; each runs its own TMA ring)
 constexpr int NT = NW * 32;   // threads per CTA
-constexpr int SLOTS = 2;      // ring slots per warp (8 KB each)
+constexpr int MAX_SLOTS = 2;  // TMA ring slots per warp (8 KB each); 1 when m is too large for 2
+constexpr int MAX_DEPTH = 8;  // see Smem::depth
 constexpr int RED_DOUBLES = 64;   // [0,32): double-buffered reduction scratch; [40]: broadcast slot
 constexpr int MISC_INTS = 16;
 constexpr int EPT_MAX = 20;       // max vector elements per thread (mp_max <= EPT_MAX * NT)
@@ -73,19 +76,22 @@ __device__ __forceinline__ void tma_load_tile(void* dst, const void* src, uint64
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
-// first tile column J >= I with J mod stride == gw (gw = global warp id inside the cluster)
-__device__ __forceinline__ int first_col(int I, int gw, int stride) { return I + ((gw - I) % stride + stride) % stride; }
 
 struct Smem {
   double* x;     // trial vector (mp)
   double* accM;  // M x (strict), then reused as int scratch in rounding
   double* accC;  // C x (strict)
-  double* part;  // [2][NW][2][32] row partials, double buffered over tile-rows
+  double* part;  // [depth][NW][2][32] row partials, ring over tile-rows
   double* red;   // [2][2*NW] reduction scratch, double buffered
   uint64_t* bar; // [NW][SLOTS]
   double* ring;  // [NW][SLOTS][1024]
   int* misc;     // small ints / broadcast slots
+  int slots;     // TMA ring slots per warp (1 or 2)
+  int depth;     // tile-rows in flight between the fastest and slowest warp: 8 (decoupled) or 2 (lock-step)
 };
 
 struct Reducer {
@@ -120,134 +126,196 @@ struct Reducer {
 
 // One fused pass: accM += M x, accC += C x over the packed upper triangle of one problem.
 // Preconditions: x complete, accM/accC zeroed, all threads past a __syncthreads.
-// With a cluster of C CTAs, tile column J belongs to CTA (J mod C), warp ((J / C) mod NW); the
-// results are this CTA's PARTIAL sums (combined by cluster_combine afterwards).
+//
+// Work split.  Tile-rows are dealt to the C CTAs of the cluster in balanced pairs (tile-row p
+// has nb-p tiles, tile-row nb-1-p has p+1: a pair always has nb+1), pair q going to CTA q mod C;
+// inside a CTA the tiles of a tile-row are dealt to the 8 warps by tile column, J mod 8.  The
+// results are this CTA's PARTIAL sums (combined by cluster_combine afterwards).  Warp (K mod 8)
+// is the only writer of output block K in its CTA: it owns both the column sums of tile column
+// K and the final add of the row sums of tile-row K, so there are no atomics and the summation
+// order is fixed.
+//
+// A tile sits in shared memory in the XOR-swizzled layout of rb_common.cuh, so one warp sweeps
+// it twice without bank conflicts: with lane = row (row sums of block I, one register per lane,
+// no cross-lane reduction) and with lane = column (column sums of block J).
+struct TileIter {
+  int nb, C, w, p, h, I, J;
+  bool ok;
+  __device__ __forceinline__ int row() const { return h == 0 ? p : nb - 1 - p; }
+  // position on the first tile (J >= I, J mod NW == w) at or after tile-row slot (p, h)
+  __device__ __forceinline__ void settle() {
+    const int npairs = (nb + 1) >> 1;
+    while (p < npairs) {
+      if (!(h == 1 && nb - 1 - p == p)) {  // the middle tile-row of an odd nb is visited once
+        I = row();
+        J = I + ((w - I) % NW + NW) % NW;
+        if (J < nb) { ok = true; return; }
+      }
+      if (h == 0) h = 1; else { h = 0; p += C; }
+    }
+    ok = false;
+  }
+  __device__ __forceinline__ void init(int nb_, int C_, int crank, int w_) {
+    nb = nb_; C = C_; w = w_; p = crank; h = 0; I = 0; J = 0;
+    settle();
+  }
+  __device__ __forceinline__ void next() {
+    J += NW;
+    if (J < nb) return;
+    if (h == 0) h = 1; else { h = 0; p += C; }
+    settle();
+  }
+};
+
 __device__ __forceinline__ void matvec_pass(const Smem& S, const double* __restrict__ tiles, int nb,
                                             uint32_t& phase_bits, int C, int crank) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int gw = w * C + crank, stride = NW * C;
-  uint64_t* bar = S.bar + w * SLOTS;
+  const int SLOTS = S.slots;
+  uint64_t* bar = S.bar + w * MAX_SLOTS;
   double* ring = S.ring + (size_t)w * SLOTS * RB_TILE_ELEMS;
 
-  // prefetch iterator over this warp's tile sequence
-  int pfI = 0, pfJ = 0;
-  bool pf_ok = false;
-  for (pfI = 0; pfI < nb; ++pfI) {
-    pfJ = first_col(pfI, gw, stride);
-    if (pfJ < nb) { pf_ok = true; break; }
-  }
+  TileIter pf;  // prefetch iterator: runs SLOTS tiles ahead of the consumer along the same sequence
+  pf.init(nb, C, crank, w);
   auto pf_issue = [&](int slot) {
     if (lane == 0)
-      tma_load_tile(ring + slot * RB_TILE_ELEMS, tiles + rb_tile_index(pfI, pfJ, nb) * RB_TILE_ELEMS, bar + slot);
-    pfJ += stride;
-    while (pfJ >= nb) {
-      ++pfI;
-      if (pfI >= nb) { pf_ok = false; break; }
-      pfJ = first_col(pfI, gw, stride);
-    }
+      tma_load_tile(ring + slot * RB_TILE_ELEMS, tiles + rb_tile_index(pf.I, pf.J, nb) * RB_TILE_ELEMS, bar + slot);
+    pf.next();
   };
-#pragma unroll
   for (int s = 0; s < SLOTS; ++s)
-    if (pf_ok) pf_issue(s);
+    if (pf.ok) pf_issue(s);
 
-  int slot = 0;
-  for (int I = 0; I < nb; ++I) {
-    double rowM[RB_TILE], rowC[RB_TILE];
-#pragma unroll
-    for (int r = 0; r < RB_TILE; ++r) { rowM[r] = 0.0; rowC[r] = 0.0; }
-    const double* xI = S.x + I * RB_TILE;
+  int slot = 0, pos = 0;
+  const int npairs = (nb + 1) >> 1;
+  for (int p = crank; p < npairs; p += C) {
+    for (int h = 0; h < 2; ++h) {
+      const int I = (h == 0) ? p : nb - 1 - p;
+      if (h == 1 && I == p) break;
+      // row sums of block I over this warp's tiles: lane = row; two chains each to shorten the
+      // dependent-add latency
+      double rM0 = 0.0, rM1 = 0.0, rC0 = 0.0, rC1 = 0.0;
+      const double* xI = S.x + I * RB_TILE;
 
-    for (int J = first_col(I, gw, stride); J < nb; J += stride) {
-      mbar_wait(bar + slot, (phase_bits >> slot) & 1u);
-      phase_bits ^= (1u << slot);
-      const double* buf = ring + slot * RB_TILE_ELEMS;
-      const double xJ = S.x[J * RB_TILE + lane];
-      if (J != I) {
-        double colM = 0.0, colC = 0.0;
+      for (int J = I + ((w - I) % NW + NW) % NW; J < nb; J += NW) {
+        mbar_wait(bar + slot, (phase_bits >> slot) & 1u);
+        phase_bits ^= (1u << slot);
+        const double* buf = ring + slot * RB_TILE_ELEMS;
+        const double* xJ = S.x + J * RB_TILE;
+        const double* rowp = buf + lane * RB_TILE;  // this lane's row (row orientation)
+        // An all-(+0.0) tile contributes nothing to either product: find out with 16 wide loads
+        // per lane and one vote, and skip the fp64 work (the bytes were still streamed, as always).
+        unsigned long long any = 0ull;
+        {
+          const ulonglong2* rp2 = reinterpret_cast<const ulonglong2*>(rowp);
 #pragma unroll
-        for (int r = 0; r < RB_TILE; ++r) {
-          const double v = buf[r * RB_TILE + lane];
-          const double xi = xI[r];
-          const bool nz = (__double_as_longlong(v) != 0ll);  // +0.0 <=> no edge (-0.0: constraint-only entry)
-          rowM[r] = fma(v, xJ, rowM[r]);
-          colM = fma(v, xi, colM);
-          if (nz) { rowC[r] += xJ; colC += xi; }
+          for (int t = 0; t < RB_TILE / 2; ++t) {
+            const ulonglong2 q = rp2[t ^ (lane & 15)];  // a permutation of the row's 16-byte chunks, conflict-free
+            any |= q.x | q.y;
+          }
         }
-        // this warp is the only writer of output block J in this CTA
-        S.accM[J * RB_TILE + lane] += colM;
-        S.accC[J * RB_TILE + lane] += colC;
-      } else {
-        // diagonal tile holds both triangles: row sums only
+        if (!__any_sync(0xffffffffu, any != 0ull)) {
+          // nothing to do
+        } else if (J != I) {
+          double cM0 = 0.0, cM1 = 0.0, cC0 = 0.0, cC1 = 0.0;
 #pragma unroll
-        for (int r = 0; r < RB_TILE; ++r) {
-          const double v = buf[r * RB_TILE + lane];
-          const bool nz = (__double_as_longlong(v) != 0ll);
-          rowM[r] = fma(v, xJ, rowM[r]);
-          if (nz) rowC[r] += xJ;
+          for (int t = 0; t < RB_TILE; t += 2) {
+            // row orientation: elements (lane, t), (lane, t+1); x_J[t], x_J[t+1] are broadcasts
+            const double a0 = rowp[t ^ lane], a1 = rowp[(t + 1) ^ lane];
+            const double2 xj = *reinterpret_cast<const double2*>(xJ + t);
+            rM0 = fma(a0, xj.x, rM0);
+            rM1 = fma(a1, xj.y, rM1);
+            if (__double_as_longlong(a0) != 0ll) rC0 += xj.x;  // +0.0 <=> no edge (-0.0: constraint-only)
+            if (__double_as_longlong(a1) != 0ll) rC1 += xj.y;
+            // column orientation: elements (t, lane), (t+1, lane); x_I[t], x_I[t+1] are broadcasts
+            const double b0 = buf[t * RB_TILE + (lane ^ t)], b1 = buf[(t + 1) * RB_TILE + (lane ^ (t + 1))];
+            const double2 xi = *reinterpret_cast<const double2*>(xI + t);
+            cM0 = fma(b0, xi.x, cM0);
+            cM1 = fma(b1, xi.y, cM1);
+            if (__double_as_longlong(b0) != 0ll) cC0 += xi.x;
+            if (__double_as_longlong(b1) != 0ll) cC1 += xi.y;
+          }
+          // this warp is the only writer of output block J in this CTA
+          S.accM[J * RB_TILE + lane] += cM0 + cM1;
+          S.accC[J * RB_TILE + lane] += cC0 + cC1;
+        } else {
+          // diagonal tile holds both triangles: row sums only
+#pragma unroll
+          for (int t = 0; t < RB_TILE; t += 2) {
+            const double a0 = rowp[t ^ lane], a1 = rowp[(t + 1) ^ lane];
+            const double2 xj = *reinterpret_cast<const double2*>(xJ + t);
+            rM0 = fma(a0, xj.x, rM0);
+            rM1 = fma(a1, xj.y, rM1);
+            if (__double_as_longlong(a0) != 0ll) rC0 += xj.x;
+            if (__double_as_longlong(a1) != 0ll) rC1 += xj.y;
+          }
         }
+        __syncwarp();
+        if (pf.ok) pf_issue(slot);  // refill the slot just drained
+        slot = (slot + 1 == SLOTS) ? 0 : slot + 1;
       }
-      __syncwarp();
-      if (pf_ok) pf_issue(slot);  // refill the slot just drained
-      slot = (slot + 1 == SLOTS) ? 0 : slot + 1;
-    }
 
-    // Lane-transpose reduction: afterwards lane r holds this warp's total for row r of block I.
+      // Combine the 8 warps' row partials of block I (fixed order) into this CTA's accumulators.
+      // depth == 8: a warp only WAITS on the tile-row's named barrier when it has to — as the
+      // owner of block I, or once every 8 tile-rows so that nobody runs more than 7 tile-rows
+      // ahead of the slowest warp (the partial ring and the barrier ids are reused modulo 8) —
+      // and otherwise just ARRIVES and moves on, so one warp's late tile does not stall the
+      // CTA's seven other TMA rings.
+      const int pslot = pos % S.depth;
+      double* part = S.part + (size_t)pslot * (NW * 2 * RB_TILE);
+      part[(w * 2 + 0) * RB_TILE + lane] = rM0 + rM1;
+      part[(w * 2 + 1) * RB_TILE + lane] = rC0 + rC1;
+      const bool owner = ((I % NW) == w);
+      if (owner || S.depth < MAX_DEPTH || (pos % NW) == w) named_bar_sync(1 + pslot, NT);
+      else named_bar_arrive(1 + pslot, NT);
+      if (owner) {
+        double sm = 0.0, sc = 0.0;
 #pragma unroll
-    for (int h = 16; h >= 1; h >>= 1) {
-#pragma unroll
-      for (int i = 0; i < h; ++i) {
-        const bool up = (lane & h) != 0;
-        const double sendM = up ? rowM[i] : rowM[i + h];
-        const double keepM = up ? rowM[i + h] : rowM[i];
-        rowM[i] = keepM + __shfl_xor_sync(0xffffffffu, sendM, h);
-        const double sendC = up ? rowC[i] : rowC[i + h];
-        const double keepC = up ? rowC[i + h] : rowC[i];
-        rowC[i] = keepC + __shfl_xor_sync(0xffffffffu, sendC, h);
+        for (int ww = 0; ww < NW; ++ww) {
+          sm += part[(ww * 2 + 0) * RB_TILE + lane];
+          sc += part[(ww * 2 + 1) * RB_TILE + lane];
+        }
+        S.accM[I * RB_TILE + lane] += sm;
+        S.accC[I * RB_TILE + lane] += sc;
       }
-    }
-    double* part = S.part + (size_t)(I & 1) * (NW * 2 * RB_TILE);
-    part[(w * 2 + 0) * RB_TILE + lane] = rowM[0];
-    part[(w * 2 + 1) * RB_TILE + lane] = rowC[0];
-    named_bar_sync(1, NT);
-    if (((I / C) % NW) == w) {  // this CTA's writer of output block I combines the 8 warps in fixed order
-      double sm = 0.0, sc = 0.0;
-#pragma unroll
-      for (int ww = 0; ww < NW; ++ww) {
-        sm += part[(ww * 2 + 0) * RB_TILE + lane];
-        sc += part[(ww * 2 + 1) * RB_TILE + lane];
-      }
-      S.accM[I * RB_TILE + lane] += sm;
-      S.accC[I * RB_TILE + lane] += sc;
+      ++pos;
     }
   }
 }
 
-// Combine the per-CTA partial (accM, accC) of a cluster: every CTA sums all C partial vectors
-// in rank order (bitwise identical result everywhere) and overwrites its own copy with the
-// total.  Two cluster barriers: partials complete -> read; all reads done -> overwrite.
-__device__ __forceinline__ void cluster_combine(const Smem& S, int mp, int C) {
+// Combine the per-CTA partial (accM, accC) of a cluster through distributed shared memory:
+// reduce-scatter (CTA r sums slice r of all C partial vectors, in rank order) then all-gather
+// (it stores the totals of its slice into every CTA's accumulators).  Every CTA ends up with
+// bitwise identical totals.  Three cluster barriers: partials complete -> read; all reads done
+// -> overwrite; all slices delivered.
+__device__ __forceinline__ void cluster_combine(const Smem& S, int mp, int C, int crank) {
   if (C == 1) { __syncthreads(); return; }
   cg::cluster_group cluster = cg::this_cluster();
+  const int L = ((mp / RB_TILE + C - 1) / C) * RB_TILE;  // slice length (multiple of 32)
+  const int lo = crank * L, hi = (lo + L < mp) ? lo + L : mp;
   cluster.sync();
-  double sm[EPT_MAX], sc[EPT_MAX];
+  constexpr int SL = 9;  // slice elements per thread: L <= SL * NT (mp <= 4608 at C = 2)
+  double sm[SL], sc[SL];
 #pragma unroll
-  for (int k = 0; k < EPT_MAX; ++k) { sm[k] = 0.0; sc[k] = 0.0; }
+  for (int k = 0; k < SL; ++k) { sm[k] = 0.0; sc[k] = 0.0; }
   for (int r = 0; r < C; ++r) {
     const double* rm = cluster.map_shared_rank(S.accM, r);
     const double* rc = cluster.map_shared_rank(S.accC, r);
 #pragma unroll
-    for (int k = 0; k < EPT_MAX; ++k) {
-      const int i = threadIdx.x + k * NT;
-      if (i < mp) { sm[k] += rm[i]; sc[k] += rc[i]; }
+    for (int k = 0; k < SL; ++k) {
+      const int i = lo + (int)threadIdx.x + k * NT;
+      if (i < hi) { sm[k] += rm[i]; sc[k] += rc[i]; }
     }
   }
   cluster.sync();
+  for (int r = 0; r < C; ++r) {
+    double* rm = cluster.map_shared_rank(S.accM, r);
+    double* rc = cluster.map_shared_rank(S.accC, r);
 #pragma unroll
-  for (int k = 0; k < EPT_MAX; ++k) {
-    const int i = threadIdx.x + k * NT;
-    if (i < mp) { S.accM[i] = sm[k]; S.accC[i] = sc[k]; }
+    for (int k = 0; k < SL; ++k) {
+      const int i = lo + (int)threadIdx.x + k * NT;
+      if (i < hi) { rm[i] = sm[k]; rc[i] = sc[k]; }
+    }
   }
-  __syncthreads();
+  cluster.sync();
 }
 
 __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
@@ -256,18 +324,20 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
   {
     const size_t mp = (size_t)A.mp_max;
     unsigned char* p = smem_raw;
-    S.ring = (double*)p; p += (size_t)NW * SLOTS * RB_TILE_BYTES;
+    S.slots = A.slots;
+    S.depth = A.depth;
+    S.ring = (double*)p; p += (size_t)NW * A.slots * RB_TILE_BYTES;
     S.x = (double*)p; p += mp * 8;
     S.accM = (double*)p; p += mp * 8;
     S.accC = (double*)p; p += mp * 8;
-    S.part = (double*)p; p += (size_t)2 * NW * 2 * RB_TILE * 8;
+    S.part = (double*)p; p += (size_t)A.depth * NW * 2 * RB_TILE * 8;
     S.red = (double*)p; p += (size_t)RED_DOUBLES * 8;
-    S.bar = (uint64_t*)p; p += (size_t)NW * SLOTS * 8;
+    S.bar = (uint64_t*)p; p += (size_t)NW * MAX_SLOTS * 8;
     S.misc = (int*)p;
   }
   const int tid = threadIdx.x;
   if (tid == 0) {
-    for (int i = 0; i < NW * SLOTS; ++i) mbar_init(S.bar + i, 1);
+    for (int i = 0; i < NW * MAX_SLOTS; ++i) mbar_init(S.bar + i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -279,7 +349,9 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
   const int crank = (int)cluster.block_rank();
   const bool lead = (crank == 0);
 
+  long long t_mv = 0, t_cb = 0, t_tot0 = clock64(), t_q = 0, t_round = 0;
   for (;;) {
+    long long tq0 = clock64();
     // one problem per cluster: rank 0 pulls from the queue and posts the index to every CTA
     cluster.sync();
     if (lead && tid == 0) {
@@ -288,6 +360,7 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
     }
     cluster.sync();
     const int b = S.misc[0];
+    t_q += clock64() - tq0;
     if (b >= A.B) break;
     const RbProblem pr = A.probs[b];
     const int m = pr.m, nb = pr.nb, mp = nb * RB_TILE;
@@ -312,9 +385,9 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
     }
     __syncthreads();
     if (sp.rescale_u0) {
-      matvec_pass(S, tiles, nb, phase, C, crank);
-      ++passes;
-      cluster_combine(S, mp, C);
+      { long long t0 = clock64(); matvec_pass(S, tiles, nb, phase, C, crank); long long t1 = clock64();
+        ++passes;
+        cluster_combine(S, mp, C, crank); t_mv += t1 - t0; t_cb += clock64() - t1; }
     }
     double nrm2 = 0.0;
     for (int i = tid; i < mp; i += NT) {
@@ -336,9 +409,10 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
       }
     }
     sum_u = R.sum1(sum_u);
-    matvec_pass(S, tiles, nb, phase, C, crank);  // (M u, C u) of the normalised start vector
-    ++passes;
-    cluster_combine(S, mp, C);
+    { long long t0 = clock64(); matvec_pass(S, tiles, nb, phase, C, crank);  // (M u, C u) of the normalised start vector
+      long long t1 = clock64();
+      ++passes;
+      cluster_combine(S, mp, C, crank); t_mv += t1 - t0; t_cb += clock64() - t1; }
 
     // ---- initial d (clipper.cpp:271-280)
     double d = 0.0;
@@ -389,9 +463,9 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
             S.accC[i] = 0.0;
           }
           sum_un = R.sum1(su);
-          matvec_pass(S, tiles, nb, phase, C, crank);
-          ++passes;
-          cluster_combine(S, mp, C);
+          { long long t0 = clock64(); matvec_pass(S, tiles, nb, phase, C, crank); long long t1 = clock64();
+            ++passes;
+            cluster_combine(S, mp, C, crank); t_mv += t1 - t0; t_cb += clock64() - t1; }
           // gradFnew, Fnew (clipper.cpp:309-315) and, speculatively, ||unew - u||^2
           double f = 0.0, dd = 0.0;
           for (int i = tid; i < m; i += NT) {
@@ -435,6 +509,7 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
     __syncthreads();
     // every CTA of the cluster holds identical data; rank 0 alone produces the outputs
     if (!lead) continue;
+    long long tr0 = clock64();
     int32_t* nodes = A.nodes + pr.off_assoc;
     int* rank = (int*)S.accM;  // accM is dead from here on
     int n_sel = 0;
@@ -455,18 +530,28 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
         for (int i = tid; i < m; i += NT) npos += (S.x[i] > 0.0) ? 1.0 : 0.0;
         npos = R.sum1(npos);
         const bool only_pos = ((double)k <= npos);  // then no zero can be among the k largest
-        // rank_i = #{j : (x_j, j) > (x_i, i)}  == position in "descending value, larger index first"
+        // candidates = positive entries (all entries if zeros are needed); compacted so that the
+        // O(n^2) ranking below runs over the support of u only
+        int* cand = (int*)S.accC;  // accC is dead from here on
+        if (tid == 0) S.misc[2] = 0;
+        __syncthreads();
         for (int i = tid; i < m; i += NT) {
+          rank[i] = m;  // sentinel: not ranked
+          if (!only_pos || S.x[i] > 0.0) cand[atomicAdd(&S.misc[2], 1)] = i;
+        }
+        __syncthreads();
+        const int nc = S.misc[2];
+        // rank_i = #{j : (x_j, j) > (x_i, i)}  == position in "descending value, larger index first"
+        for (int c = tid; c < nc; c += NT) {
+          const int i = cand[c];
           const double xi = S.x[i];
-          int rk = m;  // sentinel: not ranked
-          if (!only_pos || xi > 0.0) {
-            rk = 0;
-            for (int j = 0; j < m; ++j) {
-              const double xj = S.x[j];
-              rk += (xj > xi || (xj == xi && j > i)) ? 1 : 0;
-            }
-            if (rk == k - 1) S.red[40] = xi;  // value of the k-th largest (unique writer)
+          int rk = 0;
+          for (int q = 0; q < nc; ++q) {
+            const int j = cand[q];
+            const double xj = S.x[j];
+            rk += (xj > xi || (xj == xi && j > i)) ? 1 : 0;
           }
+          if (rk == k - 1) S.red[40] = xi;  // value of the k-th largest (unique writer)
           rank[i] = rk;
         }
         __syncthreads();
@@ -527,14 +612,28 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
       A.ifinal[b] = i_ol;
       A.n_passes[b] = passes;
     }
+    t_round += clock64() - tr0;
+  }
+  if (A.debug && tid == 0) {
+    long long* d = A.debug + (size_t)blockIdx.x * 8;
+    d[0] = clock64() - t_tot0; d[1] = t_mv; d[2] = t_cb; d[3] = t_q; d[4] = t_round;
   }
 }
 
 }  // namespace
 
-size_t rb_solver_smem_bytes(int mp_max, int /*slots*/) {
-  return (size_t)NW * SLOTS * RB_TILE_BYTES + (size_t)3 * mp_max * 8 + (size_t)2 * NW * 2 * RB_TILE * 8 +
-         (size_t)RED_DOUBLES * 8 + (size_t)NW * SLOTS * 8 + (size_t)MISC_INTS * 4;
+size_t rb_solver_smem_bytes(int mp_max, int slots, int depth) {
+  return (size_t)NW * slots * RB_TILE_BYTES + (size_t)3 * mp_max * 8 + (size_t)depth * NW * 2 * RB_TILE * 8 +
+         (size_t)RED_DOUBLES * 8 + (size_t)NW * MAX_SLOTS * 8 + (size_t)MISC_INTS * 4;
+}
+
+// Largest shared-memory configuration that fits: (2 slots, depth 8) > (2, 2) > (1, 2).
+bool rb_solver_config(int mp_max, size_t optin, int* slots, int* depth) {
+  static const int cfg[3][2] = {{2, MAX_DEPTH}, {2, 2}, {1, 2}};
+  if (mp_max > EPT_MAX * NT) return false;
+  for (auto& c : cfg)
+    if (rb_solver_smem_bytes(mp_max, c[0], c[1]) <= optin) { *slots = c[0]; *depth = c[1]; return true; }
+  return false;
 }
 
 static size_t g_max_optin = 0;
@@ -566,13 +665,15 @@ static void fill_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int 
 cudaError_t rb_solver_max_clusters(int mp_max, int cluster, int* out) {
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  fill_config(cfg, attr, cluster, cluster, rb_solver_smem_bytes(mp_max, SLOTS), nullptr);
+  int slots = 1, depth = 2;
+  if (!rb_solver_config(mp_max, g_max_optin, &slots, &depth)) return cudaErrorInvalidValue;
+  fill_config(cfg, attr, cluster, cluster, rb_solver_smem_bytes(mp_max, slots, depth), nullptr);
   return cudaOccupancyMaxActiveClusters(out, rb_solver_kernel, &cfg);
 }
 
 cudaError_t rb_launch_solver(const RbSolveArgs& a, int max_clusters, cudaStream_t st) {
   if (a.B == 0) return cudaSuccess;
-  const size_t smem = rb_solver_smem_bytes(a.mp_max, SLOTS);
+  const size_t smem = rb_solver_smem_bytes(a.mp_max, a.slots, a.depth);
   if (g_max_optin && smem > g_max_optin) return cudaErrorInvalidValue;
   if (a.mp_max > EPT_MAX * NT) return cudaErrorInvalidValue;
   int nclusters = a.B < max_clusters ? a.B : max_clusters;
