@@ -182,7 +182,7 @@ def run_b200(args):
     D1d, D2d, u0d = D1p.to(dev), D2p.to(dev), u0p.to(dev)
     res = eng.alloc_result()
     rec = torch.zeros((B, 20), dtype=torch.float64, device=dev)       # status, n_inliers, F, pad, T[16]
-    gathered = torch.zeros((world * B, 20), dtype=torch.float64, device=dev) if world > 1 else None
+    gathered = torch.zeros((world * B, 20), dtype=torch.float64, device=dev) if world > 1 else None  # (rank-major)
 
     def step():
         eng.align_batch(D1d, D2d, u0d, out=res)

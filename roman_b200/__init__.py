@@ -7,3 +7,14 @@ the C ABI of include/roman_b200.h, plus the Python host layer that mirrors the r
 `clipperpy` module and `roman.align` registration classes.
 """
 __version__ = "0.1.0"
+
+
+def install_as_clipperpy():
+    """Register roman_b200.clipperpy under the module name `clipperpy`, so that an unmodified
+    `roman.align` (which does `import clipperpy`) runs on the B200 path."""
+    import sys
+    from . import clipperpy as _cp
+    sys.modules["clipperpy"] = _cp
+    sys.modules["clipperpy.invariants"] = _cp.invariants
+    sys.modules["clipperpy.utils"] = _cp.utils
+    return _cp

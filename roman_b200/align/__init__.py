@@ -1,0 +1,15 @@
+"""
+Host-side mirror of the reference's roman.align registration interface for the CLIPPER path
+(same class names, argument meaning, return types and exceptions), plus the batched entry point
+`register_batch` that the GPU path is built for.
+
+  object_registration.py   <- roman/align/object_registration.py
+  roman_registration.py    <- roman/align/roman_registration.py
+  dist_reg_with_pruning.py <- roman/align/dist_reg_with_pruning.py
+  params.py                <- roman/params/submap_align_params.py (registration-related part)
+"""
+from .object_registration import InsufficientAssociationsException, ObjectRegistration  # noqa: F401
+from .roman_registration import FusionMethod, ROMANParams, ROMANRegistration  # noqa: F401
+from .dist_reg_with_pruning import DistRegWithPruning, GravityConstraintError  # noqa: F401
+from .params import SubmapAlignParams  # noqa: F401
+from .objects import SimpleObject  # noqa: F401

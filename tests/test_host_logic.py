@@ -1,0 +1,198 @@
+"""
+CPU tests of the host side: the C-ABI library loads and exports every symbol the header declares
+(no compute calls without a GPU), the clipperpy-compatible surface exists, the registration
+factory mirrors the reference's method table, the generator is deterministic, and the multi-rank
+driver logic (round-robin partition + one all-gather of fixed-size records) works at world_size 2
+over gloo.
+"""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from roman_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "roman_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(rb_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = _lib.load()  # resolves every symbol in _lib.SIGNATURES
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert b"sm_100a" in lib.rb_version()
+
+
+def test_struct_layouts_match_defaults():
+    import ctypes as C
+    from roman_b200 import _lib
+    lib = _lib.load()
+    ip, sp = _lib.RbInvariantParams(), _lib.RbSolverParams()
+    lib.rb_default_invariant_params(C.byref(ip))
+    lib.rb_default_solver_params(C.byref(sp))
+    # reference defaults: roman.h:27-53, clipper.h:27-60
+    assert (ip.point_dim, ip.sigma, ip.epsilon, ip.cosine_min, ip.cosine_max, ip.drift_scale) == (3, 0.01, 0.06, 0.85, 0.95, 0.1)
+    assert (sp.tol_u, sp.tol_F, sp.maxiniters, sp.maxoliters, sp.beta, sp.maxlsiters) == (1e-8, 1e-9, 200, 1000, 0.25, 99)
+    assert (sp.eps, sp.affinityeps, sp.rescale_u0, sp.rounding) == (1e-9, 1e-4, 1, 2)
+
+
+def test_engine_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from roman_b200.engine import Engine, RomanB200Error
+    with pytest.raises(RomanB200Error):
+        Engine()
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under roman_b200/ may reference it."""
+    for dp, _, files in os.walk(os.path.join(ROOT, "roman_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dp, f)
+                assert "clipper_oracle" not in src and "liboracle" not in src, os.path.join(dp, f)
+
+
+def test_clipperpy_surface():
+    """Names roman.align touches in the reference module."""
+    import roman_b200
+    cp = roman_b200.install_as_clipperpy()
+    import clipperpy
+    assert clipperpy is cp
+    for name in ["CLIPPER", "CLIPPERPairwiseAndSingle", "Params", "Rounding", "Solution", "invariants", "utils", "__version__"]:
+        assert hasattr(cp, name)
+    for name in ["ROMANParams", "ROMAN", "EuclideanDistanceParams", "EuclideanDistance", "PairwiseInvariant"]:
+        assert hasattr(cp.invariants, name)
+    assert (cp.invariants.ROMAN.GEOMETRIC_MEAN, cp.invariants.ROMAN.ARITHMETIC_MEAN, cp.invariants.ROMAN.PRODUCT) == (0, 1, 2)
+    assert cp.Rounding.DSD_HEU == cp.DSD_HEU == 2
+    p = cp.invariants.ROMANParams()
+    for attr in ["point_dim", "ratio_feature_dim", "cos_feature_dim", "fusion_method", "sigma", "epsilon", "mindist",
+                 "distance_weight", "ratio_weight", "cosine_weight", "ratio_epsilon", "cosine_min", "cosine_max",
+                 "gravity_guided", "gravity_unc_ang_rad", "drift_aware", "drift_scale_sigma", "drift_scale"]:
+        assert hasattr(p, attr)
+    q = cp.Params()
+    for attr in ["tol_u", "tol_F", "tol_Fop", "maxiniters", "maxoliters", "beta", "maxlsiters", "eps", "affinityeps",
+                 "rescale_u0", "rounding"]:
+        assert hasattr(q, attr)
+    A = cp.utils.create_all_to_all(4, 3)
+    assert A.dtype == np.int32 and A.shape == (12, 2) and tuple(A[7]) == (2, 1)
+    # k2ij enumerates the strict upper triangle row by row (utils.cpp:87-97)
+    n = 7
+    assert [cp.utils.k2ij(k, n) for k in range(n * (n - 1) // 2)] == [(i, j) for i in range(n) for j in range(i + 1, n)]
+
+
+def test_registration_factory_method_table():
+    from roman_b200.align import SubmapAlignParams, ROMANRegistration, DistRegWithPruning
+    expect = {  # method: (ratio_feature_dim, cos_feature_dim, gravity) — reference submap_align_params.py:98-108
+        "clipper": (0, 0, False), "gravity": (0, 0, True), "pcavolgrav": (4, 0, True), "extentvolgrav": (4, 0, True),
+        "roman": (4, 768, True), "sevg": (4, 768, True), "spv": (4, 0, False), "semanticgrav": (0, 768, True),
+        "spvg": (4, 768, True), "roman_no_semantics": (4, 0, True)}
+    for method, (r, c, g) in expect.items():
+        reg = SubmapAlignParams(method=method).get_object_registration()
+        assert isinstance(reg, ROMANRegistration)
+        ip = reg.iparams
+        assert (ip.ratio_feature_dim, ip.cos_feature_dim, bool(ip.gravity_guided)) == (r, c, g)
+        assert (ip.sigma, ip.epsilon, ip.mindist, ip.cosine_min, ip.cosine_max) == (0.4, 0.6, 0.2, 0.5, 0.7)
+        assert ip.gravity_unc_ang_rad == (0.0872665 if g else 0.0)
+    assert isinstance(SubmapAlignParams(method="clipper+prune").get_object_registration(), DistRegWithPruning)
+    with pytest.raises(AssertionError):
+        SubmapAlignParams(method="nope").get_object_registration()
+
+
+def test_object_row_packing_matches_reference_order():
+    """[centre | lin, plan, scat | volume | sorted extent | descriptor] (roman_registration.py:98-108)"""
+    from roman_b200.align import ROMANParams, ROMANRegistration, SimpleObject
+    ob = SimpleObject(center=np.array([1.0, 2.0, 3.0]), volume=7.0, linearity=0.1, planarity=0.2, scattering=0.3,
+                      extent=np.array([3.0, 1.0, 2.0]), semantic_descriptor=np.array([9.0, 8.0]))
+    reg = ROMANRegistration(ROMANParams(volume=True, pca=True, extent=True, semantics_dim=2))
+    assert reg._object_to_clipper_list(ob) == [1, 2, 3, 0.1, 0.2, 0.3, 7, 1, 2, 3, 9, 8]
+    reg = ROMANRegistration(ROMANParams(volume=True))
+    assert reg._object_to_clipper_list(ob) == [1, 2, 3, 7]
+    assert reg.register([], [ob]).shape == (1, 0)  # np.array([[]]) for an empty map (object_registration.py:23-24)
+
+
+def test_prune_mask_equals_reference_row_deletion():
+    """DistRegWithPruning.putative_associations == np.delete on the all-to-all list (dist_reg_with_pruning.py:60-79)."""
+    from roman_b200.align import DistRegWithPruning, SimpleObject
+    from roman_b200.clipperpy.utils import create_all_to_all
+    rng = np.random.default_rng(4)
+    mk = lambda n: [SimpleObject(center=rng.normal(size=3), volume=rng.uniform(0.1, 2), linearity=rng.uniform(0.1, 1),
+                                 planarity=rng.uniform(0.1, 1), scattering=rng.uniform(0.1, 1),
+                                 semantic_descriptor=(lambda v: v / np.linalg.norm(v))(rng.normal(size=6) + 1.5))
+                    for _ in range(n)]
+    m1, m2 = mk(9), mk(11)
+    reg = DistRegWithPruning(sigma=0.4, epsilon=0.6, shape_epsilon=0.3, cos_min=0.6)
+    A_all = create_all_to_all(9, 11)
+    d1 = np.array([o.semantic_descriptor for o in m1]); d2 = np.array([o.semantic_descriptor for o in m2])
+    A_put = np.delete(A_all, ((d1 @ d2.T) < 0.6)[A_all[:, 0], A_all[:, 1]], axis=0)
+    s = lambda objs, idx: np.array([[o.volume, o.linearity, o.planarity, o.scattering] for o in objs])[idx]
+    comb = np.stack([s(m1, A_put[:, 0]), s(m2, A_put[:, 1])], axis=2)
+    A_put = np.delete(A_put, np.any((comb.min(axis=2) / comb.max(axis=2)) < 0.3, axis=1), axis=0)
+    assert np.array_equal(reg.putative_associations(m1, m2), A_put)
+
+
+def test_synth_is_deterministic_and_shaped():
+    from roman_b200 import synth
+    a, b = synth.make_pair(5, 40, 50), synth.make_pair(5, 40, 50)
+    assert np.array_equal(a.D1, b.D1) and np.array_equal(a.u0, b.u0)
+    assert a.D1.shape == (40, 775) and a.D2.shape == (50, 775) and a.u0.shape == (2000,)
+    assert a.n_inliers == 20
+    assert np.allclose(np.linalg.norm(a.D1[:, 7:], axis=1), 1.0)
+    got = (a.centres2[:20] @ a.T_gt[:3, :3].T) + a.T_gt[:3, 3]
+    assert np.abs(got - a.centres1[:20]).max() < 0.3  # planted matches, 5 cm noise
+
+
+def test_shard_roundtrip_single_process():
+    from roman_b200 import dist as rd
+    for n, world in [(10, 1), (10, 3), (7, 8), (0, 2)]:
+        idx = [rd.shard_indices(n, world, r) for r in range(world)]
+        assert sorted(np.concatenate(idx).tolist()) == list(range(n))
+        assert max((len(i) for i in idx), default=0) <= rd.shard_size(n, world)
+
+
+WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from roman_b200 import dist as rd
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+n = 11
+mine = rd.shard_indices(n, world, rank)
+# fake per-pair results that encode the global index, so the reassembly can be checked exactly
+status = (mine % 2).astype(np.int32)
+assoc = [np.stack([np.arange(g % 5 + 1), np.arange(g % 5 + 1) + g], axis=1).astype(np.int32) for g in mine]
+T = np.tile(np.eye(4), (len(mine), 1, 1)); T[:, 0, 3] = mine
+slots = rd.shard_size(n, world)
+rec = rd.pack_records(status, [len(a) for a in assoc], mine * 0.5, T, slots)
+inl = rd.pack_inliers(assoc, slots, 8)
+out = rd.unshard(*((lambda r, i: (r, n, i))(*rd.all_gather_records(rec, inl))))
+assert out["status"].tolist() == [g % 2 for g in range(n)]
+assert np.allclose(out["score"], np.arange(n) * 0.5)
+assert np.allclose(out["T"][:, 0, 3], np.arange(n))
+for g in range(n):
+    assert out["inliers"][g].tolist() == [[k, k + g] for k in range(g % 5 + 1)], (g, out["inliers"][g])
+dist.barrier()
+if rank == 0:
+    print("GLOO_OK")
+dist.destroy_process_group()
+'''
+
+
+def test_all_gather_of_records_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    port = 29500 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script), ROOT]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env={**os.environ, "OMP_NUM_THREADS": "1"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "GLOO_OK" in r.stdout
