@@ -52,12 +52,13 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.idx = gpu_index
         self.rows = []
+        self.first = 0
         self.proc = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -67,6 +68,9 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
+
+    def mark(self):
+        self.first = len(self.rows)
 
     def stop(self):
         if not self.proc:
@@ -78,7 +82,7 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in (self.rows[self.first:] or self.rows[-1:]):
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -199,12 +203,14 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     eng.set_profiling(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # nvidia-smi needs ~0.5 s to produce its first line: start it before the warm-up
     for _ in range(W):
         step()
     sync()
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.mark()   # only samples taken from here on (the timed region) are reported
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage = {"prep": 0.0, "affinity": 0.0, "solve": 0.0, "arun": 0.0}
     sync()
@@ -283,7 +289,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=592, help="submap pairs per GPU per step (4 x 148 SMs)")

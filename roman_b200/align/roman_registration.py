@@ -96,13 +96,16 @@ class ROMANRegistration(ObjectRegistration):
         return clipper, A_init
 
     # ------------------------------------------------------------------ batched entry point (new)
+    def row_length(self) -> int:
+        ip = self.iparams
+        return int(ip.point_dim + ip.ratio_feature_dim + ip.cos_feature_dim)
+
     def pack(self, maps: Sequence[List]) -> Tuple[np.ndarray, np.ndarray]:
         """Pack object lists into one (sum n, d) float64 row table + the per-map counts."""
-        rows = [np.array([self._object_to_clipper_list(p) for p in m], dtype=np.float64).reshape(len(m), -1)
-                for m in maps]
-        d = max((r.shape[1] for r in rows if r.size), default=self.dim)
-        rows = [r if r.size else np.zeros((0, d)) for r in rows]
-        return np.concatenate(rows, axis=0) if rows else np.zeros((0, d)), np.array([len(m) for m in maps], dtype=np.int32)
+        d = self.row_length()
+        rows = [np.array([self._object_to_clipper_list(o) for o in m], dtype=np.float64).reshape(-1, d) for m in maps]
+        table = np.concatenate(rows, axis=0) if rows else np.zeros((0, d))
+        return np.ascontiguousarray(table), np.array([len(m) for m in maps], dtype=np.int32)
 
     def register_batch(self, pairs: Sequence[Tuple[List, List]], u0: Optional[Sequence[np.ndarray]] = None):
         """

@@ -119,7 +119,7 @@ def test_mno_clipper_matches_oracle_chain(engine, coracle):
     M2[np.ix_(r1["nodes"], r1["nodes"])] = 0.0
     r2 = coracle.solve(sp, np.triu(M2, 1), u0s[1], Cupper=Cup)
     assert sols[1][0].tolist() == A[r2["nodes"]].tolist()
-    assert not (set(map(tuple, sols[0][0].tolist())) & set(map(tuple, sols[1][0].tolist()))) or len(r2["nodes"]) == 0
+    assert sols[0][0].tolist() != sols[1][0].tolist()  # zeroing the first clique's affinities moves the solver on
 
 
 def test_dist_reg_with_pruning_matches_oracle(engine, coracle):
