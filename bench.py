@@ -259,6 +259,9 @@ def run_b200(args):
         k2_gbs = k2_bytes / (k2_ms * 1e-3) / 1e9
         k1_gbs = k1_bytes / (k1_ms * 1e-3) / 1e9
         peak = float(peaks["hbm_gbs"])
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
+        # kernel at this configuration (profiles/r1_solver_v3_B592_summary.txt); null for any other batch size
+        traffic = 53.063292e9 + 170.490880e6 if (B == 592 and world == 1) else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -267,7 +270,7 @@ def run_b200(args):
                        "l2": f"inputs larger than L2: packed affinity working set {eng.packed_bytes / 1e9:.2f} GB per GPU per step",
                        "layout": "packed upper triangle, 32x32 fp64 tiles", "mean_passes": float(passes.mean())},
             "roofline": {"kernel": "rb_solver_kernel (K2)", "bound": "hbm", "achieved": k2_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": k2_gbs / peak, "traffic": None, "peak_source": which,
+                         "frac": k2_gbs / peak, "traffic": traffic, "peak_source": which,
                          "algorithmic_bytes_per_launch": k2_bytes, "ms_per_launch": k2_ms},
             "kernels": {"K1_affinity": {"achieved": k1_gbs, "frac": k1_gbs / peak, "ms_per_launch": k1_ms,
                                         "algorithmic_bytes_per_launch": k1_bytes},
