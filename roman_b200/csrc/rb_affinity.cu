@@ -368,11 +368,12 @@ __device__ __forceinline__ void tile_coords(int64_t q, int nb, int& I, int& J) {
 // Work list = all stored tiles of all problems (flat), grid-strided by a persistent grid.
 __global__ void __launch_bounds__(256) rb_affinity_kernel(const RbProblem* __restrict__ probs, int B,
                                                           const int64_t* __restrict__ tile_prefix,
-                                                          int64_t total_tiles, RbAssocSoA rec,
+                                                          int64_t tile_base, int64_t total_tiles, RbAssocSoA rec,
                                                           double* __restrict__ Mp, RbDevParams P) {
   __shared__ Rec s_row[8][RB_TILE];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int64_t t = (int64_t)blockIdx.x * 8 + warp; t < total_tiles; t += (int64_t)gridDim.x * 8) {
+  for (int64_t tt = (int64_t)blockIdx.x * 8 + warp; tt < total_tiles; tt += (int64_t)gridDim.x * 8) {
+    const int64_t t = tt + tile_base;  // probs / tile_prefix point at the first problem of the launched range
     int lo = 0, hi = B;  // largest b with tile_prefix[b] <= t
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
@@ -486,14 +487,14 @@ cudaError_t rb_launch_prep(const RbProblem* probs, int B, int max_mp, int max_n1
   return cudaGetLastError();
 }
 
-cudaError_t rb_launch_affinity(const RbProblem* probs, int B, const int64_t* tile_prefix, int64_t total_tiles,
-                               const RbAssocSoA& rec, double* Mp, const RbDevParams& P, int sm_count,
-                               cudaStream_t st) {
+cudaError_t rb_launch_affinity(const RbProblem* probs, int B, const int64_t* tile_prefix, int64_t tile_base,
+                               int64_t total_tiles, const RbAssocSoA& rec, double* Mp, const RbDevParams& P,
+                               int sm_count, cudaStream_t st) {
   if (total_tiles == 0) return cudaSuccess;
   int64_t want = (total_tiles + 7) / 8;
   const int64_t cap = (int64_t)sm_count * 8;  // 8 CTAs of 256 threads per SM, persistent
   const int grid = (int)(want < cap ? want : cap);
-  rb_affinity_kernel<<<grid, 256, 0, st>>>(probs, B, tile_prefix, total_tiles, rec, Mp, P);
+  rb_affinity_kernel<<<grid, 256, 0, st>>>(probs, B, tile_prefix, tile_base, total_tiles, rec, Mp, P);
   return cudaGetLastError();
 }
 

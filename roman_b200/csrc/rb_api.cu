@@ -47,6 +47,11 @@ struct rb_handle {
   double* s_D1 = nullptr; double* s_D2 = nullptr; size_t cap_sD1 = 0, cap_sD2 = 0;
   int32_t* s_A = nullptr; double* s_u0 = nullptr; size_t cap_sA = 0, cap_su0 = 0;
   cudaStream_t own_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaStream_t own_stream2 = nullptr;  // second compute stream: consecutive ranges alternate, so the next range's
+                                       // kernels fill the SMs the previous range's solver tail leaves idle
+  cudaEvent_t join_ev = nullptr;
+  cudaEvent_t chunk_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t last_stream = nullptr;  // stream of the most recent device-pointer stage call
   bool last_valid = false;
   cudaEvent_t order_ev = nullptr;
@@ -162,7 +167,7 @@ int rb_create(rb_handle** out, int device) {
   h->sm_count = sm;
   e = rb_solver_prepare(device);
   if (e != cudaSuccess) { delete h; return RB_ERR_CUDA; }
-  if (cudaMalloc((void**)&h->d_counter, sizeof(int32_t)) != cudaSuccess ||
+  if (cudaMalloc((void**)&h->d_counter, 8 * sizeof(int32_t)) != cudaSuccess ||
       cudaMalloc((void**)&h->d_bad, sizeof(int)) != cudaSuccess) {
     delete h;
     return RB_ERR_ALLOC;
@@ -182,6 +187,10 @@ int rb_destroy(rb_handle* h) {
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->order_ev) cudaEventDestroy(h->order_ev);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->own_stream2) cudaStreamDestroy(h->own_stream2);
+  if (h->join_ev) cudaEventDestroy(h->join_ev);
+  for (auto& e : h->chunk_ev) if (e) cudaEventDestroy(e);
   delete h;
   return RB_OK;
 }
@@ -390,10 +399,13 @@ int64_t rb_packed_bytes(const rb_handle* h) {
   return h->total_tiles * (int64_t)RB_TILE_BYTES;
 }
 
-int rb_affinity(rb_handle* h, const double* D1, const double* D2, const int32_t* A, void* stream) {
-  if (!h) return RB_ERR_ARG;
+// ---- stage launches on a contiguous range [b0, b1) of the planned problems --------------------
+// (the public stage calls use the whole batch; rb_align_batch_host pipelines sub-ranges)
+namespace {
+
+int check_affinity_args(rb_handle* h, const double* D1, const double* D2, const int32_t* A) {
   if (!h->planned) return fail(h, RB_ERR_NOPLAN, "rb_affinity before rb_plan");
-  if (h->B == 0) { h->affinity_done = true; return RB_OK; }
+  if (h->B == 0) return RB_OK;
   if (!D1 || !D2) return fail(h, RB_ERR_ARG, "rb_affinity: null feature table");
   if (!h->all_to_all && !A) return fail(h, RB_ERR_ARG, "rb_affinity: plan has explicit associations but A is null");
   const rb_invariant_params& p = h->inv;
@@ -403,16 +415,74 @@ int rb_affinity(rb_handle* h, const double* D1, const double* D2, const int32_t*
   } else if (h->d > 3) {
     return fail(h, RB_ERR_ARG, "rb_affinity: EuclideanDistance invariant supports d <= 3");
   }
-  cudaStream_t st = (cudaStream_t)stream;
-  h->last_stream = st; h->last_valid = true;
+  return RB_OK;
+}
+
+int affinity_range(rb_handle* h, int b0, int b1, const double* D1, const double* D2, const int32_t* A, cudaStream_t st) {
+  if (b1 <= b0) return RB_OK;
   const RbDevParams P = dev_params(h);
   const RbAssocSoA rec = soa_of(h);
   record(h, 0, st);
-  RB_CUDA(h, rb_launch_prep(h->d_probs, h->B, h->max_mp, h->max_n1, h->max_n2, h->all_to_all, rec, D1, D2,
+  RB_CUDA(h, rb_launch_prep(h->d_probs + b0, b1 - b0, h->max_mp, h->max_n1, h->max_n2, h->all_to_all, rec, D1, D2,
                             h->all_to_all ? nullptr : A, P, st));
   record(h, 1, st);
-  RB_CUDA(h, rb_launch_affinity(h->d_probs, h->B, h->d_tile_prefix, h->total_tiles, rec, h->d_M, P, h->sm_count, st));
+  const int64_t base = h->tile_prefix[(size_t)b0];
+  RB_CUDA(h, rb_launch_affinity(h->d_probs + b0, b1 - b0, h->d_tile_prefix + b0, base,
+                                h->tile_prefix[(size_t)b1] - base, rec, h->d_M, P, h->sm_count, st));
   record(h, 2, st);
+  return RB_OK;
+}
+
+int solve_range(rb_handle* h, int b0, int b1, int queue, const double* u0, int32_t* nodes, int32_t* sel,
+                int32_t* n_nodes, double* u, double* score, int32_t* ifinal, int32_t* n_passes, cudaStream_t st) {
+  if (b1 <= b0) return RB_OK;
+  RbSolveArgs a;
+  a.probs = h->d_probs + b0; a.B = b1 - b0; a.counter = h->d_counter + queue; a.Mp = h->d_M;
+  a.i1 = h->d_pad_i32; a.i2 = h->d_pad_i32 + (size_t)h->total_pad;
+  a.u0 = u0; a.u_work = u_work(h); a.g_work = g_work(h);
+  a.nodes = nodes ? nodes : h->d_nodes;            // per-association arrays are addressed by absolute offsets
+  a.sel = sel ? sel : h->d_sel;
+  a.n_nodes = (n_nodes ? n_nodes : h->d_nsel) + b0;  // per-problem arrays are indexed relative to the range
+  a.u_out = u;
+  a.score = (score ? score : h->d_score) + b0;
+  a.ifinal = (ifinal ? ifinal : h->d_ifinal) + b0;
+  a.n_passes = (n_passes ? n_passes : h->d_npass) + b0;
+  a.sp = h->sol;
+  a.mp_max = h->max_mp;
+  a.pad_stride = h->total_pad;
+  a.cluster = h->cluster;
+  a.debug = h->d_debug;
+  a.slots = h->slots;
+  a.depth = h->depth;
+  RB_CUDA(h, cudaMemsetAsync(h->d_counter + queue, 0, sizeof(int32_t), st));
+  record(h, 3, st);
+  RB_CUDA(h, rb_launch_solver(a, h->max_clusters, st));
+  record(h, 4, st);
+  return RB_OK;
+}
+
+int arun_range(rb_handle* h, int b0, int b1, const double* D1, const double* D2, const int32_t* sel,
+               const int32_t* n_sel, double* T, int32_t* status, cudaStream_t st) {
+  if (b1 <= b0) return RB_OK;
+  const int pd = h->inv.kind == RB_INVARIANT_ROMAN ? h->inv.point_dim : (h->d < 3 ? h->d : 3);
+  if (pd < 2) return fail(h, RB_ERR_ARG, "rb_arun: point dimension must be 2 or 3");
+  record(h, 5, st);
+  RB_CUDA(h, rb_launch_arun(h->d_probs + b0, b1 - b0, pd, D1, D2, sel, n_sel + b0, (T ? T : h->d_T) + (size_t)b0 * 16,
+                            (status ? status : h->d_status) + b0, st));
+  record(h, 6, st);
+  return RB_OK;
+}
+
+}  // namespace
+
+int rb_affinity(rb_handle* h, const double* D1, const double* D2, const int32_t* A, void* stream) {
+  if (!h) return RB_ERR_ARG;
+  int rc = check_affinity_args(h, D1, D2, A);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  h->last_stream = st; h->last_valid = true;
+  rc = affinity_range(h, 0, h->B, D1, D2, A, st);
+  if (rc) return rc;
   h->affinity_done = true;
   return RB_OK;
 }
@@ -426,29 +496,7 @@ int rb_solve(rb_handle* h, const double* u0, int32_t* nodes, int32_t* sel, int32
   if (!u0 && h->total_assoc > 0) return fail(h, RB_ERR_ARG, "rb_solve: u0 is required");
   cudaStream_t st = (cudaStream_t)stream;
   h->last_stream = st; h->last_valid = true;
-  RbSolveArgs a;
-  a.probs = h->d_probs; a.B = h->B; a.counter = h->d_counter; a.Mp = h->d_M;
-  a.i1 = h->d_pad_i32; a.i2 = h->d_pad_i32 + (size_t)h->total_pad;
-  a.u0 = u0; a.u_work = u_work(h); a.g_work = g_work(h);
-  a.nodes = nodes ? nodes : h->d_nodes;
-  a.sel = sel ? sel : h->d_sel;
-  a.n_nodes = n_nodes ? n_nodes : h->d_nsel;
-  a.u_out = u;
-  a.score = score ? score : h->d_score;
-  a.ifinal = ifinal ? ifinal : h->d_ifinal;
-  a.n_passes = n_passes ? n_passes : h->d_npass;
-  a.sp = h->sol;
-  a.mp_max = h->max_mp;
-  a.pad_stride = h->total_pad;
-  a.cluster = h->cluster;
-  a.debug = h->d_debug;
-  a.slots = h->slots;
-  a.depth = h->depth;
-  RB_CUDA(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int32_t), st));
-  record(h, 3, st);
-  RB_CUDA(h, rb_launch_solver(a, h->max_clusters, st));
-  record(h, 4, st);
-  return RB_OK;
+  return solve_range(h, 0, h->B, 0, u0, nodes, sel, n_nodes, u, score, ifinal, n_passes, st);
 }
 
 int rb_arun(rb_handle* h, const double* D1, const double* D2, const int32_t* sel, const int32_t* n_sel, double* T,
@@ -458,12 +506,8 @@ int rb_arun(rb_handle* h, const double* D1, const double* D2, const int32_t* sel
   if (h->B == 0) return RB_OK;
   if (!D1 || !D2 || !sel || !n_sel) return fail(h, RB_ERR_ARG, "rb_arun: null input");
   cudaStream_t st = (cudaStream_t)stream;
-  int pd = h->inv.kind == RB_INVARIANT_ROMAN ? h->inv.point_dim : (h->d < 3 ? h->d : 3);
-  if (pd < 2) return fail(h, RB_ERR_ARG, "rb_arun: point dimension must be 2 or 3");
-  record(h, 5, st);
-  RB_CUDA(h, rb_launch_arun(h->d_probs, h->B, pd, D1, D2, sel, n_sel, T ? T : h->d_T, status ? status : h->d_status, st));
-  record(h, 6, st);
-  return RB_OK;
+  h->last_stream = st; h->last_valid = true;
+  return arun_range(h, 0, h->B, D1, D2, sel, n_sel, T, status, st);
 }
 
 int rb_align_batch(rb_handle* h, const double* D1, const double* D2, const int32_t* A, const double* u0,
@@ -514,30 +558,68 @@ int rb_align_batch_host(rb_handle* h, const double* D1, const double* D2, const 
   if (!h->planned) return fail(h, RB_ERR_NOPLAN, "rb_align_batch_host before rb_plan");
   if (h->B == 0) return RB_OK;
   RB_CUDA(h, cudaSetDevice(h->device));
+  if (!D1 || !D2 || !u0) return fail(h, RB_ERR_ARG, "rb_align_batch_host: null input");
+  if (!h->all_to_all && !A) return fail(h, RB_ERR_ARG, "rb_align_batch_host: A required");
+  int rc = check_affinity_args(h, D1, D2, A);
+  if (rc) return rc;
   if (!h->own_stream) RB_CUDA(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-  cudaStream_t st = h->own_stream;
+  if (!h->copy_stream) RB_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  if (!h->own_stream2) RB_CUDA(h, cudaStreamCreateWithFlags(&h->own_stream2, cudaStreamNonBlocking));
+  if (!h->join_ev) RB_CUDA(h, cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming));
+  cudaStream_t st = h->own_stream, cs = h->copy_stream;
+  cudaStream_t cst[2] = {h->own_stream, h->own_stream2};
   if (h->last_valid && h->last_stream != st) {  // scratch may still be in use by work queued on the caller's stream
     if (!h->order_ev) RB_CUDA(h, cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
     RB_CUDA(h, cudaEventRecord(h->order_ev, h->last_stream));
     RB_CUDA(h, cudaStreamWaitEvent(st, h->order_ev, 0));
+    RB_CUDA(h, cudaStreamWaitEvent(cst[1], h->order_ev, 0));
+    RB_CUDA(h, cudaStreamWaitEvent(cs, h->order_ev, 0));
   }
   const size_t nD1 = (size_t)h->total_obj1 * h->d, nD2 = (size_t)h->total_obj2 * h->d, nA = (size_t)h->total_assoc;
-  int rc;
   if ((rc = ensure(h, &h->s_D1, &h->cap_sD1, nD1))) return rc;
   if ((rc = ensure(h, &h->s_D2, &h->cap_sD2, nD2))) return rc;
   if ((rc = ensure(h, &h->s_u0, &h->cap_su0, nA))) return rc;
   if (!h->all_to_all && (rc = ensure(h, &h->s_A, &h->cap_sA, 2 * nA))) return rc;
-  if (!D1 || !D2 || !u0) return fail(h, RB_ERR_ARG, "rb_align_batch_host: null input");
-  RB_CUDA(h, cudaMemcpyAsync(h->s_D1, D1, nD1 * sizeof(double), cudaMemcpyHostToDevice, st));
-  RB_CUDA(h, cudaMemcpyAsync(h->s_D2, D2, nD2 * sizeof(double), cudaMemcpyHostToDevice, st));
-  RB_CUDA(h, cudaMemcpyAsync(h->s_u0, u0, nA * sizeof(double), cudaMemcpyHostToDevice, st));
-  if (!h->all_to_all) {
-    if (!A) return fail(h, RB_ERR_ARG, "rb_align_batch_host: A required");
-    RB_CUDA(h, cudaMemcpyAsync(h->s_A, A, 2 * nA * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+
+  // Pipeline: the batch is cut into up to RB_HOST_CHUNKS contiguous problem ranges; the copy stream uploads
+  // range c+1 while the compute stream runs K1a/K1/K2/K3 of range c (inputs are consumed in place, no reordering).
+  constexpr int RB_HOST_CHUNKS = 4;
+  int nch = h->B / (2 * (h->max_clusters > 0 ? h->max_clusters : 1));  // keep >= 2 solver waves per range
+  if (nch < 1) nch = 1;
+  if (nch > RB_HOST_CHUNKS) nch = RB_HOST_CHUNKS;
+  for (int c = 0; c < nch; ++c)
+    if (!h->chunk_ev[c]) RB_CUDA(h, cudaEventCreateWithFlags(&h->chunk_ev[c], cudaEventDisableTiming));
+  if (h->last_valid) {  // the copy stream must not overwrite staging buffers the previous call's kernels still read
+    if (!h->order_ev) RB_CUDA(h, cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
+    RB_CUDA(h, cudaEventRecord(h->order_ev, st));
+    RB_CUDA(h, cudaStreamWaitEvent(cs, h->order_ev, 0));
   }
-  rc = rb_align_batch(h, h->s_D1, h->s_D2, h->all_to_all ? nullptr : h->s_A, h->s_u0, nullptr, nullptr, nullptr,
-                      nullptr, nullptr, nullptr, st);
-  if (rc) return rc;
+  const size_t d = (size_t)h->d;
+  for (int c = 0; c < nch; ++c) {
+    const int b0 = (int)((int64_t)h->B * c / nch), b1 = (int)((int64_t)h->B * (c + 1) / nch);
+    const RbProblem& p0 = h->probs[(size_t)b0];
+    const size_t o1 = (size_t)p0.off_obj1 * d, o2 = (size_t)p0.off_obj2 * d, oa = (size_t)p0.off_assoc;
+    const size_t e1 = (b1 < h->B ? (size_t)h->probs[(size_t)b1].off_obj1 : (size_t)h->total_obj1) * d;
+    const size_t e2 = (b1 < h->B ? (size_t)h->probs[(size_t)b1].off_obj2 : (size_t)h->total_obj2) * d;
+    const size_t ea = b1 < h->B ? (size_t)h->probs[(size_t)b1].off_assoc : (size_t)h->total_assoc;
+    RB_CUDA(h, cudaMemcpyAsync(h->s_D1 + o1, D1 + o1, (e1 - o1) * sizeof(double), cudaMemcpyHostToDevice, cs));
+    RB_CUDA(h, cudaMemcpyAsync(h->s_D2 + o2, D2 + o2, (e2 - o2) * sizeof(double), cudaMemcpyHostToDevice, cs));
+    RB_CUDA(h, cudaMemcpyAsync(h->s_u0 + oa, u0 + oa, (ea - oa) * sizeof(double), cudaMemcpyHostToDevice, cs));
+    if (!h->all_to_all)
+      RB_CUDA(h, cudaMemcpyAsync(h->s_A + 2 * oa, A + 2 * oa, 2 * (ea - oa) * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+    RB_CUDA(h, cudaEventRecord(h->chunk_ev[c], cs));
+    cudaStream_t ks = cst[c & 1];
+    RB_CUDA(h, cudaStreamWaitEvent(ks, h->chunk_ev[c], 0));
+    if ((rc = affinity_range(h, b0, b1, h->s_D1, h->s_D2, h->all_to_all ? nullptr : h->s_A, ks))) return rc;
+    if ((rc = solve_range(h, b0, b1, c, h->s_u0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ks))) return rc;
+    if ((rc = arun_range(h, b0, b1, h->s_D1, h->s_D2, h->d_sel, h->d_nsel, nullptr, nullptr, ks))) return rc;
+  }
+  if (nch > 1) {  // join the second compute stream before reading results back
+    RB_CUDA(h, cudaEventRecord(h->join_ev, cst[1]));
+    RB_CUDA(h, cudaStreamWaitEvent(st, h->join_ev, 0));
+  }
+  h->affinity_done = true;
+  h->last_stream = st; h->last_valid = true;
   const size_t B = (size_t)h->B;
   if (sel) RB_CUDA(h, cudaMemcpyAsync(sel, h->d_sel, 2 * nA * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   if (n_sel) RB_CUDA(h, cudaMemcpyAsync(n_sel, h->d_nsel, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));

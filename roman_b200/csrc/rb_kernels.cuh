@@ -40,9 +40,9 @@ struct RbSolveArgs {
 cudaError_t rb_launch_prep(const RbProblem* probs, int B, int max_mp, int max_n1, int max_n2, bool all_to_all,
                            const RbAssocSoA& rec, const double* D1, const double* D2, const int32_t* A,
                            const RbDevParams& P, cudaStream_t st);
-cudaError_t rb_launch_affinity(const RbProblem* probs, int B, const int64_t* tile_prefix, int64_t total_tiles,
-                               const RbAssocSoA& rec, double* Mp, const RbDevParams& P, int sm_count,
-                               cudaStream_t st);
+cudaError_t rb_launch_affinity(const RbProblem* probs, int B, const int64_t* tile_prefix, int64_t tile_base,
+                               int64_t total_tiles, const RbAssocSoA& rec, double* Mp, const RbDevParams& P,
+                               int sm_count, cudaStream_t st);
 cudaError_t rb_launch_unpack(const RbProblem& pr, const double* Mp, double* Mout, double* Cout, cudaStream_t st);
 cudaError_t rb_launch_pack(const RbProblem& pr, const double* Min, const double* Cin, double* Mp, int* bad,
                            cudaStream_t st);
