@@ -168,6 +168,12 @@ int rb_set_solver_cluster(rb_handle* h, int32_t ctas_per_problem);
 int rb_get_solver_cluster(const rb_handle* h);
 int rb_get_solver_max_clusters(const rb_handle* h); /* co-resident clusters of that size (after rb_plan) */
 
+/* Storage format of the packed affinity matrix.  on (default): K1 records per 32x32 tile whether it
+ * holds any non-zero word, writes only such tiles, and K2 streams only those ("tile skip").  off: every
+ * tile of the packed upper triangle is written and streamed each pass (the plain dense kernels).
+ * Results are bitwise identical in both modes.  Takes effect at the next rb_affinity / rb_set_dense. */
+int rb_set_tile_skip(rb_handle* h, int32_t on);
+
 /* Device milliseconds of the last rb_align_batch / stage calls, measured with CUDA events on
  * the launch stream: ms[0]=prep(K1a) ms[1]=affinity(K1) ms[2]=solve(K2) ms[3]=arun(K3).
  * Synchronises on the recorded events.  Enabled by rb_set_profiling(h, 1). */

@@ -369,7 +369,8 @@ __device__ __forceinline__ void tile_coords(int64_t q, int nb, int& I, int& J) {
 __global__ void __launch_bounds__(256) rb_affinity_kernel(const RbProblem* __restrict__ probs, int B,
                                                           const int64_t* __restrict__ tile_prefix,
                                                           int64_t tile_base, int64_t total_tiles, RbAssocSoA rec,
-                                                          double* __restrict__ Mp, RbDevParams P) {
+                                                          double* __restrict__ Mp, uint8_t* __restrict__ flags,
+                                                          RbDevParams P) {
   __shared__ Rec s_row[8][RB_TILE];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int64_t tt = (int64_t)blockIdx.x * 8 + warp; tt < total_tiles; tt += (int64_t)gridDim.x * 8) {
@@ -383,25 +384,32 @@ __global__ void __launch_bounds__(256) rb_affinity_kernel(const RbProblem* __res
     const int64_t q = t - tile_prefix[lo];
     int I, J;
     tile_coords(q, pr.nb, I, J);
-    const Rec col = load_rec(rec, pr.off_pad + (int64_t)J * RB_TILE + lane);
-    const Rec myrow = load_rec(rec, pr.off_pad + (int64_t)I * RB_TILE + lane);
+    const int64_t oc = pr.off_pad + (int64_t)J * RB_TILE + lane, orow = pr.off_pad + (int64_t)I * RB_TILE + lane;
     double* out = Mp + (pr.off_tile + q) * RB_TILE_ELEMS;
     // An association whose single score is below affinityeps (clipper.cpp:104-108), or padding,
-    // can have no edge at all: rows/columns made only of such associations are written as zeros
-    // without evaluating anything.  (NaN scores are "live", exactly as the reference's `<` test.)
+    // can have no edge at all: rows/columns made only of such associations need no evaluation.
+    // (NaN scores are "live", exactly as the reference's `<` test.)  Only the 12 bytes that
+    // decide this are read first; the full records follow for live tiles only.
     const bool roman = (P.inv.kind == RB_INVARIANT_ROMAN);
-    const unsigned col_live = __ballot_sync(0xffffffffu, col.i1 >= 0 && !(roman && col.s < P.affinityeps));
-    const unsigned row_live = __ballot_sync(0xffffffffu, myrow.i1 >= 0 && !(roman && myrow.s < P.affinityeps));
+    const unsigned col_live = __ballot_sync(0xffffffffu, rec.i1[oc] >= 0 && !(roman && rec.single[oc] < P.affinityeps));
+    const unsigned row_live = __ballot_sync(0xffffffffu, rec.i1[orow] >= 0 && !(roman && rec.single[orow] < P.affinityeps));
     if (col_live == 0u || row_live == 0u) {
-      double2* o2 = reinterpret_cast<double2*>(out);
+      if (flags) {  // tile-skip format: a dead tile is recorded as such and never written nor read
+        if (lane == 0) flags[pr.off_tile + q] = 0;
+      } else {
+        double2* o2 = reinterpret_cast<double2*>(out);
 #pragma unroll
-      for (int t = 0; t < RB_TILE_ELEMS / 2 / 32; ++t) o2[t * 32 + lane] = make_double2(0.0, 0.0);
+        for (int t = 0; t < RB_TILE_ELEMS / 2 / 32; ++t) o2[t * 32 + lane] = make_double2(0.0, 0.0);
+      }
       continue;
     }
+    const Rec col = load_rec(rec, oc);
+    const Rec myrow = load_rec(rec, orow);
     __syncwarp();
     s_row[warp][lane] = myrow;
     __syncwarp();
     const bool diag = (I == J);
+    bool any_nz = false;
 #pragma unroll 4
     for (int r = 0; r < RB_TILE; ++r) {
       double v = 0.0;
@@ -411,15 +419,18 @@ __global__ void __launch_bounds__(256) rb_affinity_kernel(const RbProblem* __res
         else if (r > lane) v = pair_score(P, col, row);           // mirrored entry of the diagonal tile
         // r == lane: identity is implicit (clipper.cpp:129-130)
       }
+      any_nz |= (v != 0.0);
       out[rb_tile_elem(r, lane)] = v;
     }
+    const unsigned nzb = __ballot_sync(0xffffffffu, any_nz);
+    if (flags && lane == 0) flags[pr.off_tile + q] = nzb ? 1 : 0;
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // Dense <-> packed conversions (clipper.cpp:202-229).
-__global__ void rb_unpack_kernel(RbProblem pr, const double* __restrict__ Mp, double* __restrict__ Mout,
-                                 double* __restrict__ Cout) {
+__global__ void rb_unpack_kernel(RbProblem pr, const double* __restrict__ Mp, const uint8_t* __restrict__ flags,
+                                 double* __restrict__ Mout, double* __restrict__ Cout) {
   const int m = pr.m;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < (int64_t)m * m;
        e += (int64_t)gridDim.x * blockDim.x) {
@@ -431,7 +442,8 @@ __global__ void rb_unpack_kernel(RbProblem pr, const double* __restrict__ Mp, do
     } else {
       const int a = i < j ? i : j, b = i < j ? j : i;
       const int I = a / RB_TILE, J = b / RB_TILE;
-      const double v = Mp[(pr.off_tile + rb_tile_index(I, J, pr.nb)) * RB_TILE_ELEMS + rb_tile_elem(a % RB_TILE, b % RB_TILE)];
+      const int64_t tl = pr.off_tile + rb_tile_index(I, J, pr.nb);
+      const double v = (flags && !flags[tl]) ? 0.0 : Mp[tl * RB_TILE_ELEMS + rb_tile_elem(a % RB_TILE, b % RB_TILE)];
       cv = (__double_as_longlong(v) != 0ll) ? 1.0 : 0.0;
       mv = (cv != 0.0) ? fabs(v) : 0.0;  // -0.0 (constraint-only entry) reads back as 0
     }
@@ -488,21 +500,22 @@ cudaError_t rb_launch_prep(const RbProblem* probs, int B, int max_mp, int max_n1
 }
 
 cudaError_t rb_launch_affinity(const RbProblem* probs, int B, const int64_t* tile_prefix, int64_t tile_base,
-                               int64_t total_tiles, const RbAssocSoA& rec, double* Mp, const RbDevParams& P,
-                               int sm_count, cudaStream_t st) {
+                               int64_t total_tiles, const RbAssocSoA& rec, double* Mp, uint8_t* flags,
+                               const RbDevParams& P, int sm_count, cudaStream_t st) {
   if (total_tiles == 0) return cudaSuccess;
   int64_t want = (total_tiles + 7) / 8;
   const int64_t cap = (int64_t)sm_count * 8;  // 8 CTAs of 256 threads per SM, persistent
   const int grid = (int)(want < cap ? want : cap);
-  rb_affinity_kernel<<<grid, 256, 0, st>>>(probs, B, tile_prefix, tile_base, total_tiles, rec, Mp, P);
+  rb_affinity_kernel<<<grid, 256, 0, st>>>(probs, B, tile_prefix, tile_base, total_tiles, rec, Mp, flags, P);
   return cudaGetLastError();
 }
 
-cudaError_t rb_launch_unpack(const RbProblem& pr, const double* Mp, double* Mout, double* Cout, cudaStream_t st) {
+cudaError_t rb_launch_unpack(const RbProblem& pr, const double* Mp, const uint8_t* flags, double* Mout, double* Cout,
+                             cudaStream_t st) {
   if (pr.m == 0) return cudaSuccess;
   const int64_t n = (int64_t)pr.m * pr.m;
   const int grid = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
-  rb_unpack_kernel<<<grid, 256, 0, st>>>(pr, Mp, Mout, Cout);
+  rb_unpack_kernel<<<grid, 256, 0, st>>>(pr, Mp, flags, Mout, Cout);
   return cudaGetLastError();
 }
 

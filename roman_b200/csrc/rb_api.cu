@@ -34,6 +34,8 @@ struct rb_handle {
   RbProblem* d_probs = nullptr; size_t cap_probs = 0;
   int64_t* d_tile_prefix = nullptr; size_t cap_prefix = 0;
   double* d_M = nullptr; size_t cap_M = 0;            // packed tiles
+  uint8_t* d_flags = nullptr; size_t cap_flags = 0;   // per stored tile: holds a non-zero word (tile-skip mode)
+  bool tile_skip = true;                              // rb_set_tile_skip
   double* d_pad_f64 = nullptr; size_t cap_pad = 0;    // padded double arrays (7 record + u, g per cluster CTA)
   int32_t* d_pad_i32 = nullptr;                       // 2 padded int arrays
   int32_t* d_counter = nullptr;
@@ -179,7 +181,7 @@ int rb_create(rb_handle** out, int device) {
 int rb_destroy(rb_handle* h) {
   if (!h) return RB_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->d_probs); cudaFree(h->d_tile_prefix); cudaFree(h->d_M); cudaFree(h->d_pad_f64);
+  cudaFree(h->d_probs); cudaFree(h->d_tile_prefix); cudaFree(h->d_M); cudaFree(h->d_flags); cudaFree(h->d_pad_f64);
   cudaFree(h->d_pad_i32); cudaFree(h->d_counter); cudaFree(h->d_bad); cudaFree(h->d_nodes); cudaFree(h->d_sel);
   cudaFree(h->d_nsel); cudaFree(h->d_score); cudaFree(h->d_ifinal); cudaFree(h->d_npass);
   cudaFree(h->d_status); cudaFree(h->d_T);
@@ -243,6 +245,13 @@ int rb_debug_solver_cycles(rb_handle* h, long long* out, int n_ctas) {
     return RB_OK;
   }
   if (out && n_ctas > 0) RB_CUDA(h, cudaMemcpy(out, h->d_debug, (size_t)(n_ctas > 1024 ? 1024 : n_ctas) * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return RB_OK;
+}
+
+int rb_set_tile_skip(rb_handle* h, int32_t on) {
+  if (!h) return RB_ERR_ARG;
+  h->tile_skip = on != 0;
+  h->affinity_done = false;  // the packed buffer of a previous rb_affinity is in the other format
   return RB_OK;
 }
 
@@ -336,6 +345,7 @@ int rb_plan(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const int32_t
   if ((rc = ensure(h, &h->d_probs, &h->cap_probs, (size_t)B))) return rc;
   if ((rc = ensure(h, &h->d_tile_prefix, &h->cap_prefix, (size_t)B + 1))) return rc;
   if ((rc = ensure(h, &h->d_M, &h->cap_M, (size_t)ot * RB_TILE_ELEMS))) return rc;
+  if ((rc = ensure(h, &h->d_flags, &h->cap_flags, (size_t)ot))) return rc;
   {
     const size_t need = (size_t)op;
     if (need > h->cap_pad || !h->d_pad_f64) {
@@ -428,7 +438,8 @@ int affinity_range(rb_handle* h, int b0, int b1, const double* D1, const double*
   record(h, 1, st);
   const int64_t base = h->tile_prefix[(size_t)b0];
   RB_CUDA(h, rb_launch_affinity(h->d_probs + b0, b1 - b0, h->d_tile_prefix + b0, base,
-                                h->tile_prefix[(size_t)b1] - base, rec, h->d_M, P, h->sm_count, st));
+                                h->tile_prefix[(size_t)b1] - base, rec, h->d_M, h->tile_skip ? h->d_flags : nullptr, P,
+                                h->sm_count, st));
   record(h, 2, st);
   return RB_OK;
 }
@@ -438,6 +449,8 @@ int solve_range(rb_handle* h, int b0, int b1, int queue, const double* u0, int32
   if (b1 <= b0) return RB_OK;
   RbSolveArgs a;
   a.probs = h->d_probs + b0; a.B = b1 - b0; a.counter = h->d_counter + queue; a.Mp = h->d_M;
+  a.flags = h->tile_skip ? h->d_flags : nullptr;
+  a.nt_max = (h->max_mp / RB_TILE) * (h->max_mp / RB_TILE + 1) / 2;
   a.i1 = h->d_pad_i32; a.i2 = h->d_pad_i32 + (size_t)h->total_pad;
   a.u0 = u0; a.u_work = u_work(h); a.g_work = g_work(h);
   a.nodes = nodes ? nodes : h->d_nodes;            // per-association arrays are addressed by absolute offsets
@@ -527,7 +540,8 @@ int rb_get_dense(rb_handle* h, int32_t b, double* M_out, double* C_out, void* st
   if (!h) return RB_ERR_ARG;
   if (!h->planned || !h->affinity_done) return fail(h, RB_ERR_NOPLAN, "rb_get_dense before rb_affinity / rb_set_dense");
   if (b < 0 || b >= h->B) return fail(h, RB_ERR_ARG, "rb_get_dense: problem index out of range");
-  RB_CUDA(h, rb_launch_unpack(h->probs[(size_t)b], h->d_M, M_out, C_out, (cudaStream_t)stream));
+  RB_CUDA(h, rb_launch_unpack(h->probs[(size_t)b], h->d_M, h->tile_skip ? h->d_flags : nullptr, M_out, C_out,
+                              (cudaStream_t)stream));
   return RB_OK;
 }
 
@@ -543,6 +557,7 @@ int rb_set_dense(rb_handle* h, int32_t b, const double* M, const double* C, void
   RB_CUDA(h, cudaMemsetAsync(h->d_pad_i32 + pr.off_pad, 0, n * sizeof(int32_t), st));
   RB_CUDA(h, cudaMemsetAsync(h->d_pad_i32 + (size_t)h->total_pad + pr.off_pad, 0, n * sizeof(int32_t), st));
   RB_CUDA(h, rb_launch_pack(pr, M, C, h->d_M, h->d_bad, st));
+  RB_CUDA(h, cudaMemsetAsync(h->d_flags + pr.off_tile, 1, (size_t)pr.n_tiles, st));  // every tile of b is stored
   int bad = 0;
   RB_CUDA(h, cudaMemcpyAsync(&bad, h->d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
   RB_CUDA(h, cudaStreamSynchronize(st));

@@ -15,6 +15,8 @@ struct RbSolveArgs {
   int32_t B;
   int32_t* counter;        // dynamic problem queue (zeroed before launch)
   const double* Mp;        // packed tiles
+  const uint8_t* flags;    // per stored tile: 1 = holds a non-zero word; null = every tile is streamed (dense mode)
+  int32_t nt_max;          // max stored tiles of one problem (sizes the shared-memory copy of the flags)
   const int32_t* i1;       // association object indices (padded arrays), for `sel`
   const int32_t* i2;
   const double* u0;        // user layout (off_assoc)
@@ -41,9 +43,10 @@ cudaError_t rb_launch_prep(const RbProblem* probs, int B, int max_mp, int max_n1
                            const RbAssocSoA& rec, const double* D1, const double* D2, const int32_t* A,
                            const RbDevParams& P, cudaStream_t st);
 cudaError_t rb_launch_affinity(const RbProblem* probs, int B, const int64_t* tile_prefix, int64_t tile_base,
-                               int64_t total_tiles, const RbAssocSoA& rec, double* Mp, const RbDevParams& P,
-                               int sm_count, cudaStream_t st);
-cudaError_t rb_launch_unpack(const RbProblem& pr, const double* Mp, double* Mout, double* Cout, cudaStream_t st);
+                               int64_t total_tiles, const RbAssocSoA& rec, double* Mp, uint8_t* flags,
+                               const RbDevParams& P, int sm_count, cudaStream_t st);
+cudaError_t rb_launch_unpack(const RbProblem& pr, const double* Mp, const uint8_t* flags, double* Mout, double* Cout,
+                             cudaStream_t st);
 cudaError_t rb_launch_pack(const RbProblem& pr, const double* Min, const double* Cin, double* Mp, int* bad,
                            cudaStream_t st);
 

@@ -90,6 +90,8 @@ struct Smem {
   uint64_t* bar; // [NW][SLOTS]
   double* ring;  // [NW][SLOTS][1024]
   int* misc;     // small ints / broadcast slots
+  const uint8_t* flag;    // this problem's tile flags (shared-memory copy), or null: stream every tile
+  const uint8_t* rowany;  // per tile-row: any flagged tile (null with flag == null)
   int slots;     // TMA ring slots per warp (1 or 2)
   int depth;     // tile-rows in flight between the fastest and slowest warp: 8 (decoupled) or 2 (lock-step)
 };
@@ -140,7 +142,9 @@ struct Reducer {
 // no cross-lane reduction) and with lane = column (column sums of block J).
 struct TileIter {
   int nb, C, w, p, h, I, J;
+  const uint8_t* F;  // tile flags or null
   bool ok;
+  __device__ __forceinline__ bool live(int i, int j) const { return F == nullptr || F[rb_tile_index(i, j, nb)] != 0; }
   __device__ __forceinline__ int row() const { return h == 0 ? p : nb - 1 - p; }
   // position on the first tile (J >= I, J mod NW == w) at or after tile-row slot (p, h)
   __device__ __forceinline__ void settle() {
@@ -149,18 +153,20 @@ struct TileIter {
       if (!(h == 1 && nb - 1 - p == p)) {  // the middle tile-row of an odd nb is visited once
         I = row();
         J = I + ((w - I) % NW + NW) % NW;
+        while (J < nb && !live(I, J)) J += NW;
         if (J < nb) { ok = true; return; }
       }
       if (h == 0) h = 1; else { h = 0; p += C; }
     }
     ok = false;
   }
-  __device__ __forceinline__ void init(int nb_, int C_, int crank, int w_) {
-    nb = nb_; C = C_; w = w_; p = crank; h = 0; I = 0; J = 0;
+  __device__ __forceinline__ void init(int nb_, int C_, int crank, int w_, const uint8_t* F_) {
+    nb = nb_; C = C_; w = w_; p = crank; h = 0; I = 0; J = 0; F = F_;
     settle();
   }
   __device__ __forceinline__ void next() {
     J += NW;
+    while (J < nb && !live(I, J)) J += NW;
     if (J < nb) return;
     if (h == 0) h = 1; else { h = 0; p += C; }
     settle();
@@ -175,7 +181,7 @@ __device__ __forceinline__ void matvec_pass(const Smem& S, const double* __restr
   double* ring = S.ring + (size_t)w * SLOTS * RB_TILE_ELEMS;
 
   TileIter pf;  // prefetch iterator: runs SLOTS tiles ahead of the consumer along the same sequence
-  pf.init(nb, C, crank, w);
+  pf.init(nb, C, crank, w, S.flag);
   auto pf_issue = [&](int slot) {
     if (lane == 0)
       tma_load_tile(ring + slot * RB_TILE_ELEMS, tiles + rb_tile_index(pf.I, pf.J, nb) * RB_TILE_ELEMS, bar + slot);
@@ -190,12 +196,14 @@ __device__ __forceinline__ void matvec_pass(const Smem& S, const double* __restr
     for (int h = 0; h < 2; ++h) {
       const int I = (h == 0) ? p : nb - 1 - p;
       if (h == 1 && I == p) break;
+      if (S.rowany && !S.rowany[I]) continue;  // no flagged tile in this tile-row: nothing to add, for any warp
       // row sums of block I over this warp's tiles: lane = row; two chains each to shorten the
       // dependent-add latency
       double rM0 = 0.0, rM1 = 0.0, rC0 = 0.0, rC1 = 0.0;
       const double* xI = S.x + I * RB_TILE;
 
       for (int J = I + ((w - I) % NW + NW) % NW; J < nb; J += NW) {
+        if (S.flag && !S.flag[rb_tile_index(I, J, nb)]) continue;  // not stored / all zero: never fetched
         mbar_wait(bar + slot, (phase_bits >> slot) & 1u);
         phase_bits ^= (1u << slot);
         const double* buf = ring + slot * RB_TILE_ELEMS;
@@ -333,7 +341,9 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
     S.part = (double*)p; p += (size_t)A.depth * NW * 2 * RB_TILE * 8;
     S.red = (double*)p; p += (size_t)RED_DOUBLES * 8;
     S.bar = (uint64_t*)p; p += (size_t)NW * MAX_SLOTS * 8;
-    S.misc = (int*)p;
+    S.misc = (int*)p; p += (size_t)MISC_INTS * 4;
+    S.flag = A.flags ? (const uint8_t*)p : nullptr; p += (size_t)((A.nt_max + 15) / 16) * 16;
+    S.rowany = A.flags ? (const uint8_t*)p : nullptr;
   }
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -369,6 +379,20 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
     double* g = A.g_work + (size_t)crank * A.pad_stride + pr.off_pad;
     const double* u0 = A.u0 + pr.off_assoc;
     int passes = 0;
+    if (A.flags) {  // this problem's tile flags and per-tile-row summary into shared memory
+      uint8_t* fl = const_cast<uint8_t*>(S.flag);
+      uint8_t* ra = const_cast<uint8_t*>(S.rowany);
+      const int nt = (int)pr.n_tiles;
+      for (int t = tid; t < nt; t += NT) fl[t] = A.flags[pr.off_tile + t];
+      __syncthreads();
+      for (int I = tid; I < nb; I += NT) {
+        uint8_t any = 0;
+        const int64_t base = rb_tile_index(I, I, nb);
+        for (int J = I; J < nb; ++J) any |= fl[base + (J - I)];
+        ra[I] = any;
+      }
+      __syncthreads();
+    }
 
     if (m == 0) {
       if (lead && tid == 0) {
@@ -623,8 +647,11 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
 }  // namespace
 
 size_t rb_solver_smem_bytes(int mp_max, int slots, int depth) {
+  const int nb = mp_max / RB_TILE;
+  const size_t nt = (size_t)nb * (nb + 1) / 2;  // tile flags + per-tile-row summary (tile-skip mode)
   return (size_t)NW * slots * RB_TILE_BYTES + (size_t)3 * mp_max * 8 + (size_t)depth * NW * 2 * RB_TILE * 8 +
-         (size_t)RED_DOUBLES * 8 + (size_t)NW * MAX_SLOTS * 8 + (size_t)MISC_INTS * 4;
+         (size_t)RED_DOUBLES * 8 + (size_t)NW * MAX_SLOTS * 8 + (size_t)MISC_INTS * 4 + ((nt + 15) / 16) * 16 +
+         (size_t)((nb + 15) / 16) * 16;
 }
 
 // Largest shared-memory configuration that fits: (2 slots, depth 8) > (2, 2) > (1, 2).

@@ -111,6 +111,10 @@ class Engine:
     def solver_cluster(self) -> int:
         return int(self._lib.rb_get_solver_cluster(self._h))
 
+    def set_tile_skip(self, on: bool):
+        """Packed-affinity format: True (default) stores/streams only tiles holding a non-zero; False = plain dense."""
+        self._check(self._lib.rb_set_tile_skip(self._h, int(on)))
+
     def set_profiling(self, on: bool):
         self._check(self._lib.rb_set_profiling(self._h, int(on)))
 

@@ -199,3 +199,37 @@ def test_topk_tie_semantics_match_heap(engine, coracle):
         ref = coracle.solve(sp, np.triu(M, 1), u0)
         k = int(sol["n_nodes"][0])
         assert sol["nodes"][:k].cpu().numpy().tolist() == ref["nodes"]
+
+
+def test_tile_skip_and_dense_formats_are_bitwise_identical(engine, coracle):
+    """rb_set_tile_skip: storing/streaming only tiles that hold a non-zero must not change a single bit."""
+    ip_o, ip_g = params_for_method("roman", semantics_dim=32)
+    shapes = [(40, 50), (33, 18), (40, 40), (9, 9)]
+    pairs = [synth.make_pair(40 + i, a, b, method="roman", semantics_dim=32, desc_common=(0.0 if i % 2 else 1.0))
+             for i, (a, b) in enumerate(shapes)]
+    D1 = np.concatenate([p.D1.reshape(-1) for p in pairs])
+    D2 = np.concatenate([p.D2.reshape(-1) for p in pairs])
+    u0 = np.concatenate([p.u0 for p in pairs])
+    engine.set_invariant_params(ip_g)
+    outs = []
+    try:
+        for mode in (True, False):
+            engine.set_tile_skip(mode)
+            engine.plan(pairs[0].D1.shape[1], [s[0] for s in shapes], [s[1] for s in shapes])
+            engine.affinity(D1, D2)
+            dense = [tuple(t.cpu().numpy() for t in engine.get_dense(b)) for b in range(len(pairs))]
+            sol = engine.solve(u0, want_u=True)
+            outs.append((dense, {k: (v.cpu().numpy() if v is not None else None) for k, v in sol.items()}))
+    finally:
+        engine.set_tile_skip(True)
+    (d_a, s_a), (d_b, s_b) = outs
+    for b in range(len(pairs)):
+        assert np.array_equal(d_a[b][0], d_b[b][0]) and np.array_equal(d_a[b][1], d_b[b][1])
+    for k in ("n_nodes", "score", "ifinal", "n_passes", "u"):
+        assert np.array_equal(s_a[k], s_b[k]), k
+    for b, p in enumerate(pairs):
+        o, n = int(engine.offsets[b]), int(s_a["n_nodes"][b])
+        assert np.array_equal(s_a["nodes"][o:o + n], s_b["nodes"][o:o + n])
+        Mo, _, _, _ = coracle.score(ip_o, 1e-4, p.D1, p.D2)
+        ref = coracle.solve(cn.SolverParams(), Mo, p.u0)
+        assert s_a["nodes"][o:o + n].tolist() == ref["nodes"]

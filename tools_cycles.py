@@ -11,8 +11,10 @@ eng.set_invariant_params(make_invariant_params(**method_invariant_kwargs("roman"
 eng.set_profiling(True)
 D1h, D2h, u0h = bench.make_inputs(1000, B)
 D1 = torch.from_numpy(D1h.reshape(-1)).cuda(); D2 = torch.from_numpy(D2h.reshape(-1)).cuda(); u0 = torch.from_numpy(u0h.reshape(-1)).cuda()
-for CL in [1, 2, 4, 8]:
+import itertools
+for CL, TS in itertools.product([1, 2, 4], [True, False]):
     eng.set_solver_cluster(CL)
+    eng.set_tile_skip(TS)
     eng.plan(775, [40] * B, [50] * B)
     for it in range(3):
         res = eng.align_batch(D1, D2, u0)
@@ -23,4 +25,4 @@ for CL in [1, 2, 4, 8]:
     eng._lib.rb_debug_solver_cycles(eng._h, C.c_void_p(buf.ctypes.data), n)
     f = buf.astype(float) / 1.965e3  # us at 1965 MHz (approx)
 
-    print(f"C={CL} ctas={n} solve={ms['solve']:.3f} ms | per-CTA us: total {f[:,0].mean():.0f} matvec {f[:,1].mean():.0f} (max {f[:,1].max():.0f}) combine {f[:,2].mean():.0f} queue {f[:,3].mean():.0f} round(lead) {f[::CL,4].mean():.0f} | passes {res.n_passes.float().sum().item():.0f}")
+    print(f"skip={TS} C={CL} ctas={n} solve={ms['solve']:.3f} ms | per-CTA us: total {f[:,0].mean():.0f} matvec {f[:,1].mean():.0f} (max {f[:,1].max():.0f}) combine {f[:,2].mean():.0f} queue {f[:,3].mean():.0f} round(lead) {f[::CL,4].mean():.0f} | passes {res.n_passes.float().sum().item():.0f}")
