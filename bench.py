@@ -119,7 +119,9 @@ def cpu_baseline(rounds=16, threads=0, seed0=10_000):
     import oracle
     O = oracle.COracle()
     ip, sp = oracle_params()
-    cores = O.max_threads() if threads <= 0 else threads
+    if threads <= 0:
+        threads = host_threads()  # all logical CPUs this process may use (torchrun would pin OMP_NUM_THREADS=1)
+    cores = threads
     nd = 2 * cores
     D1, D2, u0 = make_inputs(seed0, nd)
     O.align_batch(ip, sp, D1[:cores], D2[:cores], u0[:cores], threads=threads)  # warm the library / thread pool
@@ -161,6 +163,13 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -175,10 +184,12 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     K, W = args.steps, args.warmup
+    d_row = 3 + 3 + 1 + SEM_DIM
+    m = M_ASSOC
 
     eng = Engine(local)
     eng.set_invariant_params(make_invariant_params(**method_invariant_kwargs(METHOD, semantics_dim=SEM_DIM)))
-    eng.plan(N1 * 0 + (3 + 3 + 1 + SEM_DIM), [N1] * B, [N2] * B)
+    eng.plan(d_row, [N1] * B, [N2] * B)
     # problems are partitioned round-robin over ranks: global pair g = b*world + rank
     D1h, D2h, u0h = make_inputs(1000 + rank * B, B)
     pin = lambda a: torch.from_numpy(a).pin_memory()
@@ -202,41 +213,51 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(tile_skip, sampler=None):
+        """W warm-ups, then exactly K steps between device events; max over ranks."""
+        eng.set_tile_skip(tile_skip)
+        for _ in range(W):
+            step()
+        sync()
+        if sampler is not None:
+            sampler.mark()  # only samples taken from here on (the timed region) are reported
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stage = {"prep": 0.0, "affinity": 0.0, "solve": 0.0, "arun": 0.0}
+        sync()
+        ev0.record()
+        for _ in range(K):
+            step()
+            for k, v in eng.stage_ms().items():  # CUDA events on the launch stream (syncs on the step's last event)
+                stage[k] += v / K
+        ev1.record()
+        sync()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), stage
+
     eng.set_profiling(True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()  # nvidia-smi needs ~0.5 s to produce its first line: start it before the warm-up
-    for _ in range(W):
-        step()
-    sync()
-    if rank == 0:
-        sampler.mark()   # only samples taken from here on (the timed region) are reported
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage = {"prep": 0.0, "affinity": 0.0, "solve": 0.0, "arun": 0.0}
-    sync()
-    ev0.record()
-    for _ in range(K):
-        step()
-        for k, v in eng.stage_ms().items():  # CUDA events on the launch stream (syncs on the step's last event)
-            stage[k] += v
-    ev1.record()
-    sync()
-    ms = ev0.elapsed_time(ev1)
+    # ---- main measurement: the product's default format (tile skip: only tiles holding a non-zero are stored/streamed)
+    ms, stage = timed(True, sampler if rank == 0 else None)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
     value = world * B * K / (ms * 1e-3)
+    passes = res.n_passes.cpu().numpy().astype(np.int64)
+    stored = eng.stored_tiles().cpu().numpy().astype(np.int64)
+    # ---- same batch through the plain dense format (every tile written and streamed): the north-star kernels
+    ms_d, stage_d = timed(False)
+    passes_d = res.n_passes.cpu().numpy().astype(np.int64)
+    eng.set_tile_skip(True)
 
     # ---- end-to-end through the host-buffer C ABI: pinned host inputs, H2D + kernels + D2H inside the timed region
     out_h = None
     sync()
-    for _ in range(max(1, min(W, 2))):
+    for _ in range(max(1, min(W, 3))):
         out_h = eng.align_batch_host(D1p, D2p, u0p, out=out_h)
     sync()
     t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(K):
         out_h = eng.align_batch_host(D1p, D2p, u0p, out=out_h)
     wall = time.perf_counter() - t0
@@ -249,35 +270,52 @@ def run_b200(args):
 
     if rank == 0:
         peaks, which = measured_peaks()
-        passes = res.n_passes.cpu().numpy().astype(np.int64)
-        m = M_ASSOC
-        # algorithmic bytes (packed-upper layout, s = 8):
-        k2_bytes = float(passes.sum()) * (8.0 * m * (m - 1) / 2 + 24.0 * m)
-        d_row = 3 + 3 + 1 + SEM_DIM
-        k1_bytes = B * (8.0 * m * (m - 1) / 2 + 8.0 * d_row * (N1 + N2) + 8.0 * m)
-        k2_ms, k1_ms = stage["solve"] / K, (stage["prep"] + stage["affinity"]) / K
-        k2_gbs = k2_bytes / (k2_ms * 1e-3) / 1e9
-        k1_gbs = k1_bytes / (k1_ms * 1e-3) / 1e9
         peak = float(peaks["hbm_gbs"])
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
-        # kernel at this configuration (profiles/r1_solver_v3_B592_summary.txt); null for any other batch size
-        traffic = 53.063292e9 + 170.490880e6 if (B == 592 and world == 1) else None
+        gbs = lambda nbytes, t_ms: nbytes / (t_ms * 1e-3) / 1e9
+        in_bytes = B * (8.0 * d_row * (N1 + N2) + 8.0 * m)
+        # algorithmic bytes.  dense format (SURVEY 8d with the packed-upper layout): K1 writes, K2 reads per pass,
+        # s*m(m-1)/2.  tile-skip format: only stored tiles (8 KB each) move, plus one flag byte per tile.
+        tri = 8.0 * m * (m - 1) / 2
+        k2_dense = float(passes_d.sum()) * (tri + 24.0 * m)
+        k1_dense = B * tri + in_bytes
+        n_tiles = (m // 32 + (m % 32 > 0)) * (m // 32 + (m % 32 > 0) + 1) // 2
+        k2_skip = float((passes * (stored * 8192 + 24 * m)).sum()) + float(B * n_tiles)
+        k1_skip = float(stored.sum()) * 8192 + B * n_tiles + in_bytes
+        k1_ms = stage["prep"] + stage["affinity"]
+        k1d_ms = stage_d["prep"] + stage_d["affinity"]
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the
+        # dense-format solver at this configuration (profiles/r1_solver_v3_B592_summary.txt); null for other batch sizes
+        traffic_dense = 53.063292e9 + 170.490880e6 if (B == 592 and world == 1) else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "parallelism": f"round-robin pairs over {world} GPU(s)",
-                       "l2": f"inputs larger than L2: packed affinity working set {eng.packed_bytes / 1e9:.2f} GB per GPU per step",
-                       "layout": "packed upper triangle, 32x32 fp64 tiles", "mean_passes": float(passes.mean())},
-            "roofline": {"kernel": "rb_solver_kernel (K2)", "bound": "hbm", "achieved": k2_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": k2_gbs / peak, "traffic": traffic, "peak_source": which,
-                         "algorithmic_bytes_per_launch": k2_bytes, "ms_per_launch": k2_ms},
-            "kernels": {"K1_affinity": {"achieved": k1_gbs, "frac": k1_gbs / peak, "ms_per_launch": k1_ms,
-                                        "algorithmic_bytes_per_launch": k1_bytes},
-                        "K2_solver": {"achieved": k2_gbs, "frac": k2_gbs / peak, "ms_per_launch": k2_ms},
-                        "K3_arun_ms": stage["arun"] / K},
+                       "l2": f"inputs larger than L2: packed affinity buffer {eng.packed_bytes / 1e9:.2f} GB per GPU per step "
+                             f"({float(stored.sum()) * 8192 / 1e9:.2f} GB of it stored/streamed in the tile-skip format)",
+                       "layout": "packed upper triangle, 32x32 fp64 tiles; tile-skip format (default): only tiles holding a non-zero",
+                       "mean_passes": float(passes.mean()), "mean_stored_tiles": float(stored.mean()), "tiles_per_problem": int(n_tiles)},
+            "roofline": {"kernel": "rb_solver_kernel (K2), tile-skip format", "bound": "hbm", "achieved": gbs(k2_skip, stage["solve"]),
+                         "peak": peak, "unit": "GB/s", "frac": gbs(k2_skip, stage["solve"]) / peak, "traffic": None,
+                         "peak_source": which, "algorithmic_bytes_per_launch": k2_skip, "ms_per_launch": stage["solve"],
+                         "note": "bytes = sum over problems of passes x (stored tiles x 8 KB + 24 m) + flags; with ~7 % of the tiles "
+                                 "stored the kernel is latency-bound, see dense_stream for the same kernel on the dense format"},
+            "kernels": {"K1_affinity": {"achieved": gbs(k1_skip, k1_ms), "frac": gbs(k1_skip, k1_ms) / peak, "ms_per_launch": k1_ms,
+                                        "algorithmic_bytes_per_launch": k1_skip},
+                        "K2_solver": {"achieved": gbs(k2_skip, stage["solve"]), "frac": gbs(k2_skip, stage["solve"]) / peak,
+                                      "ms_per_launch": stage["solve"]},
+                        "K3_arun_ms": stage["arun"]},
+            "dense_stream": {
+                "what": "same batch, rb_set_tile_skip(0): every tile of the packed upper triangle written by K1 and streamed by K2 "
+                        "each pass (the dense kernels BASELINE.json's north_star names); results bitwise identical",
+                "value": world * B * K / (ms_d * 1e-3), "ms_per_step": ms_d / K,
+                "roofline": {"kernel": "rb_solver_kernel (K2), dense format", "bound": "hbm", "achieved": gbs(k2_dense, stage_d["solve"]),
+                             "peak": peak, "unit": "GB/s", "frac": gbs(k2_dense, stage_d["solve"]) / peak, "traffic": traffic_dense,
+                             "algorithmic_bytes_per_launch": k2_dense, "ms_per_launch": stage_d["solve"]},
+                "K1_affinity": {"achieved": gbs(k1_dense, k1d_ms), "frac": gbs(k1_dense, k1d_ms) / peak, "ms_per_launch": k1d_ms,
+                                "algorithmic_bytes_per_launch": k1_dense}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": "rb_align_batch_host (pinned host buffers; H2D + K1a/K1/K2/K3 + D2H per step)"},
+                    "api": "rb_align_batch_host (pinned host buffers; H2D pipelined with K1a/K1/K2/K3 over 4 problem ranges, then D2H)"},
             "gpu_launches": 4 * K,
             "clocks": clocks,
         }

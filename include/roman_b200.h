@@ -174,6 +174,9 @@ int rb_get_solver_max_clusters(const rb_handle* h); /* co-resident clusters of t
  * Results are bitwise identical in both modes.  Takes effect at the next rb_affinity / rb_set_dense. */
 int rb_set_tile_skip(rb_handle* h, int32_t on);
 
+/* Tile-skip format only: number of stored (flagged) 32x32 tiles of each problem, device int32[B]. */
+int rb_stored_tiles(rb_handle* h, int32_t* out, void* stream);
+
 /* Device milliseconds of the last rb_align_batch / stage calls, measured with CUDA events on
  * the launch stream: ms[0]=prep(K1a) ms[1]=affinity(K1) ms[2]=solve(K2) ms[3]=arun(K3).
  * Synchronises on the recorded events.  Enabled by rb_set_profiling(h, 1). */

@@ -479,7 +479,32 @@ __global__ void rb_pack_kernel(RbProblem pr, const double* __restrict__ Min, con
   }
 }
 
+// stored (flagged) tiles per problem: the tile-skip format's footprint, for the roofline accounting
+__global__ void rb_count_flags_kernel(const RbProblem* __restrict__ probs, int B, const uint8_t* __restrict__ flags,
+                                      int32_t* __restrict__ out) {
+  const int b = blockIdx.x;
+  if (b >= B) return;
+  const RbProblem pr = probs[b];
+  int c = 0;
+  for (int64_t t = threadIdx.x; t < pr.n_tiles; t += blockDim.x) c += flags[pr.off_tile + t] ? 1 : 0;
+  __shared__ int s[32];
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s[w];
+    out[b] = tot;
+  }
+}
+
 }  // namespace
+
+cudaError_t rb_launch_count_flags(const RbProblem* probs, int B, const uint8_t* flags, int32_t* out, cudaStream_t st) {
+  if (B == 0) return cudaSuccess;
+  rb_count_flags_kernel<<<B, 256, 0, st>>>(probs, B, flags, out);
+  return cudaGetLastError();
+}
 
 cudaError_t rb_launch_prep(const RbProblem* probs, int B, int max_mp, int max_n1, int max_n2, bool all_to_all,
                            const RbAssocSoA& rec, const double* D1, const double* D2, const int32_t* A,

@@ -255,6 +255,14 @@ int rb_set_tile_skip(rb_handle* h, int32_t on) {
   return RB_OK;
 }
 
+int rb_stored_tiles(rb_handle* h, int32_t* out, void* stream) {
+  if (!h || !out) return RB_ERR_ARG;
+  if (!h->planned || !h->affinity_done) return fail(h, RB_ERR_NOPLAN, "rb_stored_tiles before rb_affinity / rb_set_dense");
+  if (!h->tile_skip) return fail(h, RB_ERR_ARG, "rb_stored_tiles: the dense format stores every tile (rb_set_tile_skip is off)");
+  RB_CUDA(h, rb_launch_count_flags(h->d_probs, h->B, h->d_flags, out, (cudaStream_t)stream));
+  return RB_OK;
+}
+
 int rb_set_profiling(rb_handle* h, int32_t on) {
   if (!h) return RB_ERR_ARG;
   h->profiling = on != 0;

@@ -45,6 +45,7 @@ cudaError_t rb_launch_prep(const RbProblem* probs, int B, int max_mp, int max_n1
 cudaError_t rb_launch_affinity(const RbProblem* probs, int B, const int64_t* tile_prefix, int64_t tile_base,
                                int64_t total_tiles, const RbAssocSoA& rec, double* Mp, uint8_t* flags,
                                const RbDevParams& P, int sm_count, cudaStream_t st);
+cudaError_t rb_launch_count_flags(const RbProblem* probs, int B, const uint8_t* flags, int32_t* out, cudaStream_t st);
 cudaError_t rb_launch_unpack(const RbProblem& pr, const double* Mp, const uint8_t* flags, double* Mout, double* Cout,
                              cudaStream_t st);
 cudaError_t rb_launch_pack(const RbProblem& pr, const double* Min, const double* Cin, double* Mp, int* bad,

@@ -115,6 +115,12 @@ class Engine:
         """Packed-affinity format: True (default) stores/streams only tiles holding a non-zero; False = plain dense."""
         self._check(self._lib.rb_set_tile_skip(self._h, int(on)))
 
+    def stored_tiles(self) -> torch.Tensor:
+        """(B,) int32: 32x32 tiles actually stored per problem (tile-skip format)."""
+        out = torch.zeros(max(self.B, 1), dtype=torch.int32, device=self.device)
+        self._check(self._lib.rb_stored_tiles(self._h, _ptr(out), self._stream()))
+        return out
+
     def set_profiling(self, on: bool):
         self._check(self._lib.rb_set_profiling(self._h, int(on)))
 
