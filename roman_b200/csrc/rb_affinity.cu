@@ -363,67 +363,118 @@ __device__ __forceinline__ void tile_coords(int64_t q, int nb, int& I, int& J) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Per 32-association block: bit r set <=> association r of the block can carry an edge (not padding,
+// single score not below affinityeps — clipper.cpp:104-108; NaN counts as live like the reference's `<`).
+// One warp per block; K1 reads two of these words per tile instead of 64 records.
+__global__ void __launch_bounds__(256) rb_block_mask_kernel(const RbProblem* __restrict__ probs, RbAssocSoA rec,
+                                                            uint32_t* __restrict__ masks, RbDevParams P) {
+  const RbProblem pr = probs[blockIdx.y];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool roman = (P.inv.kind == RB_INVARIANT_ROMAN);
+  for (int I = blockIdx.x * 8 + warp; I < pr.nb; I += gridDim.x * 8) {
+    const int64_t o = pr.off_pad + (int64_t)I * RB_TILE + lane;
+    const unsigned live = __ballot_sync(0xffffffffu, rec.i1[o] >= 0 && !(roman && rec.single[o] < P.affinityeps));
+    if (lane == 0) masks[(pr.off_pad >> 5) + I] = live;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K1: one warp per 32x32 tile, lane = tile column; 32 coalesced 256-byte row stores per tile
 // (each row is written as a permutation of itself: the XOR swizzle of rb_common.cuh).
-// Work list = all stored tiles of all problems (flat), grid-strided by a persistent grid.
-__global__ void __launch_bounds__(256) rb_affinity_kernel(const RbProblem* __restrict__ probs, int B,
-                                                          const int64_t* __restrict__ tile_prefix,
-                                                          int64_t tile_base, int64_t total_tiles, RbAssocSoA rec,
+// Grid = (CTAs per problem, problems).  A CTA first condenses the problem's block live masks into the
+// list of LIVE blocks (blocks holding at least one association that can carry an edge); only tiles
+// whose row block and column block are both live are evaluated.
+//   tile-skip format (flags != null): dead tiles are never touched (their flags were zeroed by a
+//     memset); a live tile is written and flagged iff it ends up holding a non-zero word;
+//   dense format (flags == null): every tile of the packed upper triangle is written, dead ones as
+//     zeros with 16-byte stores.
+__device__ __forceinline__ void affinity_tile(const RbProblem& pr, int I, int J, unsigned row_live, unsigned col_live,
+                                              const RbAssocSoA& rec, Rec* s_row, double* __restrict__ Mp,
+                                              uint8_t* __restrict__ flags, const RbDevParams& P, int lane) {
+  const int64_t q = rb_tile_index(I, J, pr.nb);
+  double* out = Mp + (pr.off_tile + q) * RB_TILE_ELEMS;
+  const Rec col = load_rec(rec, pr.off_pad + (int64_t)J * RB_TILE + lane);
+  const Rec myrow = load_rec(rec, pr.off_pad + (int64_t)I * RB_TILE + lane);
+  __syncwarp();
+  s_row[lane] = myrow;
+  __syncwarp();
+  const bool diag = (I == J);
+  bool any_nz = false;
+#pragma unroll 4
+  for (int r = 0; r < RB_TILE; ++r) {
+    double v = 0.0;
+    if (((row_live >> r) & 1u) && ((col_live >> lane) & 1u)) {
+      const Rec row = s_row[r];
+      if (!diag || r < lane) v = pair_score(P, row, col);       // i = row index < j = column index
+      else if (r > lane) v = pair_score(P, col, row);           // mirrored entry of the diagonal tile
+      // r == lane: identity is implicit (clipper.cpp:129-130)
+    }
+    any_nz |= (v != 0.0);
+    out[rb_tile_elem(r, lane)] = v;
+  }
+  const unsigned nzb = __ballot_sync(0xffffffffu, any_nz);
+  if (flags && lane == 0) flags[pr.off_tile + q] = nzb ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) rb_affinity_kernel(const RbProblem* __restrict__ probs, RbAssocSoA rec,
+                                                          const uint32_t* __restrict__ masks,
                                                           double* __restrict__ Mp, uint8_t* __restrict__ flags,
                                                           RbDevParams P) {
   __shared__ Rec s_row[8][RB_TILE];
+  __shared__ unsigned s_mask[256];   // live mask per block (nb <= 160)
+  __shared__ unsigned char s_live[256];  // indices of live blocks, ascending
+  __shared__ int s_nl;
+  const RbProblem pr = probs[blockIdx.y];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int64_t tt = (int64_t)blockIdx.x * 8 + warp; tt < total_tiles; tt += (int64_t)gridDim.x * 8) {
-    const int64_t t = tt + tile_base;  // probs / tile_prefix point at the first problem of the launched range
-    int lo = 0, hi = B;  // largest b with tile_prefix[b] <= t
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (tile_prefix[mid] <= t) lo = mid; else hi = mid;
+  const int nb = pr.nb;
+  if (nb == 0) return;
+  // An association whose single score is below affinityeps (clipper.cpp:104-108), or padding, can
+  // have no edge at all (NaN scores are "live", exactly as the reference's `<` test);
+  // rb_block_mask_kernel has condensed that into one word per 32-association block.
+  for (int i = threadIdx.x; i < nb; i += 256) s_mask[i] = masks[(pr.off_pad >> 5) + i];
+  __syncthreads();
+  if (warp == 0) {
+    int n = 0;
+    for (int i0 = 0; i0 < nb; i0 += 32) {
+      const int i = i0 + lane;
+      const bool lv = (i < nb) && s_mask[i] != 0u;
+      const unsigned mk = __ballot_sync(0xffffffffu, lv);
+      if (lv) s_live[n + __popc(mk & ((1u << lane) - 1u))] = (unsigned char)i;
+      n += __popc(mk);
     }
-    const RbProblem pr = probs[lo];
-    const int64_t q = t - tile_prefix[lo];
-    int I, J;
-    tile_coords(q, pr.nb, I, J);
-    const int64_t oc = pr.off_pad + (int64_t)J * RB_TILE + lane, orow = pr.off_pad + (int64_t)I * RB_TILE + lane;
-    double* out = Mp + (pr.off_tile + q) * RB_TILE_ELEMS;
-    // An association whose single score is below affinityeps (clipper.cpp:104-108), or padding,
-    // can have no edge at all: rows/columns made only of such associations need no evaluation.
-    // (NaN scores are "live", exactly as the reference's `<` test.)  Only the 12 bytes that
-    // decide this are read first; the full records follow for live tiles only.
-    const bool roman = (P.inv.kind == RB_INVARIANT_ROMAN);
-    const unsigned col_live = __ballot_sync(0xffffffffu, rec.i1[oc] >= 0 && !(roman && rec.single[oc] < P.affinityeps));
-    const unsigned row_live = __ballot_sync(0xffffffffu, rec.i1[orow] >= 0 && !(roman && rec.single[orow] < P.affinityeps));
-    if (col_live == 0u || row_live == 0u) {
-      if (flags) {  // tile-skip format: a dead tile is recorded as such and never written nor read
-        if (lane == 0) flags[pr.off_tile + q] = 0;
-      } else {
-        double2* o2 = reinterpret_cast<double2*>(out);
+    if (lane == 0) s_nl = n;
+  }
+  __syncthreads();
+  const int nl = s_nl;
+
+  if (flags) {
+    // live x live block pairs only: pair index pi <-> (a <= b) over the live-block list
+    const int npairs = nl * (nl + 1) / 2;
+    for (int pi = blockIdx.x * 8 + warp; pi < npairs; pi += gridDim.x * 8) {
+      // invert pi = a*nl - a(a-1)/2 + (b - a)
+      int a = (int)floor(((2.0 * nl + 1.0) - sqrt((2.0 * nl + 1.0) * (2.0 * nl + 1.0) - 8.0 * (double)pi)) * 0.5);
+      if (a < 0) a = 0;
+      if (a > nl - 1) a = nl - 1;
+      while (a > 0 && a * nl - a * (a - 1) / 2 > pi) --a;
+      while (a + 1 < nl && (a + 1) * nl - (a + 1) * a / 2 <= pi) ++a;
+      const int bcol = a + (pi - (a * nl - a * (a - 1) / 2));
+      const int I = s_live[a], J = s_live[bcol];
+      affinity_tile(pr, I, J, s_mask[I], s_mask[J], rec, s_row[warp], Mp, flags, P, lane);
+    }
+  } else {
+    const int nt = (int)pr.n_tiles;
+    for (int q = blockIdx.x * 8 + warp; q < nt; q += gridDim.x * 8) {
+      int I, J;
+      tile_coords(q, nb, I, J);
+      const unsigned row_live = s_mask[I], col_live = s_mask[J];
+      if (row_live == 0u || col_live == 0u) {
+        double2* o2 = reinterpret_cast<double2*>(Mp + (pr.off_tile + q) * RB_TILE_ELEMS);
 #pragma unroll
         for (int t = 0; t < RB_TILE_ELEMS / 2 / 32; ++t) o2[t * 32 + lane] = make_double2(0.0, 0.0);
+        continue;
       }
-      continue;
+      affinity_tile(pr, I, J, row_live, col_live, rec, s_row[warp], Mp, nullptr, P, lane);
     }
-    const Rec col = load_rec(rec, oc);
-    const Rec myrow = load_rec(rec, orow);
-    __syncwarp();
-    s_row[warp][lane] = myrow;
-    __syncwarp();
-    const bool diag = (I == J);
-    bool any_nz = false;
-#pragma unroll 4
-    for (int r = 0; r < RB_TILE; ++r) {
-      double v = 0.0;
-      if ((row_live >> r) & 1u) {
-        const Rec row = s_row[warp][r];
-        if (!diag || r < lane) v = pair_score(P, row, col);       // i = row index < j = column index
-        else if (r > lane) v = pair_score(P, col, row);           // mirrored entry of the diagonal tile
-        // r == lane: identity is implicit (clipper.cpp:129-130)
-      }
-      any_nz |= (v != 0.0);
-      out[rb_tile_elem(r, lane)] = v;
-    }
-    const unsigned nzb = __ballot_sync(0xffffffffu, any_nz);
-    if (flags && lane == 0) flags[pr.off_tile + q] = nzb ? 1 : 0;
   }
 }
 
@@ -524,14 +575,32 @@ cudaError_t rb_launch_prep(const RbProblem* probs, int B, int max_mp, int max_n1
   return cudaGetLastError();
 }
 
-cudaError_t rb_launch_affinity(const RbProblem* probs, int B, const int64_t* tile_prefix, int64_t tile_base,
-                               int64_t total_tiles, const RbAssocSoA& rec, double* Mp, uint8_t* flags,
+cudaError_t rb_launch_affinity(const RbProblem* probs, int B, int64_t tile_base, int64_t total_tiles, int max_nb,
+                               const RbAssocSoA& rec, uint32_t* masks, double* Mp, uint8_t* flags,
                                const RbDevParams& P, int sm_count, cudaStream_t st) {
-  if (total_tiles == 0) return cudaSuccess;
-  int64_t want = (total_tiles + 7) / 8;
-  const int64_t cap = (int64_t)sm_count * 8;  // 8 CTAs of 256 threads per SM, persistent
-  const int grid = (int)(want < cap ? want : cap);
-  rb_affinity_kernel<<<grid, 256, 0, st>>>(probs, B, tile_prefix, tile_base, total_tiles, rec, Mp, flags, P);
+  if (total_tiles == 0 || B == 0) return cudaSuccess;
+  if (max_nb > 255) return cudaErrorInvalidValue;
+  {
+    dim3 g((max_nb + 7) / 8, B);
+    rb_block_mask_kernel<<<g, 256, 0, st>>>(probs, rec, masks, P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  if (flags) {  // tile-skip format: dead tiles are never visited, so their flags are cleared up front
+    cudaError_t e = cudaMemsetAsync(flags + tile_base, 0, (size_t)total_tiles, st);
+    if (e != cudaSuccess) return e;
+  }
+  // CTAs per problem: enough warps to cover the largest problem's tiles a few per warp, and at least
+  // ~8 CTAs per SM over the whole launch when there are few problems
+  const int64_t nt_max = (int64_t)max_nb * (max_nb + 1) / 2;
+  int64_t per = (nt_max + 8 * 8 - 1) / (8 * 8);
+  const int64_t fill = ((int64_t)sm_count * 8 + B - 1) / B;
+  if (per < fill) per = fill;
+  const int64_t cap = (nt_max + 7) / 8;
+  if (per > cap) per = cap;
+  if (per < 1) per = 1;
+  dim3 grid((unsigned)per, (unsigned)B);
+  rb_affinity_kernel<<<grid, 256, 0, st>>>(probs, rec, masks, Mp, flags, P);
   return cudaGetLastError();
 }
 

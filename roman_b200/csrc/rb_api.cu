@@ -38,6 +38,7 @@ struct rb_handle {
   bool tile_skip = true;                              // rb_set_tile_skip
   double* d_pad_f64 = nullptr; size_t cap_pad = 0;    // padded double arrays (7 record + u, g per cluster CTA)
   int32_t* d_pad_i32 = nullptr;                       // 2 padded int arrays
+  uint32_t* d_masks = nullptr;                        // one live-mask word per 32-association block
   int32_t* d_counter = nullptr;
   int* d_bad = nullptr;
   long long* d_debug = nullptr;  // dev builds: per-CTA cycle counters of the solver
@@ -182,7 +183,7 @@ int rb_destroy(rb_handle* h) {
   if (!h) return RB_OK;
   cudaSetDevice(h->device);
   cudaFree(h->d_probs); cudaFree(h->d_tile_prefix); cudaFree(h->d_M); cudaFree(h->d_flags); cudaFree(h->d_pad_f64);
-  cudaFree(h->d_pad_i32); cudaFree(h->d_counter); cudaFree(h->d_bad); cudaFree(h->d_nodes); cudaFree(h->d_sel);
+  cudaFree(h->d_pad_i32); cudaFree(h->d_masks); cudaFree(h->d_counter); cudaFree(h->d_bad); cudaFree(h->d_nodes); cudaFree(h->d_sel);
   cudaFree(h->d_nsel); cudaFree(h->d_score); cudaFree(h->d_ifinal); cudaFree(h->d_npass);
   cudaFree(h->d_status); cudaFree(h->d_T);
   cudaFree(h->s_D1); cudaFree(h->s_D2); cudaFree(h->s_A); cudaFree(h->s_u0);
@@ -363,6 +364,9 @@ int rb_plan(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const int32_t
       const size_t n = need ? need : 1;
       RB_CUDA(h, cudaMalloc((void**)&h->d_pad_f64, (size_t)kPadArrays * n * sizeof(double)));
       RB_CUDA(h, cudaMalloc((void**)&h->d_pad_i32, 2 * n * sizeof(int32_t)));
+      if (h->d_masks) cudaFree(h->d_masks);
+      h->d_masks = nullptr;
+      RB_CUDA(h, cudaMalloc((void**)&h->d_masks, (n / RB_TILE + 1) * sizeof(uint32_t)));
       h->cap_pad = n;
     }
   }
@@ -445,9 +449,8 @@ int affinity_range(rb_handle* h, int b0, int b1, const double* D1, const double*
                             h->all_to_all ? nullptr : A, P, st));
   record(h, 1, st);
   const int64_t base = h->tile_prefix[(size_t)b0];
-  RB_CUDA(h, rb_launch_affinity(h->d_probs + b0, b1 - b0, h->d_tile_prefix + b0, base,
-                                h->tile_prefix[(size_t)b1] - base, rec, h->d_M, h->tile_skip ? h->d_flags : nullptr, P,
-                                h->sm_count, st));
+  RB_CUDA(h, rb_launch_affinity(h->d_probs + b0, b1 - b0, base, h->tile_prefix[(size_t)b1] - base, h->max_mp / RB_TILE,
+                                rec, h->d_masks, h->d_M, h->tile_skip ? h->d_flags : nullptr, P, h->sm_count, st));
   record(h, 2, st);
   return RB_OK;
 }

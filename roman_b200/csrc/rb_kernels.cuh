@@ -42,8 +42,8 @@ struct RbSolveArgs {
 cudaError_t rb_launch_prep(const RbProblem* probs, int B, int max_mp, int max_n1, int max_n2, bool all_to_all,
                            const RbAssocSoA& rec, const double* D1, const double* D2, const int32_t* A,
                            const RbDevParams& P, cudaStream_t st);
-cudaError_t rb_launch_affinity(const RbProblem* probs, int B, const int64_t* tile_prefix, int64_t tile_base,
-                               int64_t total_tiles, const RbAssocSoA& rec, double* Mp, uint8_t* flags,
+cudaError_t rb_launch_affinity(const RbProblem* probs, int B, int64_t tile_base, int64_t total_tiles, int max_nb,
+                               const RbAssocSoA& rec, uint32_t* masks, double* Mp, uint8_t* flags,
                                const RbDevParams& P, int sm_count, cudaStream_t st);
 cudaError_t rb_launch_count_flags(const RbProblem* probs, int B, const uint8_t* flags, int32_t* out, cudaStream_t st);
 cudaError_t rb_launch_unpack(const RbProblem& pr, const double* Mp, const uint8_t* flags, double* Mout, double* Cout,

@@ -90,8 +90,10 @@ struct Smem {
   uint64_t* bar; // [NW][SLOTS]
   double* ring;  // [NW][SLOTS][1024]
   int* misc;     // small ints / broadcast slots
-  const uint8_t* flag;    // this problem's tile flags (shared-memory copy), or null: stream every tile
-  const uint8_t* rowany;  // per tile-row: any flagged tile (null with flag == null)
+  uint16_t* wlist;        // tile-skip format: per warp, its stored tiles (I << 8 | J) in processing order; else null
+  int wl_cap;             // entries per warp in wlist
+  int* wcnt;              // [NW] tiles per warp, [NW] = number of live tile-rows of this CTA
+  uint8_t* live_rows;     // the CTA's live tile-rows in processing order
   int slots;     // TMA ring slots per warp (1 or 2)
   int depth;     // tile-rows in flight between the fastest and slowest warp: 8 (decoupled) or 2 (lock-step)
 };
@@ -140,11 +142,10 @@ struct Reducer {
 // A tile sits in shared memory in the XOR-swizzled layout of rb_common.cuh, so one warp sweeps
 // it twice without bank conflicts: with lane = row (row sums of block I, one register per lane,
 // no cross-lane reduction) and with lane = column (column sums of block J).
-struct TileIter {
+__device__ long long g_dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+struct TileIter {  // dense format: the arithmetic tile sequence of one warp
   int nb, C, w, p, h, I, J;
-  const uint8_t* F;  // tile flags or null
   bool ok;
-  __device__ __forceinline__ bool live(int i, int j) const { return F == nullptr || F[rb_tile_index(i, j, nb)] != 0; }
   __device__ __forceinline__ int row() const { return h == 0 ? p : nb - 1 - p; }
   // position on the first tile (J >= I, J mod NW == w) at or after tile-row slot (p, h)
   __device__ __forceinline__ void settle() {
@@ -153,35 +154,127 @@ struct TileIter {
       if (!(h == 1 && nb - 1 - p == p)) {  // the middle tile-row of an odd nb is visited once
         I = row();
         J = I + ((w - I) % NW + NW) % NW;
-        while (J < nb && !live(I, J)) J += NW;
         if (J < nb) { ok = true; return; }
       }
       if (h == 0) h = 1; else { h = 0; p += C; }
     }
     ok = false;
   }
-  __device__ __forceinline__ void init(int nb_, int C_, int crank, int w_, const uint8_t* F_) {
-    nb = nb_; C = C_; w = w_; p = crank; h = 0; I = 0; J = 0; F = F_;
+  __device__ __forceinline__ void init(int nb_, int C_, int crank, int w_) {
+    nb = nb_; C = C_; w = w_; p = crank; h = 0; I = 0; J = 0;
     settle();
   }
   __device__ __forceinline__ void next() {
     J += NW;
-    while (J < nb && !live(I, J)) J += NW;
     if (J < nb) return;
     if (h == 0) h = 1; else { h = 0; p += C; }
     settle();
   }
 };
 
-__device__ __forceinline__ void matvec_pass(const Smem& S, const double* __restrict__ tiles, int nb,
-                                            uint32_t& phase_bits, int C, int crank) {
+struct RowAcc {  // row sums of one tile-row held by a warp: lane = row
+  double rM0, rC0;
+  __device__ __forceinline__ void clear() { rM0 = rC0 = 0.0; }
+};
+
+// One tile, already in shared memory (XOR-swizzled): row sums into `ra`, column sums into this
+// warp's output block J.  Affinity matrices are sparse inside a tile as well (a few edges per 32x32
+// block), so the tile is first reduced to bit masks — which words of my row are non-zero (lane = row),
+// and, by a ballot transpose, which rows are non-zero in my column (lane = column) — and the fp64
+// work then runs over the set bits only, in ascending index order.  A stored -0.0 (constraint-only
+// entry of rb_set_dense) counts as present: it adds nothing to M x and x to C x.
+__device__ __forceinline__ void process_tile(const Smem& S, const double* __restrict__ buf, int I, int J, int lane,
+                                             RowAcc& ra) {
+  const double* xI = S.x + I * RB_TILE;
+  const double* xJ = S.x + J * RB_TILE;
+  const double* rowp = buf + lane * RB_TILE;  // this lane's row (row orientation)
+  unsigned rowmask = 0u;
+  {
+    const ulonglong2* rp2 = reinterpret_cast<const ulonglong2*>(rowp);
+#pragma unroll
+    for (int t = 0; t < RB_TILE / 2; ++t) {
+      const int ch = t ^ (lane & 15);  // a permutation of the row's 16-byte chunks, conflict-free
+      const ulonglong2 q = rp2[ch];
+      // chunk ch holds physical words 2ch, 2ch+1 = logical columns (2ch)^lane, (2ch+1)^lane
+      if (q.x != 0ull) rowmask |= 1u << ((2 * ch) ^ lane);
+      if (q.y != 0ull) rowmask |= 1u << ((2 * ch + 1) ^ lane);
+    }
+  }
+  unsigned cols = __reduce_or_sync(0xffffffffu, rowmask);  // columns holding any entry
+  if (cols == 0u) return;
+  {  // row sums: lane = row
+    unsigned mk = rowmask;
+    double sM = 0.0, sC = 0.0;
+    while (mk) {
+      const int t = __ffs(mk) - 1;
+      mk &= mk - 1;
+      const double v = rowp[t ^ lane];
+      const double xj = xJ[t];
+      sM = fma(v, xj, sM);
+      sC += xj;
+    }
+    ra.rM0 += sM;
+    ra.rC0 += sC;
+  }
+  if (J == I) return;  // diagonal tile holds both triangles: row sums only
+  {  // column sums: lane = column; colmask bit r <=> (r, lane) is present
+    unsigned colmask = 0u;
+    while (cols) {
+      const int t = __ffs(cols) - 1;
+      cols &= cols - 1;
+      const unsigned bt = __ballot_sync(0xffffffffu, (rowmask >> t) & 1u);
+      if (lane == t) colmask = bt;
+    }
+    double sM = 0.0, sC = 0.0;
+    while (colmask) {
+      const int r = __ffs(colmask) - 1;
+      colmask &= colmask - 1;
+      const double v = buf[r * RB_TILE + (lane ^ r)];
+      const double xi = xI[r];
+      sM = fma(v, xi, sM);
+      sC += xi;
+    }
+    // this warp is the only writer of output block J in this CTA
+    S.accM[J * RB_TILE + lane] += sM;
+    S.accC[J * RB_TILE + lane] += sC;
+  }
+}
+
+// Combine the 8 warps' row partials of block I (fixed order) into this CTA's accumulators.
+// depth == 8: a warp only WAITS on the tile-row's named barrier when it has to — as the owner of
+// block I, or once every 8 tile-rows so that nobody runs more than 7 tile-rows ahead of the
+// slowest warp (the partial ring and the barrier ids are reused modulo 8) — and otherwise just
+// ARRIVES and moves on, so one warp's late tile does not stall the CTA's seven other TMA rings.
+__device__ __forceinline__ void finish_tile_row(const Smem& S, int I, int pos, int lane, int w, const RowAcc& ra) {
+  const int pslot = pos % S.depth;
+  double* part = S.part + (size_t)pslot * (NW * 2 * RB_TILE);
+  part[(w * 2 + 0) * RB_TILE + lane] = ra.rM0;
+  part[(w * 2 + 1) * RB_TILE + lane] = ra.rC0;
+  const bool owner = ((I % NW) == w);
+  if (owner || S.depth < MAX_DEPTH || (pos % NW) == w) named_bar_sync(1 + pslot, NT);
+  else named_bar_arrive(1 + pslot, NT);
+  if (owner) {
+    double sm = 0.0, sc = 0.0;
+#pragma unroll
+    for (int ww = 0; ww < NW; ++ww) {
+      sm += part[(ww * 2 + 0) * RB_TILE + lane];
+      sc += part[(ww * 2 + 1) * RB_TILE + lane];
+    }
+    S.accM[I * RB_TILE + lane] += sm;
+    S.accC[I * RB_TILE + lane] += sc;
+  }
+}
+
+// Dense format: every tile of the packed upper triangle is fetched.
+__device__ __forceinline__ void matvec_pass_dense(const Smem& S, const double* __restrict__ tiles, int nb,
+                                               uint32_t& phase_bits, int C, int crank) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int SLOTS = S.slots;
   uint64_t* bar = S.bar + w * MAX_SLOTS;
   double* ring = S.ring + (size_t)w * SLOTS * RB_TILE_ELEMS;
 
   TileIter pf;  // prefetch iterator: runs SLOTS tiles ahead of the consumer along the same sequence
-  pf.init(nb, C, crank, w, S.flag);
+  pf.init(nb, C, crank, w);
   auto pf_issue = [&](int slot) {
     if (lane == 0)
       tma_load_tile(ring + slot * RB_TILE_ELEMS, tiles + rb_tile_index(pf.I, pf.J, nb) * RB_TILE_ELEMS, bar + slot);
@@ -196,97 +289,111 @@ __device__ __forceinline__ void matvec_pass(const Smem& S, const double* __restr
     for (int h = 0; h < 2; ++h) {
       const int I = (h == 0) ? p : nb - 1 - p;
       if (h == 1 && I == p) break;
-      if (S.rowany && !S.rowany[I]) continue;  // no flagged tile in this tile-row: nothing to add, for any warp
-      // row sums of block I over this warp's tiles: lane = row; two chains each to shorten the
-      // dependent-add latency
-      double rM0 = 0.0, rM1 = 0.0, rC0 = 0.0, rC1 = 0.0;
-      const double* xI = S.x + I * RB_TILE;
-
+      RowAcc ra;
+      ra.clear();
       for (int J = I + ((w - I) % NW + NW) % NW; J < nb; J += NW) {
-        if (S.flag && !S.flag[rb_tile_index(I, J, nb)]) continue;  // not stored / all zero: never fetched
         mbar_wait(bar + slot, (phase_bits >> slot) & 1u);
         phase_bits ^= (1u << slot);
-        const double* buf = ring + slot * RB_TILE_ELEMS;
-        const double* xJ = S.x + J * RB_TILE;
-        const double* rowp = buf + lane * RB_TILE;  // this lane's row (row orientation)
-        // An all-(+0.0) tile contributes nothing to either product: find out with 16 wide loads
-        // per lane and one vote, and skip the fp64 work (the bytes were still streamed, as always).
-        unsigned long long any = 0ull;
-        {
-          const ulonglong2* rp2 = reinterpret_cast<const ulonglong2*>(rowp);
-#pragma unroll
-          for (int t = 0; t < RB_TILE / 2; ++t) {
-            const ulonglong2 q = rp2[t ^ (lane & 15)];  // a permutation of the row's 16-byte chunks, conflict-free
-            any |= q.x | q.y;
-          }
-        }
-        if (!__any_sync(0xffffffffu, any != 0ull)) {
-          // nothing to do
-        } else if (J != I) {
-          double cM0 = 0.0, cM1 = 0.0, cC0 = 0.0, cC1 = 0.0;
-#pragma unroll
-          for (int t = 0; t < RB_TILE; t += 2) {
-            // row orientation: elements (lane, t), (lane, t+1); x_J[t], x_J[t+1] are broadcasts
-            const double a0 = rowp[t ^ lane], a1 = rowp[(t + 1) ^ lane];
-            const double2 xj = *reinterpret_cast<const double2*>(xJ + t);
-            rM0 = fma(a0, xj.x, rM0);
-            rM1 = fma(a1, xj.y, rM1);
-            if (__double_as_longlong(a0) != 0ll) rC0 += xj.x;  // +0.0 <=> no edge (-0.0: constraint-only)
-            if (__double_as_longlong(a1) != 0ll) rC1 += xj.y;
-            // column orientation: elements (t, lane), (t+1, lane); x_I[t], x_I[t+1] are broadcasts
-            const double b0 = buf[t * RB_TILE + (lane ^ t)], b1 = buf[(t + 1) * RB_TILE + (lane ^ (t + 1))];
-            const double2 xi = *reinterpret_cast<const double2*>(xI + t);
-            cM0 = fma(b0, xi.x, cM0);
-            cM1 = fma(b1, xi.y, cM1);
-            if (__double_as_longlong(b0) != 0ll) cC0 += xi.x;
-            if (__double_as_longlong(b1) != 0ll) cC1 += xi.y;
-          }
-          // this warp is the only writer of output block J in this CTA
-          S.accM[J * RB_TILE + lane] += cM0 + cM1;
-          S.accC[J * RB_TILE + lane] += cC0 + cC1;
-        } else {
-          // diagonal tile holds both triangles: row sums only
-#pragma unroll
-          for (int t = 0; t < RB_TILE; t += 2) {
-            const double a0 = rowp[t ^ lane], a1 = rowp[(t + 1) ^ lane];
-            const double2 xj = *reinterpret_cast<const double2*>(xJ + t);
-            rM0 = fma(a0, xj.x, rM0);
-            rM1 = fma(a1, xj.y, rM1);
-            if (__double_as_longlong(a0) != 0ll) rC0 += xj.x;
-            if (__double_as_longlong(a1) != 0ll) rC1 += xj.y;
-          }
-        }
+        process_tile(S, ring + slot * RB_TILE_ELEMS, I, J, lane, ra);
         __syncwarp();
         if (pf.ok) pf_issue(slot);  // refill the slot just drained
         slot = (slot + 1 == SLOTS) ? 0 : slot + 1;
       }
-
-      // Combine the 8 warps' row partials of block I (fixed order) into this CTA's accumulators.
-      // depth == 8: a warp only WAITS on the tile-row's named barrier when it has to — as the
-      // owner of block I, or once every 8 tile-rows so that nobody runs more than 7 tile-rows
-      // ahead of the slowest warp (the partial ring and the barrier ids are reused modulo 8) —
-      // and otherwise just ARRIVES and moves on, so one warp's late tile does not stall the
-      // CTA's seven other TMA rings.
-      const int pslot = pos % S.depth;
-      double* part = S.part + (size_t)pslot * (NW * 2 * RB_TILE);
-      part[(w * 2 + 0) * RB_TILE + lane] = rM0 + rM1;
-      part[(w * 2 + 1) * RB_TILE + lane] = rC0 + rC1;
-      const bool owner = ((I % NW) == w);
-      if (owner || S.depth < MAX_DEPTH || (pos % NW) == w) named_bar_sync(1 + pslot, NT);
-      else named_bar_arrive(1 + pslot, NT);
-      if (owner) {
-        double sm = 0.0, sc = 0.0;
-#pragma unroll
-        for (int ww = 0; ww < NW; ++ww) {
-          sm += part[(ww * 2 + 0) * RB_TILE + lane];
-          sc += part[(ww * 2 + 1) * RB_TILE + lane];
-        }
-        S.accM[I * RB_TILE + lane] += sm;
-        S.accC[I * RB_TILE + lane] += sc;
-      }
+      finish_tile_row(S, I, pos, lane, w, ra);
       ++pos;
     }
   }
+}
+
+// Tile-skip format: each warp walks the list of ITS stored tiles (built once per problem by
+// build_tile_lists from the tile flags), tile-row by tile-row over the CTA's live tile-rows.
+__device__ __forceinline__ void matvec_pass_list(const Smem& S, const double* __restrict__ tiles, int nb,
+                                              uint32_t& phase_bits) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int SLOTS = S.slots;
+  uint64_t* bar = S.bar + w * MAX_SLOTS;
+  double* ring = S.ring + (size_t)w * SLOTS * RB_TILE_ELEMS;
+  const uint16_t* wl = S.wlist + (size_t)w * S.wl_cap;
+  const int cnt = S.wcnt[w], nlive = S.wcnt[NW];
+
+  int kpf = 0;
+  auto pf_issue = [&](int slot) {
+    const int e = wl[kpf++];
+    if (lane == 0)
+      tma_load_tile(ring + slot * RB_TILE_ELEMS, tiles + rb_tile_index(e >> 8, e & 255, nb) * RB_TILE_ELEMS, bar + slot);
+  };
+  for (int s = 0; s < SLOTS; ++s)
+    if (kpf < cnt) pf_issue(s);
+
+  int slot = 0, k = 0;
+  long long dw = 0, dc = 0, db = 0, t_in = clock64();
+  for (int pos = 0; pos < nlive; ++pos) {
+    const int I = S.live_rows[pos];
+    RowAcc ra;
+    ra.clear();
+    while (k < cnt && (wl[k] >> 8) == I) {
+      const int J = wl[k] & 255;
+      long long q0 = clock64();
+      mbar_wait(bar + slot, (phase_bits >> slot) & 1u);
+      long long q1 = clock64();
+      phase_bits ^= (1u << slot);
+      process_tile(S, ring + slot * RB_TILE_ELEMS, I, J, lane, ra);
+      __syncwarp();
+      dw += q1 - q0; dc += clock64() - q1;
+      if (kpf < cnt) pf_issue(slot);
+      slot = (slot + 1 == SLOTS) ? 0 : slot + 1;
+      ++k;
+    }
+    long long b0 = clock64();
+    finish_tile_row(S, I, pos, lane, w, ra);
+    db += clock64() - b0;
+  }
+  if (blockIdx.x < 8 && w == 3 && lane == 0) {
+    atomicAdd((unsigned long long*)&g_dbg[0], (unsigned long long)dw); atomicAdd((unsigned long long*)&g_dbg[1], (unsigned long long)dc);
+    atomicAdd((unsigned long long*)&g_dbg[2], (unsigned long long)db); atomicAdd((unsigned long long*)&g_dbg[3], (unsigned long long)cnt);
+    atomicAdd((unsigned long long*)&g_dbg[4], (unsigned long long)nlive); atomicAdd((unsigned long long*)&g_dbg[5], 1ull);
+    atomicAdd((unsigned long long*)&g_dbg[6], (unsigned long long)(clock64() - t_in));
+  }
+}
+
+// Once per problem (tile-skip format): from the tile flags, the CTA's live tile-rows in
+// processing order and, per warp, the list of its stored tiles (I << 8 | J) in that order.
+__device__ __forceinline__ void build_tile_lists(const Smem& S, const uint8_t* __restrict__ gflags, int nb, int C,
+                                                 int crank) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint16_t* wl = S.wlist + (size_t)w * S.wl_cap;
+  int cnt = 0, nlive = 0;
+  const int npairs = (nb + 1) >> 1;
+  for (int p = crank; p < npairs; p += C) {
+    for (int h = 0; h < 2; ++h) {
+      const int I = (h == 0) ? p : nb - 1 - p;
+      if (h == 1 && I == p) break;
+      const int64_t base = rb_tile_index(I, I, nb) - I;  // + J gives the tile index of (I, J)
+      // any stored tile in tile-row I?  (uniform over the CTA: every warp scans the whole row)
+      unsigned any = 0;
+      for (int J = I + lane; J < nb; J += 32) any |= gflags[base + J];
+      if (!__any_sync(0xffffffffu, any != 0)) continue;
+      if (w == 0 && lane == 0) S.live_rows[nlive] = (uint8_t)I;
+      ++nlive;
+      // this warp's columns of the row: J = J0 + 8 t
+      const int J0 = I + ((w - I) % NW + NW) % NW;
+      for (int t0 = 0; J0 + NW * t0 < nb; t0 += 32) {
+        const int J = J0 + NW * (t0 + lane);
+        const bool st = (J < nb) && gflags[base + J] != 0;
+        const unsigned mk = __ballot_sync(0xffffffffu, st);
+        if (st) wl[cnt + __popc(mk & ((1u << lane) - 1u))] = (uint16_t)((I << 8) | J);
+        cnt += __popc(mk);
+      }
+    }
+  }
+  if (lane == 0) S.wcnt[w] = cnt;
+  if (w == 0 && lane == 0) S.wcnt[NW] = nlive;
+}
+
+__device__ __forceinline__ void matvec_pass(const Smem& S, const double* __restrict__ tiles, int nb,
+                                            uint32_t& phase_bits, int C, int crank) {
+  if (S.wlist) matvec_pass_list(S, tiles, nb, phase_bits);
+  else matvec_pass_dense(S, tiles, nb, phase_bits, C, crank);
 }
 
 // Combine the per-CTA partial (accM, accC) of a cluster through distributed shared memory:
@@ -342,8 +449,11 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
     S.red = (double*)p; p += (size_t)RED_DOUBLES * 8;
     S.bar = (uint64_t*)p; p += (size_t)NW * MAX_SLOTS * 8;
     S.misc = (int*)p; p += (size_t)MISC_INTS * 4;
-    S.flag = A.flags ? (const uint8_t*)p : nullptr; p += (size_t)((A.nt_max + 15) / 16) * 16;
-    S.rowany = A.flags ? (const uint8_t*)p : nullptr;
+    S.wcnt = S.misc + 4;
+    const int nbm = A.mp_max / RB_TILE;
+    S.wl_cap = (A.nt_max + NW - 1) / NW + nbm;
+    S.wlist = A.flags ? (uint16_t*)p : nullptr; p += (size_t)NW * S.wl_cap * 2;
+    S.live_rows = (uint8_t*)p;
   }
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -379,18 +489,8 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
     double* g = A.g_work + (size_t)crank * A.pad_stride + pr.off_pad;
     const double* u0 = A.u0 + pr.off_assoc;
     int passes = 0;
-    if (A.flags) {  // this problem's tile flags and per-tile-row summary into shared memory
-      uint8_t* fl = const_cast<uint8_t*>(S.flag);
-      uint8_t* ra = const_cast<uint8_t*>(S.rowany);
-      const int nt = (int)pr.n_tiles;
-      for (int t = tid; t < nt; t += NT) fl[t] = A.flags[pr.off_tile + t];
-      __syncthreads();
-      for (int I = tid; I < nb; I += NT) {
-        uint8_t any = 0;
-        const int64_t base = rb_tile_index(I, I, nb);
-        for (int J = I; J < nb; ++J) any |= fl[base + (J - I)];
-        ra[I] = any;
-      }
+    if (A.flags) {
+      build_tile_lists(S, A.flags + pr.off_tile, nb, C, crank);
       __syncthreads();
     }
 
@@ -641,6 +741,7 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
   if (A.debug && tid == 0) {
     long long* d = A.debug + (size_t)blockIdx.x * 8;
     d[0] = clock64() - t_tot0; d[1] = t_mv; d[2] = t_cb; d[3] = t_q; d[4] = t_round;
+    if (blockIdx.x == 1) for (int i = 0; i < 8; ++i) d[i] = g_dbg[i];
   }
 }
 
@@ -648,10 +749,11 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
 
 size_t rb_solver_smem_bytes(int mp_max, int slots, int depth) {
   const int nb = mp_max / RB_TILE;
-  const size_t nt = (size_t)nb * (nb + 1) / 2;  // tile flags + per-tile-row summary (tile-skip mode)
+  const size_t nt = (size_t)nb * (nb + 1) / 2;
+  const size_t wl_cap = (nt + NW - 1) / NW + nb;  // tile-skip format: per-warp tile lists + live tile-rows
   return (size_t)NW * slots * RB_TILE_BYTES + (size_t)3 * mp_max * 8 + (size_t)depth * NW * 2 * RB_TILE * 8 +
-         (size_t)RED_DOUBLES * 8 + (size_t)NW * MAX_SLOTS * 8 + (size_t)MISC_INTS * 4 + ((nt + 15) / 16) * 16 +
-         (size_t)((nb + 15) / 16) * 16;
+         (size_t)RED_DOUBLES * 8 + (size_t)NW * MAX_SLOTS * 8 + (size_t)MISC_INTS * 4 + (size_t)NW * wl_cap * 2 +
+         (size_t)((nb + 15) / 16) * 16 + 16;
 }
 
 // Largest shared-memory configuration that fits: (2 slots, depth 8) > (2, 2) > (1, 2).
