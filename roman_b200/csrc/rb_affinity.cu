@@ -213,25 +213,29 @@ __global__ void __launch_bounds__(256) rb_prep_kernel(const RbProblem* __restric
 // ---------------------------------------------------------------------------------------------
 // K1a for all-to-all plans: the n1 x n2 cosine table is a small dense contraction
 // (descriptors^T * descriptors), so it is tiled through shared memory instead of re-reading two
-// D-vectors per association: one CTA per 64x64 block of (object of map 1, object of map 2), 4x4
-// outputs per thread, descriptors streamed once in chunks of 32 columns.  Each dot product and
-// squared norm is accumulated sequentially over the descriptor index with separate multiply and
-// add (the translation unit is built with -fmad=false), i.e. in the same order as the scalar loop
-// of the reference's restatement.
-constexpr int PT = 64;   // objects per tile edge
-constexpr int PK = 32;   // descriptor columns per chunk
+// D-vectors per association.  One CTA per (<=64) x (<=64) block of (object of map 1, object of map
+// 2); the thread grid is TY x TX with 4x4 outputs per thread, sized to the batch's largest maps
+// (40 x 50 objects -> 10 x 13 threads), descriptors streamed once in chunks of 32 columns and kept
+// k-major in shared memory so that a thread's four operands are one 32-byte load.  Each dot product
+// and squared norm is accumulated sequentially over the descriptor index (the order of the scalar
+// loop of the reference's restatement) with fused multiply-adds: one rounding per term instead of
+// two, i.e. at least as accurate as the reference's own (compiler-contracted, vectorised) sums.
+constexpr int PT = 64;        // max objects per tile edge
+constexpr int PK = 32;        // descriptor columns per chunk
+constexpr int PLD = PT + 2;   // shared-memory row length (doubles): rows stay 16-byte aligned
 __global__ void __launch_bounds__(256) rb_prep_table_kernel(const RbProblem* __restrict__ probs, RbAssocSoA rec,
                                                             const double* __restrict__ D1,
                                                             const double* __restrict__ D2, RbDevParams P,
-                                                            int tiles2_max) {
-  __shared__ double As[PT][PK + 1];
-  __shared__ double Bs[PT][PK + 1];
+                                                            int tiles2_max, int TY, int TX) {
+  __shared__ __align__(16) double As[PK][PLD];
+  __shared__ __align__(16) double Bs[PK][PLD];
   __shared__ double s_na[PT], s_nb[PT];
   const RbProblem pr = probs[blockIdx.y];
   const rb_invariant_params& p = P.inv;
+  const int PT1 = 4 * TY, PT2 = 4 * TX;
   const int t1 = blockIdx.x / tiles2_max, t2 = blockIdx.x % tiles2_max;
-  const int i1_0 = t1 * PT, i2_0 = t2 * PT;
-  const int tid = threadIdx.x;
+  const int i1_0 = t1 * PT1, i2_0 = t2 * PT2;
+  const int tid = threadIdx.x;  // always 256 threads: TY*TX of them compute, all of them stage data
   if (blockIdx.x == 0) {  // padding records of this problem
     for (int k = pr.m + tid; k < pr.nb * RB_TILE; k += 256) {
       const int64_t o = pr.off_pad + k;
@@ -242,11 +246,15 @@ __global__ void __launch_bounds__(256) rb_prep_table_kernel(const RbProblem* __r
     }
   }
   if (i1_0 >= pr.n1 || i2_0 >= pr.n2) return;
-  const int tx = tid & 15, ty = tid >> 4;
+  const bool active = tid < TY * TX;
+  const int tx = active ? tid % TX : 0, ty = active ? tid / TX : 0;
   const double* A0 = D1 + pr.off_obj1 * (int64_t)pr.d;
   const double* B0 = D2 + pr.off_obj2 * (int64_t)pr.d;
   const int foff = p.point_dim + p.ratio_feature_dim;
   const int Dc = (p.kind == RB_INVARIANT_ROMAN) ? p.cos_feature_dim : 0;
+  // the squared norms of the 4*TX map-2 objects are accumulated by the threads of thread-row 0
+  // only, those of the map-1 objects by thread-column 0 only
+  const bool do_nb = active && ty == 0, do_na = active && tx == 0;
 
   double acc[4][4];
   double na[4] = {0, 0, 0, 0}, nb[4] = {0, 0, 0, 0};
@@ -255,40 +263,66 @@ __global__ void __launch_bounds__(256) rb_prep_table_kernel(const RbProblem* __r
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
 
-  for (int k0 = 0; k0 < Dc; k0 += PK) {
-    __syncthreads();
-    for (int e = tid; e < PT * PK; e += 256) {  // coalesced along the descriptor index
+  // Software pipeline: while chunk c is consumed from shared memory, chunk c+1 is already in flight
+  // from HBM into registers (each of the 256 threads carries at most 8 + 8 elements of a chunk).
+  constexpr int NLD = PT * PK / 256;
+  double ra_[NLD], rb_[NLD];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < NLD; ++j) {
+      const int e = tid + j * 256;  // coalesced along the descriptor index
       const int o = e / PK, k = e % PK;
       const bool kin = (k0 + k) < Dc;
-      As[o][k] = (kin && i1_0 + o < pr.n1) ? A0[(int64_t)(i1_0 + o) * pr.d + foff + k0 + k] : 0.0;
-      Bs[o][k] = (kin && i2_0 + o < pr.n2) ? B0[(int64_t)(i2_0 + o) * pr.d + foff + k0 + k] : 0.0;
+      ra_[j] = (e < PT1 * PK && kin && i1_0 + o < pr.n1) ? A0[(int64_t)(i1_0 + o) * pr.d + foff + k0 + k] : 0.0;
+      rb_[j] = (e < PT2 * PK && kin && i2_0 + o < pr.n2) ? B0[(int64_t)(i2_0 + o) * pr.d + foff + k0 + k] : 0.0;
     }
+  };
+  auto stage = [&]() {
+#pragma unroll
+    for (int j = 0; j < NLD; ++j) {
+      const int e = tid + j * 256;
+      const int o = e / PK, k = e % PK;
+      if (e < PT1 * PK) As[k][o] = ra_[j];
+      if (e < PT2 * PK) Bs[k][o] = rb_[j];
+    }
+  };
+  if (Dc > 0) fetch(0);
+  for (int k0 = 0; k0 < Dc; k0 += PK) {
+    __syncthreads();  // everybody is done reading the previous chunk
+    stage();
     __syncthreads();
-    const int kend = (Dc - k0) < PK ? (Dc - k0) : PK;
-    for (int k = 0; k < kend; ++k) {
-      double a[4], b[4];
+    if (k0 + PK < Dc) fetch(k0 + PK);
+    if (active) {
+      const int kend = (Dc - k0) < PK ? (Dc - k0) : PK;
+      for (int k = 0; k < kend; ++k) {
+        const double2 a01 = *reinterpret_cast<const double2*>(&As[k][ty * 4]);
+        const double2 a23 = *reinterpret_cast<const double2*>(&As[k][ty * 4 + 2]);
+        const double2 b01 = *reinterpret_cast<const double2*>(&Bs[k][tx * 4]);
+        const double2 b23 = *reinterpret_cast<const double2*>(&Bs[k][tx * 4 + 2]);
+        const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+        const double b[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
-      for (int r = 0; r < 4; ++r) a[r] = As[ty * 4 + r][k];
+        for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) b[c] = Bs[tx * 4 + c][k];
+          for (int c = 0; c < 4; ++c) acc[r][c] = fma(a[r], b[c], acc[r][c]);
+        if (do_na)
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
+          for (int r = 0; r < 4; ++r) na[r] = fma(a[r], a[r], na[r]);
+        if (do_nb)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] += a[r] * b[c];
-        na[r] += a[r] * a[r];
+          for (int c = 0; c < 4; ++c) nb[c] = fma(b[c], b[c], nb[c]);
       }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) nb[c] += b[c] * b[c];
     }
   }
   __syncthreads();
-  if (tx == 0)
+  if (do_na)
 #pragma unroll
     for (int r = 0; r < 4; ++r) s_na[ty * 4 + r] = na[r];
-  if (ty == 0)
+  if (do_nb)
 #pragma unroll
     for (int c = 0; c < 4; ++c) s_nb[tx * 4 + c] = nb[c];
   __syncthreads();
+  if (!active) return;
 
   const int pd = (p.kind == RB_INVARIANT_ROMAN) ? p.point_dim : (pr.d < 3 ? pr.d : 3);
 #pragma unroll
@@ -562,10 +596,16 @@ cudaError_t rb_launch_prep(const RbProblem* probs, int B, int max_mp, int max_n1
                            const RbDevParams& P, cudaStream_t st) {
   if (B == 0 || max_mp == 0) return cudaSuccess;
   if (all_to_all) {
-    const int t1 = (max_n1 + PT - 1) / PT, t2 = (max_n2 + PT - 1) / PT;
+    // thread grid TY x TX (4x4 outputs per thread) sized to the largest maps of the batch, at most 16 x 16
+    int TY = (max_n1 + 3) / 4, TX = (max_n2 + 3) / 4;
+    if (TY > 16) TY = 16;
+    if (TX > 16) TX = 16;
+    if (TY < 1) TY = 1;
+    if (TX < 1) TX = 1;
+    const int t1 = (max_n1 + 4 * TY - 1) / (4 * TY), t2 = (max_n2 + 4 * TX - 1) / (4 * TX);
     if ((int64_t)t1 * t2 <= 65535 * 32) {
-      dim3 grid((unsigned)(t1 * t2), B);
-      rb_prep_table_kernel<<<grid, 256, 0, st>>>(probs, rec, D1, D2, P, t2);
+      dim3 grid((unsigned)(t1 * t2 > 0 ? t1 * t2 : 1), B);
+      rb_prep_table_kernel<<<grid, 256, 0, st>>>(probs, rec, D1, D2, P, t2 > 0 ? t2 : 1, TY, TX);
       return cudaGetLastError();
     }
   }
