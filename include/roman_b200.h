@@ -112,6 +112,13 @@ int rb_set_solver_params(rb_handle* h, const rb_solver_params* p);
  * Does not touch the compute stream; call it outside timed regions when shapes repeat. */
 int rb_plan(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const int32_t* n2,
             const int32_t* m);
+
+/* Same, for batches whose problems share objects (the all-pairs loop-closure search of
+ * roman/align/submap_align.py:93-94 registers every submap of run A against every submap of run B):
+ * D1 / D2 are shared tables of total_obj1 / total_obj2 object rows, uploaded once, and problem b uses
+ * rows [obj1_offset[b], obj1_offset[b] + n1[b]) of D1 and [obj2_offset[b], ... + n2[b]) of D2. */
+int rb_plan_indexed(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const int32_t* n2, const int32_t* m,
+                    const int64_t* obj1_offset, const int64_t* obj2_offset, int64_t total_obj1, int64_t total_obj2);
 int64_t rb_assoc_offset(const rb_handle* h, int32_t b); /* b == B gives the total */
 int64_t rb_obj1_offset(const rb_handle* h, int32_t b);  /* in objects (rows of d doubles) */
 int64_t rb_obj2_offset(const rb_handle* h, int32_t b);

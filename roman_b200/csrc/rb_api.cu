@@ -21,6 +21,7 @@ struct rb_handle {
   bool planned = false;
   int32_t B = 0, d = 0;
   bool all_to_all = true;
+  bool indexed = false;      // rb_plan_indexed: problems reference ranges of shared object tables
   std::vector<RbProblem> probs;
   std::vector<int64_t> tile_prefix;  // B+1
   int64_t total_assoc = 0, total_pad = 0, total_tiles = 0, total_obj1 = 0, total_obj2 = 0;
@@ -283,7 +284,21 @@ int rb_get_stage_ms(rb_handle* h, float ms[4]) {
   return RB_OK;
 }
 
+static int plan_impl(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const int32_t* n2, const int32_t* m,
+                     const int64_t* off1, const int64_t* off2, int64_t tot1, int64_t tot2);
+
 int rb_plan(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const int32_t* n2, const int32_t* m) {
+  return plan_impl(h, B, d, n1, n2, m, nullptr, nullptr, 0, 0);
+}
+
+int rb_plan_indexed(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const int32_t* n2, const int32_t* m,
+                    const int64_t* obj1_offset, const int64_t* obj2_offset, int64_t total_obj1, int64_t total_obj2) {
+  if (B > 0 && (!obj1_offset || !obj2_offset)) return h ? fail(h, RB_ERR_ARG, "rb_plan_indexed: null offsets") : RB_ERR_ARG;
+  return plan_impl(h, B, d, n1, n2, m, obj1_offset, obj2_offset, total_obj1, total_obj2);
+}
+
+static int plan_impl(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const int32_t* n2, const int32_t* m,
+                     const int64_t* off1, const int64_t* off2, int64_t tot1, int64_t tot2) {
   if (!h) return RB_ERR_ARG;
   if (B < 0 || d < 1 || (B > 0 && (!n1 || !n2))) return fail(h, RB_ERR_ARG, "rb_plan: bad arguments");
   RB_CUDA(h, cudaSetDevice(h->device));
@@ -300,7 +315,10 @@ int rb_plan(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const int32_t
     RbProblem& p = h->probs[(size_t)b];
     p.n1 = n1[b]; p.n2 = n2[b]; p.m = (int32_t)mm; p.nb = (int32_t)((mm + RB_TILE - 1) / RB_TILE);
     p.d = d; p.all_to_all = m ? 0 : 1;
-    p.off_obj1 = o1; p.off_obj2 = o2; p.off_assoc = oa; p.off_pad = op; p.off_tile = ot;
+    p.off_obj1 = off1 ? off1[b] : o1; p.off_obj2 = off2 ? off2[b] : o2;
+    if (off1 && (off1[b] < 0 || off1[b] + n1[b] > tot1 || off2[b] < 0 || off2[b] + n2[b] > tot2))
+      return fail(h, RB_ERR_ARG, "rb_plan_indexed: object range outside the shared tables");
+    p.off_assoc = oa; p.off_pad = op; p.off_tile = ot;
     p.n_tiles = (int64_t)p.nb * (p.nb + 1) / 2;
     h->tile_prefix[(size_t)b] = ot;
     o1 += n1[b]; o2 += n2[b]; oa += mm; op += (int64_t)p.nb * RB_TILE; ot += p.n_tiles;
@@ -321,7 +339,9 @@ int rb_plan(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const int32_t
   h->slots = slots;
   h->depth = depth;
   h->B = B; h->d = d; h->all_to_all = (m == nullptr);
-  h->total_assoc = oa; h->total_pad = op; h->total_tiles = ot; h->total_obj1 = o1; h->total_obj2 = o2;
+  h->total_assoc = oa; h->total_pad = op; h->total_tiles = ot;
+  h->total_obj1 = off1 ? tot1 : o1; h->total_obj2 = off2 ? tot2 : o2;
+  h->indexed = (off1 != nullptr);
   h->max_mp = max_mp;
   h->max_n1 = mx1;
   h->max_n2 = mx2;
@@ -621,6 +641,10 @@ int rb_align_batch_host(rb_handle* h, const double* D1, const double* D2, const 
     RB_CUDA(h, cudaStreamWaitEvent(cs, h->order_ev, 0));
   }
   const size_t d = (size_t)h->d;
+  if (h->indexed) {  // shared object tables: uploaded once, every range may reference any part of them
+    RB_CUDA(h, cudaMemcpyAsync(h->s_D1, D1, nD1 * sizeof(double), cudaMemcpyHostToDevice, cs));
+    RB_CUDA(h, cudaMemcpyAsync(h->s_D2, D2, nD2 * sizeof(double), cudaMemcpyHostToDevice, cs));
+  }
   for (int c = 0; c < nch; ++c) {
     const int b0 = (int)((int64_t)h->B * c / nch), b1 = (int)((int64_t)h->B * (c + 1) / nch);
     const RbProblem& p0 = h->probs[(size_t)b0];
@@ -628,8 +652,10 @@ int rb_align_batch_host(rb_handle* h, const double* D1, const double* D2, const 
     const size_t e1 = (b1 < h->B ? (size_t)h->probs[(size_t)b1].off_obj1 : (size_t)h->total_obj1) * d;
     const size_t e2 = (b1 < h->B ? (size_t)h->probs[(size_t)b1].off_obj2 : (size_t)h->total_obj2) * d;
     const size_t ea = b1 < h->B ? (size_t)h->probs[(size_t)b1].off_assoc : (size_t)h->total_assoc;
-    RB_CUDA(h, cudaMemcpyAsync(h->s_D1 + o1, D1 + o1, (e1 - o1) * sizeof(double), cudaMemcpyHostToDevice, cs));
-    RB_CUDA(h, cudaMemcpyAsync(h->s_D2 + o2, D2 + o2, (e2 - o2) * sizeof(double), cudaMemcpyHostToDevice, cs));
+    if (!h->indexed) {
+      RB_CUDA(h, cudaMemcpyAsync(h->s_D1 + o1, D1 + o1, (e1 - o1) * sizeof(double), cudaMemcpyHostToDevice, cs));
+      RB_CUDA(h, cudaMemcpyAsync(h->s_D2 + o2, D2 + o2, (e2 - o2) * sizeof(double), cudaMemcpyHostToDevice, cs));
+    }
     RB_CUDA(h, cudaMemcpyAsync(h->s_u0 + oa, u0 + oa, (ea - oa) * sizeof(double), cudaMemcpyHostToDevice, cs));
     if (!h->all_to_all)
       RB_CUDA(h, cudaMemcpyAsync(h->s_A + 2 * oa, A + 2 * oa, 2 * (ea - oa) * sizeof(int32_t), cudaMemcpyHostToDevice, cs));

@@ -129,19 +129,31 @@ class Engine:
         self._check(self._lib.rb_get_stage_ms(self._h, ms))
         return dict(prep=ms[0], affinity=ms[1], solve=ms[2], arun=ms[3])
 
-    def plan(self, d: int, n1: Sequence[int], n2: Sequence[int], m: Optional[Sequence[int]] = None):
-        """Describe the batch shapes (host side).  m=None: all-to-all associations."""
+    def plan(self, d: int, n1: Sequence[int], n2: Sequence[int], m: Optional[Sequence[int]] = None,
+             obj1_offsets: Optional[Sequence[int]] = None, obj2_offsets: Optional[Sequence[int]] = None,
+             total_obj1: Optional[int] = None, total_obj2: Optional[int] = None):
+        """Describe the batch shapes (host side).  m=None: all-to-all associations.
+        obj*_offsets: problems reference row ranges of shared object tables (rb_plan_indexed)."""
         n1a = np.ascontiguousarray(n1, dtype=np.int32)
         n2a = np.ascontiguousarray(n2, dtype=np.int32)
         B = len(n1a)
         assert len(n2a) == B
         ma = None if m is None else np.ascontiguousarray(m, dtype=np.int32)
-        self._check(self._lib.rb_plan(self._h, B, int(d), n1a.ctypes.data, n2a.ctypes.data,
-                                      None if ma is None else ma.ctypes.data))
+        if obj1_offsets is None:
+            self._check(self._lib.rb_plan(self._h, B, int(d), n1a.ctypes.data, n2a.ctypes.data,
+                                          None if ma is None else ma.ctypes.data))
+        else:
+            o1 = np.ascontiguousarray(obj1_offsets, dtype=np.int64)
+            o2 = np.ascontiguousarray(obj2_offsets, dtype=np.int64)
+            assert len(o1) == B and len(o2) == B
+            self._check(self._lib.rb_plan_indexed(self._h, B, int(d), n1a.ctypes.data, n2a.ctypes.data,
+                                                  None if ma is None else ma.ctypes.data, o1.ctypes.data,
+                                                  o2.ctypes.data, int(total_obj1), int(total_obj2)))
         self.B, self.d, self.all_to_all = B, int(d), ma is None
         self.offsets = np.array([self._lib.rb_assoc_offset(self._h, b) for b in range(B + 1)], dtype=np.int64)
         self.obj1_offsets = np.array([self._lib.rb_obj1_offset(self._h, b) for b in range(B + 1)], dtype=np.int64)
         self.obj2_offsets = np.array([self._lib.rb_obj2_offset(self._h, b) for b in range(B + 1)], dtype=np.int64)
+        self.total_obj1, self.total_obj2 = int(self.obj1_offsets[-1]), int(self.obj2_offsets[-1])
         self.n1, self.n2 = n1a, n2a
         return self
 
@@ -167,7 +179,7 @@ class Engine:
     def affinity(self, D1, D2, A=None):
         D1 = self._dev(D1, torch.float64)
         D2 = self._dev(D2, torch.float64)
-        assert D1.numel() == self.obj1_offsets[-1] * self.d and D2.numel() == self.obj2_offsets[-1] * self.d
+        assert D1.numel() == self.total_obj1 * self.d and D2.numel() == self.total_obj2 * self.d
         if not self.all_to_all:
             A = self._dev(A, torch.int32)
             assert A.numel() == 2 * self.total_assoc

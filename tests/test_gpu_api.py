@@ -243,3 +243,92 @@ def test_geometry_only_dense_graph_m2000(engine, coracle):
     assert np.array_equal(r.associations(0), ref["sel"])
     assert abs(float(r.score[0]) - ref["score"]) <= 1e-9
     assert int(r.n_passes[0]) >= 20
+
+
+def _world_submaps(seed, S0=3, S1=4, n=18, sem=24):
+    """Run 0: S0 random submaps; run 1: transformed, noisy, partially overlapping copies + one unrelated."""
+    from roman_b200.align.objects import objects_from_rows
+    rng = np.random.default_rng(seed)
+    run0, run1, gt = [], [], {}
+    for i in range(S0):
+        p = synth.make_pair(seed * 10 + i, n + i, n + 2, method="roman", semantics_dim=sem, desc_common=1.0)
+        run0.append(p)
+    for j in range(S1):
+        if j < S0:
+            run1.append(("match", run0[j]))
+        else:
+            run1.append(("rand", synth.make_pair(seed * 10 + 50 + j, n, n + 3, method="roman", semantics_dim=sem, desc_common=1.0)))
+    sub0 = [objects_from_rows(p.D1, "roman", sem) for p in run0]
+    sub1 = [objects_from_rows(q.D2, "roman", sem) for _, q in run1]
+    rows0 = [p.D1 for p in run0]
+    rows1 = [q.D2 for _, q in run1]
+    return sub0, sub1, rows0, rows1, run0
+
+
+def test_all_pairs_batched_equals_pair_loop(engine, coracle):
+    """align_submap_pairs (shared tables, one launch sequence) == the reference-style per-pair loop:
+    register + T_align + upside-down reject + roll/pitch removal (submap_align.py:153-184)."""
+    from roman_b200.align import SubmapAlignParams, align_submap_pairs, InsufficientAssociationsException
+    from roman_b200.align.submap_align import rm_roll_pitch, roll_pitch
+    sem = 24
+    sub0, sub1, rows0, rows1, run0 = _world_submaps(3, sem=sem)
+    smp = SubmapAlignParams(method="roman", semantics_dim=sem)
+    rng = np.random.default_rng(0)
+    u0 = {(i, j): rng.uniform(0, 1, len(sub0[i]) * len(sub1[j])) for i in range(len(sub0)) for j in range(len(sub1))}
+    mask = np.ones((len(sub0), len(sub1)), dtype=bool)
+    mask[1, 3] = False
+    res = align_submap_pairs(smp, sub0, sub1, pair_mask=mask, u0=u0)
+    ip_o, _ = params_for_method("roman", semantics_dim=sem)
+    reg = smp.get_object_registration()
+    n_ok = 0
+    for i in range(len(sub0)):
+        for j in range(len(sub1)):
+            if not mask[i, j]:
+                assert res.status_mat[i, j] == -1 and np.isnan(res.clipper_num_associations[i, j])
+                continue
+            ref = coracle.align_pair(ip_o, cn.SolverParams(), rows0[i], rows1[j], u0[(i, j)])
+            assoc = reg.register(sub0[i], sub1[j], u0=u0[(i, j)])
+            assert np.array_equal(assoc, ref["sel"])
+            try:
+                T = reg.T_align(sub0[i], sub1[j], assoc)
+                roll, pitch = roll_pitch(T)
+                if abs(roll) > np.pi / 2 or abs(pitch) > np.pi / 2:
+                    raise ValueError
+                T = rm_roll_pitch(T)
+                assert res.status_mat[i, j] == 0
+                assert np.array_equal(res.associated_objs_mat[i][j], assoc)
+                assert res.clipper_num_associations[i, j] == len(assoc)
+                assert rel_fro(res.T_ij_hat_mat[i, j], T) <= T_TOL
+                n_ok += 1
+            except (InsufficientAssociationsException, ValueError):
+                assert res.status_mat[i, j] in (1, 2)
+                assert np.isnan(res.T_ij_hat_mat[i, j]).all() and len(res.associated_objs_mat[i][j]) == 0
+    assert n_ok >= 3
+    # planted matches come back as yaw-only transforms close to ground truth
+    for i in range(3):
+        if res.status_mat[i, i] == 0:
+            assert np.linalg.norm(res.T_ij_hat_mat[i, i] - run0[i].T_gt) < 0.5
+
+
+def test_all_pairs_single_robot_common_ids_removed(engine):
+    """single_robot_lc: objects whose id occurs in both submaps are dropped before registering the pair."""
+    from roman_b200.align import SubmapAlignParams, align_submap_pairs
+    sem = 16
+    sub0, sub1, rows0, rows1, run0 = _world_submaps(5, S0=2, S1=2, sem=sem)
+    for k, o in enumerate(sub0[0]):
+        o.id = k
+    for k, o in enumerate(sub1[0]):
+        o.id = 1000 + k
+    sub1[0][2].id = 4      # object 4 of submap (0) and object 2 of submap (0') are "the same segment"
+    smp = SubmapAlignParams(method="roman", semantics_dim=sem, single_robot_lc=True)
+    u0 = {(0, 0): np.random.default_rng(1).uniform(0, 1, (len(sub0[0]) - 1) * (len(sub1[0]) - 1))}
+    res = align_submap_pairs(smp, sub0[:1], sub1[:1], u0=u0)
+    a = res.associated_objs_mat[0][0]
+    assert len(a) > 0 and 4 not in a[:, 0] and 2 not in a[:, 1]
+    reg = smp.get_object_registration()
+    m1 = [o for o in sub0[0] if o.id != 4]
+    m2 = [o for o in sub1[0] if o.id != 4]
+    direct = reg.register(m1, m2, u0=u0[(0, 0)])
+    back1 = np.array([k for k, o in enumerate(sub0[0]) if o.id != 4])
+    back2 = np.array([k for k, o in enumerate(sub1[0]) if o.id != 4])
+    assert np.array_equal(np.stack([back1[direct[:, 0]], back2[direct[:, 1]]], axis=1), a)
