@@ -357,6 +357,10 @@ static int plan_impl(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, cons
       if ((int64_t)B * 4 <= h->sm_count) c = 4;
       if ((int64_t)B * 8 <= h->sm_count) c = 8;
       if (max_mp <= 256) c = 1;
+      // With single-association scores (cosine / shape ratios) most associations cannot carry an edge, the
+      // tile-skip format then usually fits the solver's resident (shared-memory CSR) mode, where one CTA per
+      // problem is fastest: there is nothing left to split.
+      if (h->tile_skip && h->inv.kind == RB_INVARIANT_ROMAN && (h->inv.cos_feature_dim > 0 || h->inv.ratio_feature_dim > 0)) c = 1;
     }
     int mc = 0;
     for (;;) {

@@ -94,6 +94,12 @@ struct Smem {
   int wl_cap;             // entries per warp in wlist
   int* wcnt;              // [NW] tiles per warp, [NW] = number of live tile-rows of this CTA
   uint8_t* live_rows;     // the CTA's live tile-rows in processing order
+  // compact (resident) form of this CTA's share of the matrix, used when its non-zeros fit shared memory
+  int* c_rowptr;          // [mp+1] CSR row pointers over directed entries (both (i,j) and (j,i))
+  uint16_t* c_col;        // [2*nnz] column index
+  double* c_val;          // [2*nnz] value
+  int c_cap;              // capacity in undirected entries
+  double* c_ug;           // room for u and g (2 * mp doubles) next to the CSR, or null
   int slots;     // TMA ring slots per warp (1 or 2)
   int depth;     // tile-rows in flight between the fastest and slowest warp: 8 (decoupled) or 2 (lock-step)
 };
@@ -142,7 +148,6 @@ struct Reducer {
 // A tile sits in shared memory in the XOR-swizzled layout of rb_common.cuh, so one warp sweeps
 // it twice without bank conflicts: with lane = row (row sums of block I, one register per lane,
 // no cross-lane reduction) and with lane = column (column sums of block J).
-__device__ long long g_dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 struct TileIter {  // dense format: the arithmetic tile sequence of one warp
   int nb, C, w, p, h, I, J;
   bool ok;
@@ -326,41 +331,37 @@ __device__ __forceinline__ void matvec_pass_list(const Smem& S, const double* __
     if (kpf < cnt) pf_issue(s);
 
   int slot = 0, k = 0;
-  long long dw = 0, dc = 0, db = 0, t_in = clock64();
   for (int pos = 0; pos < nlive; ++pos) {
     const int I = S.live_rows[pos];
     RowAcc ra;
     ra.clear();
     while (k < cnt && (wl[k] >> 8) == I) {
       const int J = wl[k] & 255;
-      long long q0 = clock64();
       mbar_wait(bar + slot, (phase_bits >> slot) & 1u);
-      long long q1 = clock64();
       phase_bits ^= (1u << slot);
       process_tile(S, ring + slot * RB_TILE_ELEMS, I, J, lane, ra);
       __syncwarp();
-      dw += q1 - q0; dc += clock64() - q1;
       if (kpf < cnt) pf_issue(slot);
       slot = (slot + 1 == SLOTS) ? 0 : slot + 1;
       ++k;
     }
-    long long b0 = clock64();
     finish_tile_row(S, I, pos, lane, w, ra);
-    db += clock64() - b0;
-  }
-  if (blockIdx.x < 8 && w == 3 && lane == 0) {
-    atomicAdd((unsigned long long*)&g_dbg[0], (unsigned long long)dw); atomicAdd((unsigned long long*)&g_dbg[1], (unsigned long long)dc);
-    atomicAdd((unsigned long long*)&g_dbg[2], (unsigned long long)db); atomicAdd((unsigned long long*)&g_dbg[3], (unsigned long long)cnt);
-    atomicAdd((unsigned long long*)&g_dbg[4], (unsigned long long)nlive); atomicAdd((unsigned long long*)&g_dbg[5], 1ull);
-    atomicAdd((unsigned long long*)&g_dbg[6], (unsigned long long)(clock64() - t_in));
   }
 }
 
 // Once per problem (tile-skip format): from the tile flags, the CTA's live tile-rows in
 // processing order and, per warp, the list of its stored tiles (I << 8 | J) in that order.
-__device__ __forceinline__ void build_tile_lists(const Smem& S, const uint8_t* __restrict__ gflags, int nb, int C,
+__device__ __forceinline__ void build_tile_lists(const Smem& S, const uint8_t* __restrict__ gflags_global, int nb, int C,
                                                  int crank) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // the problem's flags (one byte per stored-tile slot) are staged into shared memory first — accC is free
+  // at this point — so that the per-tile-row scans below do not pay a global-memory latency each
+  uint8_t* gflags = reinterpret_cast<uint8_t*>(S.accC);
+  {
+    const int nt = nb * (nb + 1) / 2;
+    for (int t = threadIdx.x; t < nt; t += NT) gflags[t] = gflags_global[t];
+    __syncthreads();
+  }
   uint16_t* wl = S.wlist + (size_t)w * S.wl_cap;
   int cnt = 0, nlive = 0;
   const int npairs = (nb + 1) >> 1;
@@ -390,9 +391,132 @@ __device__ __forceinline__ void build_tile_lists(const Smem& S, const uint8_t* _
   if (w == 0 && lane == 0) S.wcnt[NW] = nlive;
 }
 
+// ---- resident (compact) form --------------------------------------------------------------------
+// In the tile-skip format a problem often has only a few hundred edges.  Then this CTA's share of
+// the matrix is read from HBM exactly once: the stored tiles are streamed through the TMA rings a
+// single time, their non-zero words collected as (i, j, v) triples, and a CSR over both directions
+// is built in shared memory (in the space of the TMA rings, idle from then on).  Every later pass is
+// a CSR product out of shared memory.  Rows are sorted by column, so the summation order is fixed.
+// Returns false (all threads agree) if the triples do not fit; the caller then streams tiles.
+__device__ __forceinline__ bool build_compact(const Smem& S, const double* __restrict__ tiles, int nb, int mp,
+                                              uint32_t& phase_bits) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, tid = threadIdx.x;
+  const int SLOTS = S.slots;
+  uint64_t* bar = S.bar + w * MAX_SLOTS;
+  double* ring = S.ring + (size_t)w * SLOTS * RB_TILE_ELEMS;
+  const uint16_t* wl = S.wlist + (size_t)w * S.wl_cap;
+  const int cnt = S.wcnt[w];
+  // staging area for the triples: accM (values) and accC (packed i << 16 | j), both unused until the first pass
+  double* tv = S.accM;
+  unsigned* tij = reinterpret_cast<unsigned*>(S.accC);
+  const int cap = S.c_cap;
+  int* n_coo = S.misc + 14;
+  if (tid == 0) *n_coo = 0;
+  __syncthreads();
+
+  int kpf = 0, slot = 0;
+  auto pf_issue = [&](int sl) {
+    const int e = wl[kpf++];
+    if (lane == 0)
+      tma_load_tile(ring + sl * RB_TILE_ELEMS, tiles + rb_tile_index(e >> 8, e & 255, nb) * RB_TILE_ELEMS, bar + sl);
+  };
+  for (int s2 = 0; s2 < SLOTS; ++s2)
+    if (kpf < cnt) pf_issue(s2);
+  for (int k = 0; k < cnt; ++k) {
+    const int I = wl[k] >> 8, J = wl[k] & 255;
+    mbar_wait(bar + slot, (phase_bits >> slot) & 1u);
+    phase_bits ^= (1u << slot);
+    const double* rowp = ring + slot * RB_TILE_ELEMS + lane * RB_TILE;  // lane = row
+#pragma unroll 4
+    for (int t = 0; t < RB_TILE; ++t) {
+      const double v = rowp[t ^ lane];
+      // diagonal tiles hold both triangles: keep the strict upper one
+      if (__double_as_longlong(v) != 0ll && (J != I || lane < t)) {
+        const int pos = atomicAdd(n_coo, 1);
+        if (pos < cap) {
+          tv[pos] = v;
+          tij[pos] = ((unsigned)(I * RB_TILE + lane) << 16) | (unsigned)(J * RB_TILE + t);
+        }
+      }
+    }
+    __syncwarp();
+    if (kpf < cnt) pf_issue(slot);
+    slot = (slot + 1 == SLOTS) ? 0 : slot + 1;
+  }
+  __syncthreads();
+  const int n = *n_coo;
+  if (n > cap) return false;
+
+  // CSR over directed entries: count, scan, fill, sort rows by column
+  int* rowptr = S.c_rowptr;                       // [mp + 1]
+  int* cursor = S.c_rowptr + (mp + 1);            // [mp]
+  for (int i = tid; i <= mp; i += NT) rowptr[i] = 0;
+  for (int i = tid; i < mp; i += NT) cursor[i] = 0;
+  __syncthreads();
+  for (int e = tid; e < n; e += NT) {
+    const unsigned ij = tij[e];
+    atomicAdd(&rowptr[(ij >> 16) + 1], 1);
+    atomicAdd(&rowptr[(ij & 0xffffu) + 1], 1);
+  }
+  __syncthreads();
+  if (w == 0) {  // inclusive scan of rowptr[1..mp] by one warp (mp <= 5120)
+    int carry = 0;
+    for (int base = 1; base <= mp; base += 32) {
+      const int i = base + lane;
+      int v = (i <= mp) ? rowptr[i] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+      }
+      if (i <= mp) rowptr[i] = v + carry;
+      carry += __shfl_sync(0xffffffffu, v, 31);
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < n; e += NT) {
+    const unsigned ij = tij[e];
+    const int i = ij >> 16, j = ij & 0xffffu;
+    const double v = tv[e];
+    int p = rowptr[i] + atomicAdd(&cursor[i], 1);
+    S.c_col[p] = (uint16_t)j; S.c_val[p] = v;
+    p = rowptr[j] + atomicAdd(&cursor[j], 1);
+    S.c_col[p] = (uint16_t)i; S.c_val[p] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < mp; i += NT) {  // insertion sort of each row by column: fixed summation order
+    const int b = rowptr[i], e = rowptr[i + 1];
+    for (int a = b + 1; a < e; ++a) {
+      const uint16_t c = S.c_col[a];
+      const double v = S.c_val[a];
+      int q = a - 1;
+      while (q >= b && S.c_col[q] > c) { S.c_col[q + 1] = S.c_col[q]; S.c_val[q + 1] = S.c_val[q]; --q; }
+      S.c_col[q + 1] = c; S.c_val[q + 1] = v;
+    }
+  }
+  __syncthreads();
+  return true;
+}
+
+// One pass out of the resident CSR: accM = M x, accC = C x (this CTA's share).
+__device__ __forceinline__ void matvec_pass_compact(const Smem& S, int mp) {
+  for (int i = threadIdx.x; i < mp; i += NT) {
+    double sM = 0.0, sC = 0.0;
+    const int b = S.c_rowptr[i], e = S.c_rowptr[i + 1];
+    for (int q = b; q < e; ++q) {
+      const double xj = S.x[S.c_col[q]];
+      sM = fma(S.c_val[q], xj, sM);
+      sC += xj;
+    }
+    S.accM[i] = sM;
+    S.accC[i] = sC;
+  }
+}
+
 __device__ __forceinline__ void matvec_pass(const Smem& S, const double* __restrict__ tiles, int nb,
-                                            uint32_t& phase_bits, int C, int crank) {
-  if (S.wlist) matvec_pass_list(S, tiles, nb, phase_bits);
+                                            uint32_t& phase_bits, int C, int crank, bool compact) {
+  if (compact) matvec_pass_compact(S, nb * RB_TILE);
+  else if (S.wlist) matvec_pass_list(S, tiles, nb, phase_bits);
   else matvec_pass_dense(S, tiles, nb, phase_bits, C, crank);
 }
 
@@ -454,6 +578,26 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
     S.wl_cap = (A.nt_max + NW - 1) / NW + nbm;
     S.wlist = A.flags ? (uint16_t*)p : nullptr; p += (size_t)NW * S.wl_cap * 2;
     S.live_rows = (uint8_t*)p;
+    {
+      // resident CSR lives in the TMA ring space (idle once the tiles have been read): row pointers + cursors,
+      // then values, then columns; capacity in undirected entries is also bounded by the triple staging area
+      // (accM/accC: mp entries each)
+      unsigned char* q = (unsigned char*)S.ring;
+      const size_t ring_bytes = (size_t)NW * A.slots * RB_TILE_BYTES;
+      S.c_rowptr = (int*)q;
+      const size_t head = (((size_t)(2 * mp + 1) * 4 + 15) / 16) * 16;
+      const size_t ug = (size_t)2 * mp * 8;
+      size_t room = ring_bytes > head ? ring_bytes - head : 0;
+      const bool ug_fits = room >= ug + 512 * 2 * (8 + 2);  // keep u, g in shared memory too if >= 512 edges still fit
+      if (ug_fits) room -= ug;
+      int cap = (int)(room / (2 * (8 + 2)));       // 2 directed entries of (double + uint16) per edge
+      if (cap > (int)mp) cap = (int)mp;
+      if (cap > 32767) cap = 32767;
+      S.c_cap = A.flags ? cap : 0;
+      S.c_val = (double*)(q + head);
+      S.c_col = (uint16_t*)(q + head + (size_t)2 * cap * 8);
+      S.c_ug = ug_fits ? (double*)(q + head + ((((size_t)2 * cap * (8 + 2)) + 15) / 16) * 16) : nullptr;
+    }
   }
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -469,7 +613,7 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
   const int crank = (int)cluster.block_rank();
   const bool lead = (crank == 0);
 
-  long long t_mv = 0, t_cb = 0, t_tot0 = clock64(), t_q = 0, t_round = 0;
+  long long t_mv = 0, t_cb = 0, t_tot0 = clock64(), t_q = 0, t_round = 0, t_build = 0;
   for (;;) {
     long long tq0 = clock64();
     // one problem per cluster: rank 0 pulls from the queue and posts the index to every CTA
@@ -485,14 +629,16 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
     const RbProblem pr = A.probs[b];
     const int m = pr.m, nb = pr.nb, mp = nb * RB_TILE;
     const double* tiles = A.Mp + pr.off_tile * RB_TILE_ELEMS;
-    double* u = A.u_work + (size_t)crank * A.pad_stride + pr.off_pad;  // per-CTA private copies
+    double* u = A.u_work + (size_t)crank * A.pad_stride + pr.off_pad;  // per-CTA private copies (global scratch)
     double* g = A.g_work + (size_t)crank * A.pad_stride + pr.off_pad;
     const double* u0 = A.u0 + pr.off_assoc;
     int passes = 0;
+    long long tb0 = clock64();
     if (A.flags) {
       build_tile_lists(S, A.flags + pr.off_tile, nb, C, crank);
       __syncthreads();
     }
+    bool compact = false;
 
     if (m == 0) {
       if (lead && tid == 0) {
@@ -501,6 +647,25 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
       continue;
     }
 
+    // tile-skip format: try to make this CTA's share of the matrix resident (read from HBM once)
+    if (A.flags && m > 0) {
+      compact = build_compact(S, tiles, nb, mp, phase);
+      if (C > 1) {  // every CTA of the cluster must run the same kind of pass (they combine their partials)
+        cluster.sync();
+        if (tid == 0) S.misc[15] = compact ? 1 : 0;
+        cluster.sync();
+        bool all = true;
+        for (int r = 0; r < C; ++r) all = all && (*cluster.map_shared_rank(S.misc + 15, r) != 0);
+        cluster.sync();
+        compact = all;
+      }
+      if (compact && S.c_ug) {  // resident mode leaves room in the ring space for the iterate and its gradient
+        u = S.c_ug;
+        g = S.c_ug + mp;
+      }
+    }
+
+    t_build += clock64() - tb0;
     // ---- init (clipper.cpp:263-269): u = M u0 + u0 (optional), u /= ||u||
     for (int i = tid; i < mp; i += NT) {
       S.x[i] = (i < m) ? u0[i] : 0.0;
@@ -509,7 +674,7 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
     }
     __syncthreads();
     if (sp.rescale_u0) {
-      { long long t0 = clock64(); matvec_pass(S, tiles, nb, phase, C, crank); long long t1 = clock64();
+      { long long t0 = clock64(); matvec_pass(S, tiles, nb, phase, C, crank, compact); long long t1 = clock64();
         ++passes;
         cluster_combine(S, mp, C, crank); t_mv += t1 - t0; t_cb += clock64() - t1; }
     }
@@ -533,7 +698,7 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
       }
     }
     sum_u = R.sum1(sum_u);
-    { long long t0 = clock64(); matvec_pass(S, tiles, nb, phase, C, crank);  // (M u, C u) of the normalised start vector
+    { long long t0 = clock64(); matvec_pass(S, tiles, nb, phase, C, crank, compact);  // (M u, C u) of the normalised start vector
       long long t1 = clock64();
       ++passes;
       cluster_combine(S, mp, C, crank); t_mv += t1 - t0; t_cb += clock64() - t1; }
@@ -569,25 +734,25 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
         double alpha = 1.0, Fnew = 0.0, deltaF = 0.0, du2 = 0.0, sum_un = 0.0;
         for (int k_ls = 0; k_ls < sp.maxlsiters; ++k_ls) {
           // unew = normalize(max(u + alpha*gradF, 0))   (clipper.cpp:306-308)
-          double z = 0.0;
+          // (sum of the normalised vector = sum of the raw one / norm: one reduction for both)
+          double z = 0.0, sraw = 0.0;
           for (int i = tid; i < m; i += NT) {
             const double t = u[i] + alpha * g[i];
             const double r = t > 0.0 ? t : 0.0;
             S.x[i] = r;
             z += r * r;
+            sraw += r;
           }
-          z = R.sum1(z);
-          double su = 0.0;
+          R.sum2(z, sraw);
           const double nrm = sqrt(z);
+          sum_un = (z > 0.0) ? sraw / nrm : sraw;
           for (int i = tid; i < mp; i += NT) {
-            double v = S.x[i];
-            if (z > 0.0 && i < m) { v = v / nrm; S.x[i] = v; }
-            su += (i < m) ? v : 0.0;
+            if (z > 0.0 && i < m) S.x[i] = S.x[i] / nrm;
             S.accM[i] = 0.0;
             S.accC[i] = 0.0;
           }
-          sum_un = R.sum1(su);
-          { long long t0 = clock64(); matvec_pass(S, tiles, nb, phase, C, crank); long long t1 = clock64();
+          __syncthreads();
+          { long long t0 = clock64(); matvec_pass(S, tiles, nb, phase, C, crank, compact); long long t1 = clock64();
             ++passes;
             cluster_combine(S, mp, C, crank); t_mv += t1 - t0; t_cb += clock64() - t1; }
           // gradFnew, Fnew (clipper.cpp:309-315) and, speculatively, ||unew - u||^2
@@ -741,7 +906,7 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
   if (A.debug && tid == 0) {
     long long* d = A.debug + (size_t)blockIdx.x * 8;
     d[0] = clock64() - t_tot0; d[1] = t_mv; d[2] = t_cb; d[3] = t_q; d[4] = t_round;
-    if (blockIdx.x == 1) for (int i = 0; i < 8; ++i) d[i] = g_dbg[i];
+    d[5] = t_build;
   }
 }
 

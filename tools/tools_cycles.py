@@ -25,4 +25,4 @@ for CL, TS in itertools.product([1, 2, 4], [True, False]):
     eng._lib.rb_debug_solver_cycles(eng._h, C.c_void_p(buf.ctypes.data), n)
     f = buf.astype(float) / 1.965e3  # us at 1965 MHz (approx)
 
-    print(f"skip={TS} C={CL} ctas={n} solve={ms['solve']:.3f} ms | per-CTA us: total {f[:,0].mean():.0f} matvec {f[:,1].mean():.0f} (max {f[:,1].max():.0f}) combine {f[:,2].mean():.0f} queue {f[:,3].mean():.0f} round(lead) {f[::CL,4].mean():.0f} | passes {res.n_passes.float().sum().item():.0f}")
+    print(f"skip={TS} C={CL} ctas={n} solve={ms['solve']:.3f} ms | per-CTA us: total {f[:,0].mean():.0f} matvec {f[:,1].mean():.0f} (max {f[:,1].max():.0f}) combine {f[:,2].mean():.0f} queue {f[:,3].mean():.0f} round(lead) {f[::CL,4].mean():.0f} build {f[:,5].mean():.0f} | passes {res.n_passes.float().sum().item():.0f}")
