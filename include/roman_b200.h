@@ -178,8 +178,13 @@ int rb_get_solver_max_clusters(const rb_handle* h); /* co-resident clusters of t
 /* Storage format of the packed affinity matrix.  on (default): K1 records per 32x32 tile whether it
  * holds any non-zero word, writes only such tiles, and K2 streams only those ("tile skip").  off: every
  * tile of the packed upper triangle is written and streamed each pass (the plain dense kernels).
- * Results are bitwise identical in both modes.  Takes effect at the next rb_affinity / rb_set_dense. */
+ * The stored matrices are bitwise identical in both formats, the solves agree to rounding (summation order).
+ * Changing the format invalidates the plan: call rb_plan again (the solver's cluster size is chosen per format). */
 int rb_set_tile_skip(rb_handle* h, int32_t on);
+
+/* After rb_solve: device int32[B], 1 where the solve ran in resident mode (the problem's stored tiles were read
+ * from HBM once and every pass ran from a shared-memory CSR), 0 where the tiles were streamed each pass. */
+int rb_solver_resident(rb_handle* h, int32_t* out, void* stream);
 
 /* Tile-skip format only: number of stored (flagged) 32x32 tiles of each problem, device int32[B]. */
 int rb_stored_tiles(rb_handle* h, int32_t* out, void* stream);

@@ -69,6 +69,7 @@ SIGNATURES = {
     "rb_get_solver_max_clusters": (C.c_int, [_vp]),
     "rb_set_tile_skip": (C.c_int, [_vp, _i32]),
     "rb_stored_tiles": (C.c_int, [_vp, _ip, _vp]),
+    "rb_solver_resident": (C.c_int, [_vp, _ip, _vp]),
     "rb_set_profiling": (C.c_int, [_vp, _i32]),
     "rb_get_stage_ms": (C.c_int, [_vp, _fp]),
     "rb_align_batch_host": (C.c_int, [_vp, _dp, _dp, _ip, _dp, _ip, _ip, _dp, _ip, _dp, _ip]),

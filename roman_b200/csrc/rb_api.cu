@@ -46,6 +46,7 @@ struct rb_handle {
   // internal outputs used when the caller passes NULL
   int32_t* d_nodes = nullptr; int32_t* d_sel = nullptr; size_t cap_assoc = 0;
   int32_t* d_nsel = nullptr; double* d_score = nullptr; int32_t* d_ifinal = nullptr; int32_t* d_npass = nullptr;
+  int32_t* d_resident = nullptr;
   int32_t* d_status = nullptr; double* d_T = nullptr; size_t cap_B = 0;
   // staging for the host entry point
   double* s_D1 = nullptr; double* s_D2 = nullptr; size_t cap_sD1 = 0, cap_sD2 = 0;
@@ -186,7 +187,7 @@ int rb_destroy(rb_handle* h) {
   cudaFree(h->d_probs); cudaFree(h->d_tile_prefix); cudaFree(h->d_M); cudaFree(h->d_flags); cudaFree(h->d_pad_f64);
   cudaFree(h->d_pad_i32); cudaFree(h->d_masks); cudaFree(h->d_counter); cudaFree(h->d_bad); cudaFree(h->d_nodes); cudaFree(h->d_sel);
   cudaFree(h->d_nsel); cudaFree(h->d_score); cudaFree(h->d_ifinal); cudaFree(h->d_npass);
-  cudaFree(h->d_status); cudaFree(h->d_T);
+  cudaFree(h->d_status); cudaFree(h->d_T); cudaFree(h->d_resident);
   cudaFree(h->s_D1); cudaFree(h->s_D2); cudaFree(h->s_A); cudaFree(h->s_u0);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->order_ev) cudaEventDestroy(h->order_ev);
@@ -252,8 +253,19 @@ int rb_debug_solver_cycles(rb_handle* h, long long* out, int n_ctas) {
 
 int rb_set_tile_skip(rb_handle* h, int32_t on) {
   if (!h) return RB_ERR_ARG;
-  h->tile_skip = on != 0;
-  h->affinity_done = false;  // the packed buffer of a previous rb_affinity is in the other format
+  if (h->tile_skip != (on != 0)) {
+    h->tile_skip = on != 0;
+    h->affinity_done = false;  // the packed buffer of a previous rb_affinity is in the other format
+    h->planned = false;        // the solver's cluster size is chosen per format: takes effect at the next rb_plan
+  }
+  return RB_OK;
+}
+
+int rb_solver_resident(rb_handle* h, int32_t* out, void* stream) {
+  if (!h || !out) return RB_ERR_ARG;
+  if (!h->planned) return fail(h, RB_ERR_NOPLAN, "rb_solver_resident before rb_plan");
+  if (h->B > 0)
+    RB_CUDA(h, cudaMemcpyAsync(out, h->d_resident, (size_t)h->B * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return RB_OK;
 }
 
@@ -408,12 +420,14 @@ static int plan_impl(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, cons
   }
   if ((size_t)B > h->cap_B || !h->d_nsel) {
     cudaFree(h->d_nsel); cudaFree(h->d_score); cudaFree(h->d_ifinal); cudaFree(h->d_npass); cudaFree(h->d_status); cudaFree(h->d_T);
+    cudaFree(h->d_resident); h->d_resident = nullptr;
     h->d_nsel = h->d_ifinal = h->d_npass = h->d_status = nullptr; h->d_score = h->d_T = nullptr; h->cap_B = 0;
     const size_t n = B ? (size_t)B : 1;
     RB_CUDA(h, cudaMalloc((void**)&h->d_nsel, n * sizeof(int32_t)));
     RB_CUDA(h, cudaMalloc((void**)&h->d_score, n * sizeof(double)));
     RB_CUDA(h, cudaMalloc((void**)&h->d_ifinal, n * sizeof(int32_t)));
     RB_CUDA(h, cudaMalloc((void**)&h->d_npass, n * sizeof(int32_t)));
+    RB_CUDA(h, cudaMalloc((void**)&h->d_resident, n * sizeof(int32_t)));
     RB_CUDA(h, cudaMalloc((void**)&h->d_status, n * sizeof(int32_t)));
     RB_CUDA(h, cudaMalloc((void**)&h->d_T, n * 16 * sizeof(double)));
     h->cap_B = n;
@@ -495,6 +509,7 @@ int solve_range(rb_handle* h, int b0, int b1, int queue, const double* u0, int32
   a.score = (score ? score : h->d_score) + b0;
   a.ifinal = (ifinal ? ifinal : h->d_ifinal) + b0;
   a.n_passes = (n_passes ? n_passes : h->d_npass) + b0;
+  a.resident = h->d_resident + b0;
   a.sp = h->sol;
   a.mp_max = h->max_mp;
   a.pad_stride = h->total_pad;

@@ -35,6 +35,7 @@ struct RbSolveArgs {
   double* score;
   int32_t* ifinal;
   int32_t* n_passes;
+  int32_t* resident;       // per problem: 1 if the solve ran from the shared-memory CSR (tiles read once), else 0
   rb_solver_params sp;
   int32_t mp_max;          // max padded m over the batch (sizes the shared-memory vectors)
 };

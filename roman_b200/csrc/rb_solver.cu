@@ -642,7 +642,7 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
 
     if (m == 0) {
       if (lead && tid == 0) {
-        A.n_nodes[b] = 0; A.score[b] = 0.0; A.ifinal[b] = 0; A.n_passes[b] = 0;
+        A.n_nodes[b] = 0; A.score[b] = 0.0; A.ifinal[b] = 0; A.n_passes[b] = 0; A.resident[b] = 0;
       }
       continue;
     }
@@ -900,6 +900,7 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
       A.score[b] = F;
       A.ifinal[b] = i_ol;
       A.n_passes[b] = passes;
+      A.resident[b] = compact ? 1 : 0;
     }
     t_round += clock64() - tr0;
   }

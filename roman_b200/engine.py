@@ -112,13 +112,20 @@ class Engine:
         return int(self._lib.rb_get_solver_cluster(self._h))
 
     def set_tile_skip(self, on: bool):
-        """Packed-affinity format: True (default) stores/streams only tiles holding a non-zero; False = plain dense."""
+        """Packed-affinity format: True (default) stores/streams only tiles holding a non-zero; False = plain dense.
+        Changing it invalidates the plan: call plan() again."""
         self._check(self._lib.rb_set_tile_skip(self._h, int(on)))
 
     def stored_tiles(self) -> torch.Tensor:
         """(B,) int32: 32x32 tiles actually stored per problem (tile-skip format)."""
         out = torch.zeros(max(self.B, 1), dtype=torch.int32, device=self.device)
         self._check(self._lib.rb_stored_tiles(self._h, _ptr(out), self._stream()))
+        return out
+
+    def solver_resident(self) -> torch.Tensor:
+        """(B,) int32: 1 where the last solve ran from the shared-memory CSR (tiles read once)."""
+        out = torch.zeros(max(self.B, 1), dtype=torch.int32, device=self.device)
+        self._check(self._lib.rb_solver_resident(self._h, _ptr(out), self._stream()))
         return out
 
     def set_profiling(self, on: bool):
