@@ -277,7 +277,11 @@ def run_b200(args):
     resident = eng.solver_resident().cpu().numpy().astype(np.int64)
     cluster_skip = eng.solver_cluster
     # ---- same batch through the plain dense format (every tile written and streamed): the north-star kernels
-    ms_d, stage_d = timed(False)
+    do_dense = (args.format == "both")
+    if do_dense:
+        ms_d, stage_d = timed(False)
+    else:
+        ms_d, stage_d = float("nan"), {k: float("nan") for k in stage}
     passes_d = res.n_passes.cpu().numpy().astype(np.int64)
     cluster_dense = eng.solver_cluster
     eng.set_tile_skip(True)
@@ -354,6 +358,8 @@ def run_b200(args):
             "gpu_launches": 5 * K,
             "clocks": clocks,
         }
+        if not do_dense:
+            line.pop("dense_stream")
         if world == 1 and not args.no_cpu:
             cb, _ = cpu_baseline(16)
             line["cpu_baseline"] = cb
@@ -370,6 +376,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=592, help="submap pairs per GPU per step (4 x 148 SMs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--format", default="both", choices=["both", "tile-skip"],
+                    help="both: also time the same batch in the dense format (dense_stream); tile-skip: default format only")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

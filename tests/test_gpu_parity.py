@@ -237,3 +237,98 @@ def test_tile_skip_and_dense_formats_agree(engine, coracle):
         Mo, _, _, _ = coracle.score(ip_o, 1e-4, p.D1, p.D2)
         ref = coracle.solve(cn.SolverParams(), Mo, p.u0)
         assert s_a["nodes"][o:o + n].tolist() == ref["nodes"]
+
+
+@pytest.mark.parametrize("variant", ["nonzero_rounding", "no_rescale", "tight_iters", "loose_tol"])
+def test_solver_parameter_variants_match_oracle(engine, coracle, variant):
+    """clipper::Params other than the defaults (clipper.h:27-60): Rounding::NONZERO, rescale_u0 = false,
+    iteration caps that bite, different tolerances."""
+    from roman_b200.engine import default_solver_params
+    ip_o, ip_g = params_for_method("gravity")
+    sp_o = cn.SolverParams()
+    sp_g = default_solver_params()
+    if variant == "nonzero_rounding":
+        sp_o.rounding, sp_g.rounding = 0, 0
+    elif variant == "no_rescale":
+        sp_o.rescale_u0, sp_g.rescale_u0 = False, 0
+    elif variant == "tight_iters":
+        sp_o.maxiniters, sp_g.maxiniters = 3, 3
+        sp_o.maxoliters, sp_g.maxoliters = 2, 2
+        sp_o.maxlsiters, sp_g.maxlsiters = 2, 2
+    else:
+        sp_o.tol_u, sp_g.tol_u = 1e-5, 1e-5
+        sp_o.tol_F, sp_g.tol_F = 1e-6, 1e-6
+        sp_o.beta, sp_g.beta = 0.5, 0.5
+    try:
+        engine.set_invariant_params(ip_g)
+        engine.set_solver_params(sp_g)
+        for seed, (n1, n2) in enumerate([(20, 20), (35, 28)]):
+            p = synth.make_pair(600 + seed, n1, n2, method="gravity")
+            engine.plan(3, [n1], [n2])
+            engine.affinity(p.D1.reshape(-1), p.D2.reshape(-1))
+            sol = engine.solve(p.u0, want_u=True)
+            Mo, _, A, _ = coracle.score(ip_o, sp_o.affinityeps, p.D1, p.D2)
+            ref = coracle.solve(sp_o, Mo, p.u0)
+            k = int(sol["n_nodes"][0])
+            assert sol["nodes"][:k].cpu().numpy().tolist() == ref["nodes"]
+            assert abs(float(sol["score"][0]) - ref["score"]) <= F_TOL
+            assert int(sol["ifinal"][0]) == ref["ifinal"]
+            assert np.abs(sol["u"].cpu().numpy() - ref["u"]).max() <= 1e-9
+    finally:
+        engine.set_solver_params(default_solver_params())
+
+
+def test_error_paths_and_limits(engine):
+    """Unsupported configurations fail loudly with the library's message; nothing falls back silently."""
+    from roman_b200.engine import RomanB200Error, default_solver_params, make_invariant_params
+    sp = default_solver_params()
+    sp.rounding = 1  # Rounding::DSD
+    with pytest.raises(RomanB200Error, match="DSD"):
+        engine.set_solver_params(sp)
+    with pytest.raises(RomanB200Error, match="point_dim"):
+        engine.set_invariant_params(make_invariant_params(point_dim=4))
+    with pytest.raises(RomanB200Error, match="gravity"):
+        engine.set_invariant_params(make_invariant_params(point_dim=2, gravity_guided=True))
+    engine.set_invariant_params(make_invariant_params())
+    with pytest.raises(RomanB200Error, match="shared-memory"):
+        engine.plan(3, [100], [100])  # m = 10000 exceeds the solver's layout
+    engine.plan(3, [4], [3])
+    with pytest.raises(RomanB200Error, match="before rb_affinity"):
+        engine.solve(np.ones(12))
+    with pytest.raises(RomanB200Error, match="row length"):
+        engine.set_invariant_params(make_invariant_params(cos_feature_dim=8))
+        engine.plan(3, [4], [3])
+        engine.affinity(np.zeros(12), np.zeros(9))
+    engine.set_invariant_params(make_invariant_params())
+
+
+def test_degenerate_inputs(engine, coracle):
+    """Empty maps, single objects, coincident points (mindist), NaN single scores from zero-norm descriptors."""
+    ip_o, ip_g = params_for_method("roman", semantics_dim=8)
+    engine.set_invariant_params(ip_g)
+    sp = cn.SolverParams()
+    rng = np.random.default_rng(2)
+    p = synth.make_pair(9, 6, 7, method="roman", semantics_dim=8, desc_common=1.0)
+    D1, D2 = p.D1.copy(), p.D2.copy()
+    D1[1, 7:] = 0.0           # zero-norm descriptor -> cosine 0/0 = NaN -> no edge (roman.cpp:129, clipper.cpp:104-124)
+    D2[3, :3] = D2[2, :3]     # coincident objects -> mindist gate
+    D1[4, 6] = 0.0            # zero volume -> ratio 0 with epsilon_shape 0: min/max = 0 -> score 0
+    shapes = [(0, 3), (1, 1), (6, 7), (2, 0)]
+    tabs1 = [D1[:a] for a, _ in shapes]
+    tabs2 = [D2[:b] for _, b in shapes]
+    engine.plan(D1.shape[1], [a for a, _ in shapes], [b for _, b in shapes])
+    u0 = [rng.uniform(0, 1, a * b) for a, b in shapes]
+    res = engine.align_batch(np.concatenate([t.reshape(-1) for t in tabs1]), np.concatenate([t.reshape(-1) for t in tabs2]),
+                             np.concatenate(u0))
+    st = res.status.cpu().numpy()
+    for b, (a, bb) in enumerate(shapes):
+        if a == 0 or bb == 0:
+            assert st[b] == 1 and int(res.n_sel[b]) == 0
+            continue
+        ref = coracle.align_pair(ip_o, sp, tabs1[b], tabs2[b], u0[b])
+        assert np.array_equal(res.associations(b), ref["sel"])
+        assert st[b] == ref["status"]
+    Mg, _ = engine.get_dense(2)
+    Mo, single, _, _ = coracle.score(ip_o, sp.affinityeps, tabs1[2], tabs2[2])
+    assert np.isnan(single).any()
+    assert np.array_equal(Mg.cpu().numpy() != 0, (Mo + Mo.T + np.eye(42)) != 0)
