@@ -87,9 +87,29 @@ class ROMANRegistration(ObjectRegistration):
     def _check_clipper_arrays(self, map1_cl, map2_cl):
         assert map1_cl.shape[1] == map2_cl.shape[1]
 
+    def rows(self, objects: List) -> np.ndarray:
+        """(n, d) float64 feature rows of an object list: the same numbers `_object_to_clipper_list` produces,
+        assembled column-group-wise instead of through per-object Python lists (the reference's packing costs
+        more than the GPU registration itself)."""
+        n, d = len(objects), self.row_length()
+        if n == 0:
+            return np.zeros((0, d))
+        cols = [np.array([np.asarray(o.center, dtype=np.float64).reshape(-1)[:self.dim] for o in objects]).reshape(n, self.dim)]
+        if self.pca:
+            cols.append(np.array([(o.linearity, o.planarity, o.scattering) for o in objects], dtype=np.float64).reshape(n, 3))
+        if self.volume:
+            cols.append(np.array([o.volume for o in objects], dtype=np.float64).reshape(n, 1))
+        if self.extent:
+            cols.append(np.sort(np.array([np.asarray(o.extent, dtype=np.float64).reshape(-1) for o in objects]).reshape(n, 3), axis=1))
+        if self.semantics:
+            cols.append(np.stack([np.asarray(o.semantic_descriptor, dtype=np.float64).ravel() for o in objects]).reshape(n, -1))
+        out = np.concatenate(cols, axis=1)
+        assert out.shape[1] == d, "object feature row does not match the invariant's dimensions"
+        return out
+
     def _clipper_score_all_to_all(self, clipper, map1: List, map2: List):
-        rows1 = np.array([self._object_to_clipper_list(o) for o in map1])
-        rows2 = np.array([self._object_to_clipper_list(o) for o in map2])
+        rows1 = self.rows(map1)
+        rows2 = self.rows(map2)
         self._check_clipper_arrays(rows1, rows2)
         A_init = clipperpy.utils.create_all_to_all(len(map1), len(map2))
         clipper.score_pairwise_and_single_consistency(rows1.T, rows2.T, A_init)
@@ -103,7 +123,7 @@ class ROMANRegistration(ObjectRegistration):
     def pack(self, maps: Sequence[List]) -> Tuple[np.ndarray, np.ndarray]:
         """Pack object lists into one (sum n, d) float64 row table + the per-map counts."""
         d = self.row_length()
-        rows = [np.array([self._object_to_clipper_list(o) for o in m], dtype=np.float64).reshape(-1, d) for m in maps]
+        rows = [self.rows(m) for m in maps]
         table = np.concatenate(rows, axis=0) if rows else np.zeros((0, d))
         return np.ascontiguousarray(table), np.array([len(m) for m in maps], dtype=np.int32)
 

@@ -422,9 +422,20 @@ __global__ void __launch_bounds__(256) rb_block_mask_kernel(const RbProblem* __r
 //     memset); a live tile is written and flagged iff it ends up holding a non-zero word;
 //   dense format (flags == null): every tile of the packed upper triangle is written, dead ones as
 //     zeros with 16-byte stores.
+// Edge list of a problem (tile-skip format): every non-zero word of the strict upper triangle is also appended as a
+// triple (i << 16 | j, value) to the problem's list, capacity nb*32 entries; the count keeps growing past the
+// capacity so that the solver can tell an overflow (it then reads the tiles instead).
+struct RbEdgeOut {
+  unsigned* ij;
+  double* v;
+  int* count;  // this problem's counter
+  int cap;
+};
+
 __device__ __forceinline__ void affinity_tile(const RbProblem& pr, int I, int J, unsigned row_live, unsigned col_live,
                                               const RbAssocSoA& rec, Rec* s_row, double* __restrict__ Mp,
-                                              uint8_t* __restrict__ flags, const RbDevParams& P, int lane) {
+                                              uint8_t* __restrict__ flags, const RbEdgeOut& eo, const RbDevParams& P,
+                                              int lane) {
   const int64_t q = rb_tile_index(I, J, pr.nb);
   double* out = Mp + (pr.off_tile + q) * RB_TILE_ELEMS;
   const Rec col = load_rec(rec, pr.off_pad + (int64_t)J * RB_TILE + lane);
@@ -445,6 +456,20 @@ __device__ __forceinline__ void affinity_tile(const RbProblem& pr, int I, int J,
     }
     any_nz |= (v != 0.0);
     out[rb_tile_elem(r, lane)] = v;
+    if (eo.count) {
+      const bool edge = (__double_as_longlong(v) != 0ll) && (!diag || r < lane);
+      const unsigned em = __ballot_sync(0xffffffffu, edge);
+      if (em) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(eo.count, __popc(em));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const int pos = base + __popc(em & ((1u << lane) - 1u));
+        if (edge && pos < eo.cap) {
+          eo.ij[pos] = ((unsigned)(I * RB_TILE + r) << 16) | (unsigned)(J * RB_TILE + lane);
+          eo.v[pos] = v;
+        }
+      }
+    }
   }
   const unsigned nzb = __ballot_sync(0xffffffffu, any_nz);
   if (flags && lane == 0) flags[pr.off_tile + q] = nzb ? 1 : 0;
@@ -453,7 +478,8 @@ __device__ __forceinline__ void affinity_tile(const RbProblem& pr, int I, int J,
 __global__ void __launch_bounds__(256) rb_affinity_kernel(const RbProblem* __restrict__ probs, RbAssocSoA rec,
                                                           const uint32_t* __restrict__ masks,
                                                           double* __restrict__ Mp, uint8_t* __restrict__ flags,
-                                                          RbDevParams P) {
+                                                          unsigned* __restrict__ edge_ij, double* __restrict__ edge_v,
+                                                          int* __restrict__ edge_cnt, RbDevParams P) {
   __shared__ Rec s_row[8][RB_TILE];
   __shared__ unsigned s_mask[256];   // live mask per block (nb <= 160)
   __shared__ unsigned char s_live[256];  // indices of live blocks, ascending
@@ -480,6 +506,11 @@ __global__ void __launch_bounds__(256) rb_affinity_kernel(const RbProblem* __res
   }
   __syncthreads();
   const int nl = s_nl;
+  RbEdgeOut eo;
+  eo.ij = edge_ij ? edge_ij + pr.off_pad : nullptr;
+  eo.v = edge_v ? edge_v + pr.off_pad : nullptr;
+  eo.count = (flags && edge_cnt) ? edge_cnt + blockIdx.y : nullptr;
+  eo.cap = nb * RB_TILE;
 
   if (flags) {
     // live x live block pairs only: pair index pi <-> (a <= b) over the live-block list
@@ -493,7 +524,7 @@ __global__ void __launch_bounds__(256) rb_affinity_kernel(const RbProblem* __res
       while (a + 1 < nl && (a + 1) * nl - (a + 1) * a / 2 <= pi) ++a;
       const int bcol = a + (pi - (a * nl - a * (a - 1) / 2));
       const int I = s_live[a], J = s_live[bcol];
-      affinity_tile(pr, I, J, s_mask[I], s_mask[J], rec, s_row[warp], Mp, flags, P, lane);
+      affinity_tile(pr, I, J, s_mask[I], s_mask[J], rec, s_row[warp], Mp, flags, eo, P, lane);
     }
   } else {
     const int nt = (int)pr.n_tiles;
@@ -507,7 +538,7 @@ __global__ void __launch_bounds__(256) rb_affinity_kernel(const RbProblem* __res
         for (int t = 0; t < RB_TILE_ELEMS / 2 / 32; ++t) o2[t * 32 + lane] = make_double2(0.0, 0.0);
         continue;
       }
-      affinity_tile(pr, I, J, row_live, col_live, rec, s_row[warp], Mp, nullptr, P, lane);
+      affinity_tile(pr, I, J, row_live, col_live, rec, s_row[warp], Mp, nullptr, eo, P, lane);
     }
   }
 }
@@ -617,7 +648,8 @@ cudaError_t rb_launch_prep(const RbProblem* probs, int B, int max_mp, int max_n1
 
 cudaError_t rb_launch_affinity(const RbProblem* probs, int B, int64_t tile_base, int64_t total_tiles, int max_nb,
                                const RbAssocSoA& rec, uint32_t* masks, double* Mp, uint8_t* flags,
-                               const RbDevParams& P, int sm_count, cudaStream_t st) {
+                               unsigned* edge_ij, double* edge_v, int* edge_cnt, const RbDevParams& P, int sm_count,
+                               cudaStream_t st) {
   if (total_tiles == 0 || B == 0) return cudaSuccess;
   if (max_nb > 255) return cudaErrorInvalidValue;
   {
@@ -629,6 +661,10 @@ cudaError_t rb_launch_affinity(const RbProblem* probs, int B, int64_t tile_base,
   if (flags) {  // tile-skip format: dead tiles are never visited, so their flags are cleared up front
     cudaError_t e = cudaMemsetAsync(flags + tile_base, 0, (size_t)total_tiles, st);
     if (e != cudaSuccess) return e;
+    if (edge_cnt) {
+      e = cudaMemsetAsync(edge_cnt, 0, (size_t)B * sizeof(int), st);
+      if (e != cudaSuccess) return e;
+    }
   }
   // CTAs per problem: enough warps to cover the largest problem's tiles a few per warp, and at least
   // ~8 CTAs per SM over the whole launch when there are few problems
@@ -640,7 +676,8 @@ cudaError_t rb_launch_affinity(const RbProblem* probs, int B, int64_t tile_base,
   if (per > cap) per = cap;
   if (per < 1) per = 1;
   dim3 grid((unsigned)per, (unsigned)B);
-  rb_affinity_kernel<<<grid, 256, 0, st>>>(probs, rec, masks, Mp, flags, P);
+  rb_affinity_kernel<<<grid, 256, 0, st>>>(probs, rec, masks, Mp, flags, flags ? edge_ij : nullptr, flags ? edge_v : nullptr,
+                                           flags ? edge_cnt : nullptr, P);
   return cudaGetLastError();
 }
 

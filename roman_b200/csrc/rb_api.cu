@@ -40,6 +40,8 @@ struct rb_handle {
   double* d_pad_f64 = nullptr; size_t cap_pad = 0;    // padded double arrays (7 record + u, g per cluster CTA)
   int32_t* d_pad_i32 = nullptr;                       // 2 padded int arrays
   uint32_t* d_masks = nullptr;                        // one live-mask word per 32-association block
+  unsigned* d_edge_ij = nullptr; double* d_edge_v = nullptr;  // K1's edge lists (padded like the records)
+  int* d_edge_cnt = nullptr;                          // edges per problem (B)
   int32_t* d_counter = nullptr;
   int* d_bad = nullptr;
   long long* d_debug = nullptr;  // dev builds: per-CTA cycle counters of the solver
@@ -62,6 +64,7 @@ struct rb_handle {
   cudaEvent_t order_ev = nullptr;
 
   bool affinity_done = false;
+  bool edges_valid = false;   // K1 wrote the edge lists of the current packed matrix (not after rb_set_dense)
   bool profiling = false;
   // e0 prep start, e1 prep end = affinity start, e2 affinity end, e3/e4 solve, e5/e6 arun
   cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -185,7 +188,8 @@ int rb_destroy(rb_handle* h) {
   if (!h) return RB_OK;
   cudaSetDevice(h->device);
   cudaFree(h->d_probs); cudaFree(h->d_tile_prefix); cudaFree(h->d_M); cudaFree(h->d_flags); cudaFree(h->d_pad_f64);
-  cudaFree(h->d_pad_i32); cudaFree(h->d_masks); cudaFree(h->d_counter); cudaFree(h->d_bad); cudaFree(h->d_nodes); cudaFree(h->d_sel);
+  cudaFree(h->d_pad_i32); cudaFree(h->d_masks); cudaFree(h->d_edge_ij); cudaFree(h->d_edge_v); cudaFree(h->d_edge_cnt);
+  cudaFree(h->d_counter); cudaFree(h->d_bad); cudaFree(h->d_nodes); cudaFree(h->d_sel);
   cudaFree(h->d_nsel); cudaFree(h->d_score); cudaFree(h->d_ifinal); cudaFree(h->d_npass);
   cudaFree(h->d_status); cudaFree(h->d_T); cudaFree(h->d_resident);
   cudaFree(h->s_D1); cudaFree(h->s_D2); cudaFree(h->s_A); cudaFree(h->s_u0);
@@ -403,6 +407,11 @@ static int plan_impl(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, cons
       if (h->d_masks) cudaFree(h->d_masks);
       h->d_masks = nullptr;
       RB_CUDA(h, cudaMalloc((void**)&h->d_masks, (n / RB_TILE + 1) * sizeof(uint32_t)));
+      if (h->d_edge_ij) cudaFree(h->d_edge_ij);
+      if (h->d_edge_v) cudaFree(h->d_edge_v);
+      h->d_edge_ij = nullptr; h->d_edge_v = nullptr;
+      RB_CUDA(h, cudaMalloc((void**)&h->d_edge_ij, n * sizeof(unsigned)));
+      RB_CUDA(h, cudaMalloc((void**)&h->d_edge_v, n * sizeof(double)));
       h->cap_pad = n;
     }
   }
@@ -428,6 +437,8 @@ static int plan_impl(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, cons
     RB_CUDA(h, cudaMalloc((void**)&h->d_ifinal, n * sizeof(int32_t)));
     RB_CUDA(h, cudaMalloc((void**)&h->d_npass, n * sizeof(int32_t)));
     RB_CUDA(h, cudaMalloc((void**)&h->d_resident, n * sizeof(int32_t)));
+    cudaFree(h->d_edge_cnt); h->d_edge_cnt = nullptr;
+    RB_CUDA(h, cudaMalloc((void**)&h->d_edge_cnt, n * sizeof(int)));
     RB_CUDA(h, cudaMalloc((void**)&h->d_status, n * sizeof(int32_t)));
     RB_CUDA(h, cudaMalloc((void**)&h->d_T, n * 16 * sizeof(double)));
     h->cap_B = n;
@@ -488,8 +499,10 @@ int affinity_range(rb_handle* h, int b0, int b1, const double* D1, const double*
   record(h, 1, st);
   const int64_t base = h->tile_prefix[(size_t)b0];
   RB_CUDA(h, rb_launch_affinity(h->d_probs + b0, b1 - b0, base, h->tile_prefix[(size_t)b1] - base, h->max_mp / RB_TILE,
-                                rec, h->d_masks, h->d_M, h->tile_skip ? h->d_flags : nullptr, P, h->sm_count, st));
+                                rec, h->d_masks, h->d_M, h->tile_skip ? h->d_flags : nullptr, h->d_edge_ij, h->d_edge_v,
+                                h->d_edge_cnt + b0, P, h->sm_count, st));
   record(h, 2, st);
+  h->edges_valid = h->tile_skip;
   return RB_OK;
 }
 
@@ -499,6 +512,9 @@ int solve_range(rb_handle* h, int b0, int b1, int queue, const double* u0, int32
   RbSolveArgs a;
   a.probs = h->d_probs + b0; a.B = b1 - b0; a.counter = h->d_counter + queue; a.Mp = h->d_M;
   a.flags = h->tile_skip ? h->d_flags : nullptr;
+  a.edge_ij = (h->tile_skip && h->edges_valid) ? h->d_edge_ij : nullptr;
+  a.edge_v = h->d_edge_v;
+  a.edge_cnt = (h->tile_skip && h->edges_valid) ? h->d_edge_cnt + b0 : nullptr;
   a.nt_max = (h->max_mp / RB_TILE) * (h->max_mp / RB_TILE + 1) / 2;
   a.i1 = h->d_pad_i32; a.i2 = h->d_pad_i32 + (size_t)h->total_pad;
   a.u0 = u0; a.u_work = u_work(h); a.g_work = g_work(h);
@@ -608,6 +624,7 @@ int rb_set_dense(rb_handle* h, int32_t b, const double* M, const double* C, void
   RB_CUDA(h, cudaMemsetAsync(h->d_pad_i32 + (size_t)h->total_pad + pr.off_pad, 0, n * sizeof(int32_t), st));
   RB_CUDA(h, rb_launch_pack(pr, M, C, h->d_M, h->d_bad, st));
   RB_CUDA(h, cudaMemsetAsync(h->d_flags + pr.off_tile, 1, (size_t)pr.n_tiles, st));  // every tile of b is stored
+  h->edges_valid = false;  // no edge list for matrices given by the caller: the solver reads the tiles
   int bad = 0;
   RB_CUDA(h, cudaMemcpyAsync(&bad, h->d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
   RB_CUDA(h, cudaStreamSynchronize(st));

@@ -10,36 +10,46 @@
 
 namespace {
 
-__device__ void jacobi_eig3(double A[9], double V[9]) {
+// One Jacobi rotation in the (P, Q) plane of a symmetric 3x3 (row-major); P, Q compile-time so that A and V
+// stay in registers (runtime-indexed arrays would live in local memory).
+template <int P, int Q>
+__device__ __forceinline__ void jacobi_rot(double (&A)[9], double (&V)[9]) {
+  const double apq = A[P * 3 + Q];
+  if (apq == 0.0) return;
+  const double app = A[P * 3 + P], aqq = A[Q * 3 + Q];
+  const double theta = (aqq - app) / (2.0 * apq);
+  const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+  const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {  // A <- A J
+    const double akp = A[k * 3 + P], akq = A[k * 3 + Q];
+    A[k * 3 + P] = c * akp - s * akq;
+    A[k * 3 + Q] = s * akp + c * akq;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {  // A <- J^T A
+    const double apk = A[P * 3 + k], aqk = A[Q * 3 + k];
+    A[P * 3 + k] = c * apk - s * aqk;
+    A[Q * 3 + k] = s * apk + c * aqk;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double vkp = V[k * 3 + P], vkq = V[k * 3 + Q];
+    V[k * 3 + P] = c * vkp - s * vkq;
+    V[k * 3 + Q] = s * vkp + c * vkq;
+  }
+}
+
+// Cyclic Jacobi eigen-decomposition of a symmetric 3x3; V columns = eigenvectors.
+__device__ __forceinline__ void jacobi_eig3(double (&A)[9], double (&V)[9]) {
 #pragma unroll
   for (int i = 0; i < 9; ++i) V[i] = (i % 4 == 0) ? 1.0 : 0.0;
   for (int sweep = 0; sweep < 60; ++sweep) {
     const double off = A[1] * A[1] + A[2] * A[2] + A[5] * A[5];
     if (off < 1e-300) break;
-    for (int p = 0; p < 2; ++p)
-      for (int q = p + 1; q < 3; ++q) {
-        const double apq = A[p * 3 + q];
-        if (apq == 0.0) continue;
-        const double app = A[p * 3 + p], aqq = A[q * 3 + q];
-        const double theta = (aqq - app) / (2.0 * apq);
-        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-        for (int k = 0; k < 3; ++k) {
-          const double akp = A[k * 3 + p], akq = A[k * 3 + q];
-          A[k * 3 + p] = c * akp - s * akq;
-          A[k * 3 + q] = s * akp + c * akq;
-        }
-        for (int k = 0; k < 3; ++k) {
-          const double apk = A[p * 3 + k], aqk = A[q * 3 + k];
-          A[p * 3 + k] = c * apk - s * aqk;
-          A[q * 3 + k] = s * apk + c * aqk;
-        }
-        for (int k = 0; k < 3; ++k) {
-          const double vkp = V[k * 3 + p], vkq = V[k * 3 + q];
-          V[k * 3 + p] = c * vkp - s * vkq;
-          V[k * 3 + q] = s * vkp + c * vkq;
-        }
-      }
+    jacobi_rot<0, 1>(A, V);
+    jacobi_rot<0, 2>(A, V);
+    jacobi_rot<1, 2>(A, V);
   }
 }
 
@@ -50,50 +60,68 @@ __device__ double det3(const double* R) {
 // R (row-major 3x3) from H for point_dim 3
 __device__ void rotation_from_H3(const double H[9], double R[9]) {
   double HtH[9], V[9];
+#pragma unroll
   for (int a = 0; a < 3; ++a)
+#pragma unroll
     for (int b = 0; b < 3; ++b) {
       double s = 0;
+#pragma unroll
       for (int c = 0; c < 3; ++c) s += H[c * 3 + a] * H[c * 3 + b];
       HtH[a * 3 + b] = s;
     }
   jacobi_eig3(HtH, V);
-  const double ev[3] = {HtH[0], HtH[4], HtH[8]};
-  int ord[3] = {0, 1, 2};
-  for (int a = 0; a < 2; ++a)
-    for (int b = a + 1; b < 3; ++b)
-      if (ev[ord[b]] > ev[ord[a]]) { const int t = ord[a]; ord[a] = ord[b]; ord[b] = t; }
+  // columns of V sorted by descending eigenvalue (compare-and-swap network, everything in registers)
+  double e0 = HtH[0], e1 = HtH[4], e2 = HtH[8];
   double Vs[9];
-  for (int c = 0; c < 3; ++c)
-    for (int r = 0; r < 3; ++r) Vs[r * 3 + c] = V[r * 3 + ord[c]];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Vs[i] = V[i];
+  auto cswap = [&](double& ea, double& eb, int ca, int cb) {
+    if (eb > ea) {
+      const double t = ea; ea = eb; eb = t;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) { const double u = Vs[r * 3 + ca]; Vs[r * 3 + ca] = Vs[r * 3 + cb]; Vs[r * 3 + cb] = u; }
+    }
+  };
+  cswap(e0, e1, 0, 1);
+  cswap(e0, e2, 0, 2);
+  cswap(e1, e2, 1, 2);
   if (det3(Vs) < 0)
+#pragma unroll
     for (int r = 0; r < 3; ++r) Vs[r * 3 + 2] = -Vs[r * 3 + 2];
   double u0[3], u1[3], u2[3];
+#pragma unroll
   for (int r = 0; r < 3; ++r) {
     u0[r] = 0; u1[r] = 0;
+#pragma unroll
     for (int c = 0; c < 3; ++c) { u0[r] += H[r * 3 + c] * Vs[c * 3 + 0]; u1[r] += H[r * 3 + c] * Vs[c * 3 + 1]; }
   }
   const double n0 = sqrt(u0[0] * u0[0] + u0[1] * u0[1] + u0[2] * u0[2]);
   if (n0 < 1e-300) {  // H == 0
+#pragma unroll
     for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
     return;
   }
+#pragma unroll
   for (int r = 0; r < 3; ++r) u0[r] /= n0;
   const double dp = u0[0] * u1[0] + u0[1] * u1[1] + u0[2] * u1[2];
+#pragma unroll
   for (int r = 0; r < 3; ++r) u1[r] -= dp * u0[r];
   double n1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
   if (n1 < 1e-13 * n0) {  // rank 1: any unit vector orthogonal to u0
     const int a = fabs(u0[0]) < fabs(u0[1]) ? (fabs(u0[0]) < fabs(u0[2]) ? 0 : 2) : (fabs(u0[1]) < fabs(u0[2]) ? 1 : 2);
-    double e[3] = {0, 0, 0};
-    e[a] = 1.0;
-    const double dq = u0[a];
-    for (int r = 0; r < 3; ++r) u1[r] = e[r] - dq * u0[r];
+    const double dq = (a == 0) ? u0[0] : (a == 1 ? u0[1] : u0[2]);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) u1[r] = ((r == a) ? 1.0 : 0.0) - dq * u0[r];
     n1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
   }
+#pragma unroll
   for (int r = 0; r < 3; ++r) u1[r] /= n1;
   u2[0] = u0[1] * u1[2] - u0[2] * u1[1];
   u2[1] = u0[2] * u1[0] - u0[0] * u1[2];
   u2[2] = u0[0] * u1[1] - u0[1] * u1[0];
+#pragma unroll
   for (int a = 0; a < 3; ++a)
+#pragma unroll
     for (int b = 0; b < 3; ++b) R[a * 3 + b] = u0[a] * Vs[b * 3 + 0] + u1[a] * Vs[b * 3 + 1] + u2[a] * Vs[b * 3 + 2];
 }
 
@@ -119,11 +147,13 @@ __global__ void __launch_bounds__(128) rb_arun_kernel(const RbProblem* __restric
   for (int i = lane; i < k; i += 32) {
     const double* a = P1 + (int64_t)s[2 * i] * pr.d;
     const double* c = P2 + (int64_t)s[2 * i + 1] * pr.d;
+#pragma unroll
     for (int t = 0; t < 3; ++t) {
       m1[t] += (t < pd) ? a[t] : 0.0;
       m2[t] += (t < pd) ? c[t] : 0.0;
     }
   }
+#pragma unroll
   for (int t = 0; t < 3; ++t) {
     m1[t] = rb_warp_sum(m1[t]) / (double)k;
     m2[t] = rb_warp_sum(m2[t]) / (double)k;
@@ -133,13 +163,17 @@ __global__ void __launch_bounds__(128) rb_arun_kernel(const RbProblem* __restric
     const double* a = P1 + (int64_t)s[2 * i] * pr.d;
     const double* c = P2 + (int64_t)s[2 * i + 1] * pr.d;
     double da[3], dc[3];
+#pragma unroll
     for (int t = 0; t < 3; ++t) {
       da[t] = (t < pd) ? a[t] - m1[t] : 0.0;
       dc[t] = (t < pd) ? c[t] - m2[t] : 0.0;
     }
+#pragma unroll
     for (int x = 0; x < 3; ++x)
+#pragma unroll
       for (int y = 0; y < 3; ++y) H[x * 3 + y] += da[x] * dc[y];
   }
+#pragma unroll
   for (int e = 0; e < 9; ++e) H[e] = rb_warp_sum(H[e]);
   if (lane == 0) {
     double R[9];
@@ -150,7 +184,9 @@ __global__ void __launch_bounds__(128) rb_arun_kernel(const RbProblem* __restric
       const double c = cos(th), sn = sin(th);
       R[0] = c; R[1] = -sn; R[2] = 0; R[3] = sn; R[4] = c; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
     }
+#pragma unroll
     for (int a = 0; a < 3; ++a) {
+#pragma unroll
       for (int c = 0; c < 3; ++c) Tb[a * 4 + c] = R[a * 3 + c];
       Tb[a * 4 + 3] = m1[a] - (R[a * 3 + 0] * m2[0] + R[a * 3 + 1] * m2[1] + R[a * 3 + 2] * m2[2]);
     }

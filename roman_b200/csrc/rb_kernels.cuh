@@ -17,6 +17,9 @@ struct RbSolveArgs {
   const double* Mp;        // packed tiles
   const uint8_t* flags;    // per stored tile: 1 = holds a non-zero word; null = every tile is streamed (dense mode)
   int32_t nt_max;          // max stored tiles of one problem (sizes the shared-memory copy of the flags)
+  const unsigned* edge_ij; // tile-skip format: K1's edge lists (padded per problem, i << 16 | j) ...
+  const double* edge_v;    // ... their values ...
+  const int* edge_cnt;     // ... and counts (may exceed the capacity nb*32: overflow); null in the dense format
   const int32_t* i1;       // association object indices (padded arrays), for `sel`
   const int32_t* i2;
   const double* u0;        // user layout (off_assoc)
@@ -45,7 +48,8 @@ cudaError_t rb_launch_prep(const RbProblem* probs, int B, int max_mp, int max_n1
                            const RbDevParams& P, cudaStream_t st);
 cudaError_t rb_launch_affinity(const RbProblem* probs, int B, int64_t tile_base, int64_t total_tiles, int max_nb,
                                const RbAssocSoA& rec, uint32_t* masks, double* Mp, uint8_t* flags,
-                               const RbDevParams& P, int sm_count, cudaStream_t st);
+                               unsigned* edge_ij, double* edge_v, int* edge_cnt, const RbDevParams& P, int sm_count,
+                               cudaStream_t st);
 cudaError_t rb_launch_count_flags(const RbProblem* probs, int B, const uint8_t* flags, int32_t* out, cudaStream_t st);
 cudaError_t rb_launch_unpack(const RbProblem& pr, const double* Mp, const uint8_t* flags, double* Mout, double* Cout,
                              cudaStream_t st);

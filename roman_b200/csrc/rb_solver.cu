@@ -399,7 +399,8 @@ __device__ __forceinline__ void build_tile_lists(const Smem& S, const uint8_t* _
 // a CSR product out of shared memory.  Rows are sorted by column, so the summation order is fixed.
 // Returns false (all threads agree) if the triples do not fit; the caller then streams tiles.
 __device__ __forceinline__ bool build_compact(const Smem& S, const double* __restrict__ tiles, int nb, int mp,
-                                              uint32_t& phase_bits) {
+                                              uint32_t& phase_bits, const unsigned* __restrict__ e_ij,
+                                              const double* __restrict__ e_v, int e_n, int C, int crank) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, tid = threadIdx.x;
   const int SLOTS = S.slots;
   uint64_t* bar = S.bar + w * MAX_SLOTS;
@@ -414,7 +415,28 @@ __device__ __forceinline__ bool build_compact(const Smem& S, const double* __res
   if (tid == 0) *n_coo = 0;
   __syncthreads();
 
+  // Fast path: K1 has already listed this problem's edges (count within capacity).  Then the tiles are not
+  // read at all: this CTA takes its share of the list (the edges of its tile-rows) straight from HBM.
+  const bool listed = (e_ij != nullptr) && e_n >= 0 && e_n <= mp;
+  if (listed) {
+    const int npairs = (nb + 1) >> 1;
+    for (int e = tid; e < e_n; e += NT) {
+      const unsigned ij = e_ij[e];
+      bool mine = true;
+      if (C > 1) {
+        const int I = (int)(ij >> 16) / RB_TILE;
+        const int pr_ = I < npairs ? I : nb - 1 - I;  // tile-row pair index (see matvec work split)
+        mine = (pr_ % C) == crank;
+      }
+      if (mine) {
+        const int pos = atomicAdd(n_coo, 1);
+        if (pos < cap) { tv[pos] = e_v[e]; tij[pos] = ij; }
+      }
+    }
+  }
+
   int kpf = 0, slot = 0;
+  if (listed) kpf = cnt;  // nothing to stream
   auto pf_issue = [&](int sl) {
     const int e = wl[kpf++];
     if (lane == 0)
@@ -422,7 +444,7 @@ __device__ __forceinline__ bool build_compact(const Smem& S, const double* __res
   };
   for (int s2 = 0; s2 < SLOTS; ++s2)
     if (kpf < cnt) pf_issue(s2);
-  for (int k = 0; k < cnt; ++k) {
+  for (int k = 0; k < (listed ? 0 : cnt); ++k) {
     const int I = wl[k] >> 8, J = wl[k] & 255;
     mbar_wait(bar + slot, (phase_bits >> slot) & 1u);
     phase_bits ^= (1u << slot);
@@ -649,7 +671,8 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
 
     // tile-skip format: try to make this CTA's share of the matrix resident (read from HBM once)
     if (A.flags && m > 0) {
-      compact = build_compact(S, tiles, nb, mp, phase);
+      compact = build_compact(S, tiles, nb, mp, phase, A.edge_ij ? A.edge_ij + pr.off_pad : nullptr,
+                              A.edge_v ? A.edge_v + pr.off_pad : nullptr, A.edge_cnt ? A.edge_cnt[b] : -1, C, crank);
       if (C > 1) {  // every CTA of the cluster must run the same kind of pass (they combine their partials)
         cluster.sync();
         if (tid == 0) S.misc[15] = compact ? 1 : 0;

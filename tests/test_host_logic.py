@@ -114,8 +114,12 @@ def test_object_row_packing_matches_reference_order():
                       extent=np.array([3.0, 1.0, 2.0]), semantic_descriptor=np.array([9.0, 8.0]))
     reg = ROMANRegistration(ROMANParams(volume=True, pca=True, extent=True, semantics_dim=2))
     assert reg._object_to_clipper_list(ob) == [1, 2, 3, 0.1, 0.2, 0.3, 7, 1, 2, 3, 9, 8]
+    assert np.array_equal(reg.rows([ob, ob]), np.array([reg._object_to_clipper_list(ob)] * 2))  # vectorised packing
+    table, counts = reg.pack([[ob], [], [ob, ob]])
+    assert table.shape == (3, 12) and counts.tolist() == [1, 0, 2]
     reg = ROMANRegistration(ROMANParams(volume=True))
     assert reg._object_to_clipper_list(ob) == [1, 2, 3, 7]
+    assert np.array_equal(reg.rows([ob]), [[1, 2, 3, 7]])
     assert reg.register([], [ob]).shape == (1, 0)  # np.array([[]]) for an empty map (object_registration.py:23-24)
 
 
