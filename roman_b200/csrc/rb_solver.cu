@@ -481,19 +481,25 @@ __device__ __forceinline__ bool build_compact(const Smem& S, const double* __res
     atomicAdd(&rowptr[(ij & 0xffffu) + 1], 1);
   }
   __syncthreads();
-  if (w == 0) {  // inclusive scan of rowptr[1..mp] by one warp (mp <= 5120)
-    int carry = 0;
-    for (int base = 1; base <= mp; base += 32) {
-      const int i = base + lane;
-      int v = (i <= mp) ? rowptr[i] : 0;
+  {  // inclusive scan of rowptr[1..mp]: each thread owns a contiguous run; warp scan of the run totals; warp offsets
+    const int per = (mp + NT - 1) / NT;
+    const int lo = 1 + tid * per, hi = (lo + per <= mp + 1) ? lo + per : mp + 1;
+    int run = 0;
+    for (int i = lo; i < hi; ++i) run += rowptr[i];
+    int v = run;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int u = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += u;
-      }
-      if (i <= mp) rowptr[i] = v + carry;
-      carry += __shfl_sync(0xffffffffu, v, 31);
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += up;
     }
+    int* wsum = reinterpret_cast<int*>(S.red + 48);  // 8 ints of scratch; no reduction is in flight here
+    if (lane == 31) wsum[w] = v;
+    __syncthreads();
+    int acc = v - run;  // exclusive prefix inside the warp ...
+#pragma unroll
+    for (int ww = 0; ww < NW; ++ww)
+      if (ww < w) acc += wsum[ww];  // ... plus the warps before
+    for (int i = lo; i < hi; ++i) { acc += rowptr[i]; rowptr[i] = acc; }
   }
   __syncthreads();
   for (int e = tid; e < n; e += NT) {
@@ -656,7 +662,11 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
     const double* u0 = A.u0 + pr.off_assoc;
     int passes = 0;
     long long tb0 = clock64();
-    if (A.flags) {
+    // tile-skip format: problems whose edges K1 has listed (count within capacity) are built straight from that
+    // list and need no tile lists at all; the others walk their stored tiles
+    const int e_n = (A.edge_cnt != nullptr) ? A.edge_cnt[b] : -1;
+    const bool listed = (A.edge_ij != nullptr) && e_n >= 0 && e_n <= mp && e_n <= S.c_cap;
+    if (A.flags && !listed) {
       build_tile_lists(S, A.flags + pr.off_tile, nb, C, crank);
       __syncthreads();
     }
@@ -671,8 +681,8 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
 
     // tile-skip format: try to make this CTA's share of the matrix resident (read from HBM once)
     if (A.flags && m > 0) {
-      compact = build_compact(S, tiles, nb, mp, phase, A.edge_ij ? A.edge_ij + pr.off_pad : nullptr,
-                              A.edge_v ? A.edge_v + pr.off_pad : nullptr, A.edge_cnt ? A.edge_cnt[b] : -1, C, crank);
+      compact = build_compact(S, tiles, nb, mp, phase, listed ? A.edge_ij + pr.off_pad : nullptr,
+                              listed ? A.edge_v + pr.off_pad : nullptr, listed ? e_n : -1, C, crank);
       if (C > 1) {  // every CTA of the cluster must run the same kind of pass (they combine their partials)
         cluster.sync();
         if (tid == 0) S.misc[15] = compact ? 1 : 0;
