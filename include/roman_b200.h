@@ -204,6 +204,10 @@ int rb_align_batch_host(rb_handle* h, const double* D1, const double* D2, const 
                         const double* u0, int32_t* sel, int32_t* n_sel, double* T,
                         int32_t* status, double* score, int32_t* n_passes);
 
+/* Diagnostics (used by tools/): first call enables per-CTA cycle counters in the solver kernel, later calls copy
+ * them out: 8 x int64 per CTA — total, mat-vec, cluster combine, queue wait, rounding, list/CSR build. */
+int rb_debug_solver_cycles(rb_handle* h, long long* out, int n_ctas);
+
 /* Library/build identification. */
 const char* rb_version(void);
 int rb_device_sm_count(const rb_handle* h);

@@ -73,6 +73,7 @@ SIGNATURES = {
     "rb_set_profiling": (C.c_int, [_vp, _i32]),
     "rb_get_stage_ms": (C.c_int, [_vp, _fp]),
     "rb_align_batch_host": (C.c_int, [_vp, _dp, _dp, _ip, _dp, _ip, _ip, _dp, _ip, _dp, _ip]),
+    "rb_debug_solver_cycles": (C.c_int, [_vp, _vp, C.c_int]),
     "rb_version": (C.c_char_p, []),
     "rb_device_sm_count": (C.c_int, [_vp]),
 }
