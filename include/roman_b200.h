@@ -182,9 +182,14 @@ int rb_get_solver_max_clusters(const rb_handle* h); /* co-resident clusters of t
  * Changing the format invalidates the plan: call rb_plan again (the solver's cluster size is chosen per format). */
 int rb_set_tile_skip(rb_handle* h, int32_t on);
 
-/* After rb_solve: device int32[B], 1 where the solve ran in resident mode (the problem's stored tiles were read
- * from HBM once and every pass ran from a shared-memory CSR), 0 where the tiles were streamed each pass. */
+/* After rb_solve: device int32[B] — 0: the problem's stored tiles were streamed every pass; 1: resident mode, the
+ * shared-memory CSR was built from one pass over the stored tiles; 2: resident mode, the CSR was built from the edge
+ * list K1 wrote (no tile read at all). */
 int rb_solver_resident(rb_handle* h, int32_t* out, void* stream);
+
+/* Tile-skip format, after rb_affinity: edges (non-zero words of the strict upper triangle) K1 found per problem,
+ * device int32[B]; a count above the list capacity (32 * ceil(m/32)) means the list overflowed and is not used. */
+int rb_edge_counts(rb_handle* h, int32_t* out, void* stream);
 
 /* Tile-skip format only: number of stored (flagged) 32x32 tiles of each problem, device int32[B]. */
 int rb_stored_tiles(rb_handle* h, int32_t* out, void* stream);

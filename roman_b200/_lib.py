@@ -68,6 +68,7 @@ SIGNATURES = {
     "rb_get_solver_cluster": (C.c_int, [_vp]),
     "rb_get_solver_max_clusters": (C.c_int, [_vp]),
     "rb_set_tile_skip": (C.c_int, [_vp, _i32]),
+    "rb_edge_counts": (C.c_int, [_vp, _ip, _vp]),
     "rb_stored_tiles": (C.c_int, [_vp, _ip, _vp]),
     "rb_solver_resident": (C.c_int, [_vp, _ip, _vp]),
     "rb_set_profiling": (C.c_int, [_vp, _i32]),

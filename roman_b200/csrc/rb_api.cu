@@ -265,6 +265,15 @@ int rb_set_tile_skip(rb_handle* h, int32_t on) {
   return RB_OK;
 }
 
+int rb_edge_counts(rb_handle* h, int32_t* out, void* stream) {
+  if (!h || !out) return RB_ERR_ARG;
+  if (!h->planned || !h->affinity_done) return fail(h, RB_ERR_NOPLAN, "rb_edge_counts before rb_affinity");
+  if (!h->tile_skip || !h->edges_valid) return fail(h, RB_ERR_ARG, "rb_edge_counts: no edge lists (dense format or rb_set_dense)");
+  if (h->B > 0)
+    RB_CUDA(h, cudaMemcpyAsync(out, h->d_edge_cnt, (size_t)h->B * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return RB_OK;
+}
+
 int rb_solver_resident(rb_handle* h, int32_t* out, void* stream) {
   if (!h || !out) return RB_ERR_ARG;
   if (!h->planned) return fail(h, RB_ERR_NOPLAN, "rb_solver_resident before rb_plan");

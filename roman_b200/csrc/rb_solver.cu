@@ -933,7 +933,7 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
       A.score[b] = F;
       A.ifinal[b] = i_ol;
       A.n_passes[b] = passes;
-      A.resident[b] = compact ? 1 : 0;
+      A.resident[b] = compact ? (listed ? 2 : 1) : 0;
     }
     t_round += clock64() - tr0;
   }

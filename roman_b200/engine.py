@@ -122,8 +122,14 @@ class Engine:
         self._check(self._lib.rb_stored_tiles(self._h, _ptr(out), self._stream()))
         return out
 
+    def edge_counts(self) -> torch.Tensor:
+        """(B,) int32: edges K1 listed per problem (tile-skip format)."""
+        out = torch.zeros(max(self.B, 1), dtype=torch.int32, device=self.device)
+        self._check(self._lib.rb_edge_counts(self._h, _ptr(out), self._stream()))
+        return out
+
     def solver_resident(self) -> torch.Tensor:
-        """(B,) int32: 1 where the last solve ran from the shared-memory CSR (tiles read once)."""
+        """(B,) int32: 0 tiles streamed every pass, 1 resident (CSR from one pass over the tiles), 2 resident (CSR from K1's edge list)."""
         out = torch.zeros(max(self.B, 1), dtype=torch.int32, device=self.device)
         self._check(self._lib.rb_solver_resident(self._h, _ptr(out), self._stream()))
         return out
