@@ -8,8 +8,10 @@ One "step" = one pass of the hot path (K1a + K1 + K2 + K3) over one batch of B s
 pairs per GPU.  Workload at every N (weak scaling, B pairs per GPU): n1=40, n2=50 objects
 (m = 2000 all-to-all correspondences), method 'roman' (gravity + PCA + volume + 768-d semantics),
 SubmapAlignParams defaults — the configuration BASELINE.json's metric is quoted on.
-Printed JSON line: see the task contract; `roofline` is for the dominant kernel (K2, the
-solver's streaming pass over the packed affinity matrix), `kernels` lists K1 and K2 separately.
+Printed JSON line: see the task contract; everything at the top level is measured in the library's
+default DENSE format (every tile of the packed affinity matrix written by K1 and streamed by K2 each
+pass): `roofline` is for the dominant kernel (K2), `kernels` lists K1 and K2 separately.  `fast_path`
+repeats value / e2e / per-kernel times with the opt-in sparse fast path (rb_set_tile_skip).
 
 --impl reference times the reference algorithm's CPU restatement (oracle/, kind "port": the
 reference itself needs Eigen3 and cannot be compiled in this image) on all host cores.
@@ -263,108 +265,110 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), stage
 
+    def e2e_run():
+        """K calls of the host-buffer C ABI entry point: pinned host inputs, H2D + kernels + D2H inside the timed region."""
+        out_h = None
+        sync()
+        for _ in range(max(1, min(W, 3))):
+            out_h = eng.align_batch_host(D1p, D2p, u0p, out=out_h)
+        sync()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            out_h = eng.align_batch_host(D1p, D2p, u0p, out=out_h)
+        wall = time.perf_counter() - t0
+        te = torch.tensor([wall], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return world * B * K / float(te.item()), out_h
+
     eng.set_profiling(True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         sampler.wait_ready()
-    # ---- main measurement: the product's default format (tile skip: only tiles holding a non-zero are stored/streamed)
-    ms, stage = timed(True, sampler if rank == 0 else None)
+    # ---- main measurement: the library's default (dense) format — every tile of the packed upper triangle is written
+    #      by K1 and streamed by K2 each pass: the kernels and byte counts of BASELINE.json's north_star / SURVEY 8d
+    ms, stage = timed(False, sampler if rank == 0 else None)
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * K / (ms * 1e-3)
     passes = res.n_passes.cpu().numpy().astype(np.int64)
-    stored = eng.stored_tiles().cpu().numpy().astype(np.int64)
-    resident = eng.solver_resident().cpu().numpy().astype(np.int64)
-    edges = eng.edge_counts().cpu().numpy().astype(np.int64)
-    cluster_skip = eng.solver_cluster
-    # ---- same batch through the plain dense format (every tile written and streamed): the north-star kernels
-    do_dense = (args.format == "both")
-    if do_dense:
-        ms_d, stage_d = timed(False)
-    else:
-        ms_d, stage_d = float("nan"), {k: float("nan") for k in stage}
-    passes_d = res.n_passes.cpu().numpy().astype(np.int64)
     cluster_dense = eng.solver_cluster
-    eng.set_tile_skip(True)
-    eng.plan(d_row, [N1] * B, [N2] * B)
-
-    # ---- end-to-end through the host-buffer C ABI: pinned host inputs, H2D + kernels + D2H inside the timed region
-    out_h = None
-    sync()
-    for _ in range(max(1, min(W, 3))):
-        out_h = eng.align_batch_host(D1p, D2p, u0p, out=out_h)
-    sync()
-    t0 = time.perf_counter()
-    for _ in range(K):
-        out_h = eng.align_batch_host(D1p, D2p, u0p, out=out_h)
-    wall = time.perf_counter() - t0
-    te = torch.tensor([wall], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * K / float(te.item())
+    e2e_value, out_h = e2e_run()
     h2d = (D1p.numel() + D2p.numel() + u0p.numel()) * 8
     d2h = sum(v.nbytes for v in out_h.values())
+
+    # ---- same batch through the opt-in sparse fast path (rb_set_tile_skip): only tiles holding a non-zero are stored,
+    #      K1 lists the edges, K2 solves from a shared-memory CSR
+    do_fast = (args.format == "both")
+    if do_fast:
+        ms_f, stage_f = timed(True)
+        passes_f = res.n_passes.cpu().numpy().astype(np.int64)
+        stored = eng.stored_tiles().cpu().numpy().astype(np.int64)
+        resident = eng.solver_resident().cpu().numpy().astype(np.int64)
+        edges = eng.edge_counts().cpu().numpy().astype(np.int64)
+        cluster_fast = eng.solver_cluster
+        e2e_fast, _ = e2e_run()
+        eng.set_tile_skip(False)
+        eng.plan(d_row, [N1] * B, [N2] * B)
 
     if rank == 0:
         peaks, which = measured_peaks()
         peak = float(peaks["hbm_gbs"])
         gbs = lambda nbytes, t_ms: nbytes / (t_ms * 1e-3) / 1e9
         in_bytes = B * (8.0 * d_row * (N1 + N2) + 8.0 * m)
-        # algorithmic bytes.  dense format (SURVEY 8d with the packed-upper layout): K1 writes, K2 reads per pass,
-        # s*m(m-1)/2.  tile-skip format: only stored tiles (8 KB each) move, plus one flag byte per tile.
+        # algorithmic bytes, dense format (SURVEY 8d with the packed-upper layout, s = 8): K1 writes and K2 reads per
+        # pass s*m(m-1)/2; K1 also reads both feature tables and writes the single scores
         tri = 8.0 * m * (m - 1) / 2
-        k2_dense = float(passes_d.sum()) * (tri + 24.0 * m)
-        k1_dense = B * tri + in_bytes
-        n_tiles = (m // 32 + (m % 32 > 0)) * (m // 32 + (m % 32 > 0) + 1) // 2
-        # K2 in the tile-skip format: a problem solved from K1's edge list reads 12 B per edge once; one built from its
-        # tiles reads them once; a streamed one reads them every pass.  Plus u0 in, u/g scratch and the outputs (~24 m).
-        per_prob = np.where(resident == 2, edges * 12, np.where(resident == 1, stored * 8192, passes * stored * 8192))
-        k2_skip = float((per_prob + 24 * m).sum()) + float(B * n_tiles)
-        k1_skip = float(stored.sum()) * 8192 + B * n_tiles + in_bytes
+        k2_bytes = float(passes.sum()) * (tri + 24.0 * m)
+        k1_bytes = B * tri + in_bytes
         k1_ms = stage["prep"] + stage["affinity"]
-        k1d_ms = stage_d["prep"] + stage_d["affinity"]
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the
-        # dense-format solver at this configuration (profiles/r1_solver_v3_B592_summary.txt); null for other batch sizes
-        traffic_dense = 53.063292e9 + 170.490880e6 if (B == 592 and world == 1) else None
+        n_tiles = (m // 32 + (m % 32 > 0)) * (m // 32 + (m % 32 > 0) + 1) // 2
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
+        # kernel at this configuration (profiles/r1_solver_final_dense_B592_summary.txt); null for other batch sizes
+        traffic = 53.054540e9 + 170.393088e6 if (B == 592 and world == 1) else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "parallelism": f"round-robin pairs over {world} GPU(s)",
-                       "l2": f"inputs larger than L2: packed affinity buffer {eng.packed_bytes / 1e9:.2f} GB per GPU per step "
-                             f"({float(stored.sum()) * 8192 / 1e9:.2f} GB of it stored/streamed in the tile-skip format)",
-                       "layout": "packed upper triangle, 32x32 fp64 tiles; tile-skip format (default): only tiles holding a non-zero",
-                       "mean_passes": float(passes.mean()), "mean_stored_tiles": float(stored.mean()), "tiles_per_problem": int(n_tiles)},
-            "roofline": {"kernel": "rb_solver_kernel (K2), tile-skip format", "bound": "hbm", "achieved": gbs(k2_skip, stage["solve"]),
-                         "peak": peak, "unit": "GB/s", "frac": gbs(k2_skip, stage["solve"]) / peak, "traffic": None,
-                         "peak_source": which, "algorithmic_bytes_per_launch": k2_skip, "ms_per_launch": stage["solve"],
-                         "resident_problems": int((resident > 0).sum()), "from_edge_list": int((resident == 2).sum()),
-                         "mean_edges": float(edges.mean()), "cluster": int(cluster_skip),
-                         "note": "default (tile-skip) format: the affinity graphs of this workload have ~400 edges per 2000x2000 "
-                                 "problem, every problem is solved from a shared-memory CSR built from K1's edge list, so this kernel "
-                                 "moves almost no HBM bytes and is latency/compute-bound by construction; the HBM roofline of the "
-                                 "solver streaming the dense format (the kernel BASELINE.json's north_star names) is dense_stream.roofline"},
-            "kernels": {"K1_affinity": {"achieved": gbs(k1_skip, k1_ms), "frac": gbs(k1_skip, k1_ms) / peak, "ms_per_launch": k1_ms,
-                                        "algorithmic_bytes_per_launch": k1_skip},
-                        "K2_solver": {"achieved": gbs(k2_skip, stage["solve"]), "frac": gbs(k2_skip, stage["solve"]) / peak,
+                       "l2": f"inputs larger than L2: packed affinity working set {eng.packed_bytes / 1e9:.2f} GB per GPU per step",
+                       "layout": "packed upper triangle, 32x32 fp64 tiles, dense format (every tile written by K1 and streamed by K2 each pass)",
+                       "mean_passes": float(passes.mean()), "solver_cluster": int(cluster_dense)},
+            "roofline": {"kernel": "rb_solver_kernel (K2)", "bound": "hbm", "achieved": gbs(k2_bytes, stage["solve"]),
+                         "peak": peak, "unit": "GB/s", "frac": gbs(k2_bytes, stage["solve"]) / peak, "traffic": traffic,
+                         "peak_source": which, "algorithmic_bytes_per_launch": k2_bytes, "ms_per_launch": stage["solve"]},
+            "kernels": {"K1_affinity": {"achieved": gbs(k1_bytes, k1_ms), "frac": gbs(k1_bytes, k1_ms) / peak, "ms_per_launch": k1_ms,
+                                        "algorithmic_bytes_per_launch": k1_bytes,
+                                        "launches": "rb_prep_table_kernel + rb_block_mask_kernel + rb_affinity_kernel"},
+                        "K2_solver": {"achieved": gbs(k2_bytes, stage["solve"]), "frac": gbs(k2_bytes, stage["solve"]) / peak,
                                       "ms_per_launch": stage["solve"]},
                         "K3_arun_ms": stage["arun"]},
-            "dense_stream": {
-                "what": "same batch, rb_set_tile_skip(0): every tile of the packed upper triangle written by K1 and streamed by K2 "
-                        "each pass (the dense kernels BASELINE.json's north_star names); results bitwise identical",
-                "value": world * B * K / (ms_d * 1e-3), "ms_per_step": ms_d / K,
-                "roofline": {"kernel": "rb_solver_kernel (K2), dense format", "bound": "hbm", "achieved": gbs(k2_dense, stage_d["solve"]),
-                             "peak": peak, "unit": "GB/s", "frac": gbs(k2_dense, stage_d["solve"]) / peak, "traffic": traffic_dense,
-                             "algorithmic_bytes_per_launch": k2_dense, "ms_per_launch": stage_d["solve"], "cluster": int(cluster_dense)},
-                "K1_affinity": {"achieved": gbs(k1_dense, k1d_ms), "frac": gbs(k1_dense, k1d_ms) / peak, "ms_per_launch": k1d_ms,
-                                "algorithmic_bytes_per_launch": k1_dense}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "api": "rb_align_batch_host (pinned host buffers; H2D pipelined with K1a/K1/K2/K3 over 4 problem ranges, then D2H)"},
             "gpu_launches": 5 * K,
             "clocks": clocks,
         }
-        if not do_dense:
-            line.pop("dense_stream")
+        if do_fast:
+            # fast path bytes: a problem solved from K1's edge list reads 12 B per edge once; one built from its tiles reads
+            # them once; a streamed one reads them every pass; plus u0 in, scratch and outputs (~24 m) and the tile flags
+            per_prob = np.where(resident == 2, edges * 12, np.where(resident == 1, stored * 8192, passes_f * stored * 8192))
+            k2f = float((per_prob + 24 * m).sum()) + float(B * n_tiles)
+            k1f = float(stored.sum()) * 8192 + B * n_tiles + float(np.minimum(edges, 32 * (m // 32 + (m % 32 > 0))).sum()) * 12 + in_bytes
+            k1f_ms = stage_f["prep"] + stage_f["affinity"]
+            line["fast_path"] = {
+                "what": "same batch with rb_set_tile_skip(1), the opt-in sparse fast path (SURVEY 8f rank 2): K1 stores only tiles "
+                        "holding a non-zero and lists the edges, K2 solves every problem of this workload from a shared-memory CSR "
+                        "built from that list; identical ordered inliers, u and F within the oracle tolerances. These kernels move "
+                        "almost no HBM bytes: they are latency / fp64 bound by construction, the HBM rooflines above do not apply",
+                "value": world * B * K / (ms_f * 1e-3), "ms_per_step": ms_f / K,
+                "e2e": {"value": e2e_fast, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "note": "PCIe-bound: the host-to-device copy of the fp64 descriptors alone takes ~6.8 ms per step"},
+                "kernels": {"K1_affinity": {"ms_per_launch": k1f_ms, "bytes_per_launch": k1f, "achieved": gbs(k1f, k1f_ms)},
+                            "K2_solver": {"ms_per_launch": stage_f["solve"], "bytes_per_launch": k2f, "achieved": gbs(k2f, stage_f["solve"])},
+                            "K3_arun_ms": stage_f["arun"]},
+                "resident_problems": int((resident > 0).sum()), "from_edge_list": int((resident == 2).sum()),
+                "mean_edges": float(edges.mean()), "mean_stored_tiles": float(stored.mean()), "tiles_per_problem": int(n_tiles),
+                "solver_cluster": int(cluster_fast)}
         if world == 1 and not args.no_cpu:
             cb, _ = cpu_baseline(16)
             line["cpu_baseline"] = cb
@@ -381,8 +385,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=592, help="submap pairs per GPU per step (4 x 148 SMs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--format", default="both", choices=["both", "tile-skip"],
-                    help="both: also time the same batch in the dense format (dense_stream); tile-skip: default format only")
+    ap.add_argument("--format", default="both", choices=["both", "dense"],
+                    help="both: also time the opt-in sparse fast path (fast_path block); dense: default format only")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -175,9 +175,10 @@ int rb_set_solver_cluster(rb_handle* h, int32_t ctas_per_problem);
 int rb_get_solver_cluster(const rb_handle* h);
 int rb_get_solver_max_clusters(const rb_handle* h); /* co-resident clusters of that size (after rb_plan) */
 
-/* Storage format of the packed affinity matrix.  on (default): K1 records per 32x32 tile whether it
- * holds any non-zero word, writes only such tiles, and K2 streams only those ("tile skip").  off: every
- * tile of the packed upper triangle is written and streamed each pass (the plain dense kernels).
+/* Storage format of the packed affinity matrix.
+ * off (default) — DENSE: every tile of the packed upper triangle is written by K1 and streamed by K2 each pass.
+ * on — TILE SKIP, the sparse fast path: K1 records per 32x32 tile whether it holds any non-zero word, writes only
+ *   such tiles and lists the edges; K2 reads only what is stored and solves small problems from a shared-memory CSR.
  * The stored matrices are bitwise identical in both formats, the solves agree to rounding (summation order).
  * Changing the format invalidates the plan: call rb_plan again (the solver's cluster size is chosen per format). */
 int rb_set_tile_skip(rb_handle* h, int32_t on);

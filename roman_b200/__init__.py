@@ -9,6 +9,12 @@ the C ABI of include/roman_b200.h, plus the Python host layer that mirrors the r
 __version__ = "0.1.0"
 
 
+def set_default_tile_skip(on: bool):
+    """Process-wide default packed-affinity format of new engines: False dense (default), True tile skip (fast path)."""
+    from . import engine
+    engine.set_default_tile_skip(on)
+
+
 def install_as_clipperpy():
     """Register roman_b200.clipperpy under the module name `clipperpy`, so that an unmodified
     `roman.align` (which does `import clipperpy`) runs on the B200 path."""

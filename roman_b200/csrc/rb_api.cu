@@ -36,7 +36,7 @@ struct rb_handle {
   int64_t* d_tile_prefix = nullptr; size_t cap_prefix = 0;
   double* d_M = nullptr; size_t cap_M = 0;            // packed tiles
   uint8_t* d_flags = nullptr; size_t cap_flags = 0;   // per stored tile: holds a non-zero word (tile-skip mode)
-  bool tile_skip = true;                              // rb_set_tile_skip
+  bool tile_skip = false;                             // rb_set_tile_skip (default: dense format)
   double* d_pad_f64 = nullptr; size_t cap_pad = 0;    // padded double arrays (7 record + u, g per cluster CTA)
   int32_t* d_pad_i32 = nullptr;                       // 2 padded int arrays
   uint32_t* d_masks = nullptr;                        // one live-mask word per 32-association block

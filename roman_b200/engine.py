@@ -22,6 +22,16 @@ class RomanB200Error(RuntimeError):
     pass
 
 
+# Packed-affinity format new Engines start in: False = dense (every tile written and streamed, the library default),
+# True = tile skip (the sparse fast path, see rb_set_tile_skip).  set_default_tile_skip() changes it process-wide.
+DEFAULT_TILE_SKIP = False
+
+
+def set_default_tile_skip(on: bool):
+    global DEFAULT_TILE_SKIP
+    DEFAULT_TILE_SKIP = bool(on)
+
+
 def default_invariant_params() -> RbInvariantParams:
     p = RbInvariantParams()
     _lib.lib().rb_default_invariant_params(C.byref(p))
@@ -68,6 +78,8 @@ class Engine:
         if rc != 0:
             raise RomanB200Error(f"rb_create failed ({rc})")
         self._h = h
+        if DEFAULT_TILE_SKIP:
+            self._lib.rb_set_tile_skip(self._h, 1)
         self.B = 0
         self.d = 0
         self.offsets = np.zeros(1, dtype=np.int64)
@@ -112,7 +124,8 @@ class Engine:
         return int(self._lib.rb_get_solver_cluster(self._h))
 
     def set_tile_skip(self, on: bool):
-        """Packed-affinity format: True (default) stores/streams only tiles holding a non-zero; False = plain dense.
+        """Packed-affinity format: False (default) = dense, True = tile skip (stores/streams only tiles holding a non-zero,
+        resident solves).
         Changing it invalidates the plan: call plan() again."""
         self._check(self._lib.rb_set_tile_skip(self._h, int(on)))
 

@@ -18,10 +18,23 @@ def coracle():
     return oracle.COracle()
 
 
-@pytest.fixture(scope="session")
-def engine():
+@pytest.fixture(scope="session", params=["dense", "tile-skip"])
+def engine(request):
+    """Every GPU test runs in both packed-affinity formats: the dense one (library default) and the tile-skip fast
+    path; the process-wide default is switched too, so engines created inside the registration classes follow."""
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
+    import roman_b200
+    from roman_b200 import clipperpy
+    from roman_b200.clipperpy import _core
+    from roman_b200.align import object_registration
     from roman_b200.engine import Engine
-    return Engine(0)
+    skip = request.param == "tile-skip"
+    roman_b200.set_default_tile_skip(skip)
+    _core._pool.clear()                     # pooled engines were created under the other default
+    object_registration._arun_engine = None
+    e = Engine(0)
+    e.default_tile_skip = skip
+    yield e
+    roman_b200.set_default_tile_skip(False)

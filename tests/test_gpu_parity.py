@@ -223,7 +223,7 @@ def test_tile_skip_and_dense_formats_agree(engine, coracle):
             sol = engine.solve(u0, want_u=True)
             outs.append((dense, {k: (v.cpu().numpy() if v is not None else None) for k, v in sol.items()}))
     finally:
-        engine.set_tile_skip(True)
+        engine.set_tile_skip(engine.default_tile_skip)
     (d_a, s_a), (d_b, s_b) = outs
     for b in range(len(pairs)):
         assert np.array_equal(d_a[b][0], d_b[b][0]) and np.array_equal(d_a[b][1], d_b[b][1])
