@@ -8,6 +8,7 @@ Host-side mirror of the reference's roman.align registration interface for the C
   dist_reg_with_pruning.py <- roman/align/dist_reg_with_pruning.py
   params.py                <- roman/params/submap_align_params.py (registration-related part)
   submap_align.py          <- the pair loop of roman/align/submap_align.py:93-200, batched (all pairs in one launch)
+  results.py               <- the loop-closure writers of roman/align/results.py:149-197 (align.g2o, align.json)
 """
 from .object_registration import InsufficientAssociationsException, ObjectRegistration  # noqa: F401
 from .roman_registration import FusionMethod, ROMANParams, ROMANRegistration  # noqa: F401
@@ -15,3 +16,4 @@ from .dist_reg_with_pruning import DistRegWithPruning, GravityConstraintError  #
 from .params import SubmapAlignParams  # noqa: F401
 from .objects import SimpleObject  # noqa: F401
 from .submap_align import align_submap_pairs, SubmapPairResults  # noqa: F401
+from .results import SubmapMeta, loop_closures, write_g2o, write_lc_json  # noqa: F401

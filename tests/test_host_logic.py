@@ -200,3 +200,47 @@ def test_all_gather_of_records_world_size_2_gloo(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env={**os.environ, "OMP_NUM_THREADS": "1"})
     assert r.returncode == 0, r.stderr[-2000:]
     assert "GLOO_OK" in r.stdout
+
+
+def test_loop_closure_wire_formats(tmp_path):
+    """align.g2o / align.json (reference roman/align/results.py:149-197): record selection, pose chain, text layout."""
+    import json
+    from scipy.spatial.transform import Rotation as Rot
+    from roman_b200.align.results import SubmapMeta, loop_closures, write_g2o, write_lc_json
+    from roman_b200.align.submap_align import SubmapPairResults
+    rng = np.random.default_rng(0)
+
+    def rand_T():
+        T = np.eye(4)
+        T[:3, :3] = Rot.from_rotvec(rng.normal(size=3)).as_matrix()
+        T[:3, 3] = rng.normal(size=3) * 5
+        return T
+    S0, S1 = 2, 3
+    meta0 = [SubmapMeta(time=100.25 + 30 * i, pose_gravity_aligned=rand_T(), pose_flu=rand_T(), pose_index=10 * i) for i in range(S0)]
+    meta1 = [SubmapMeta(time=120.5 + 30 * j, pose_gravity_aligned=rand_T(), pose_flu=rand_T(), pose_index=7 * j + 1) for j in range(S1)]
+    T = np.stack([np.stack([rand_T() for _ in range(S1)]) for _ in range(S0)])
+    n = np.array([[5.0, 3.0, np.nan], [4.0, 9.0, 0.0]])
+    res = SubmapPairResults(T_ij_hat_mat=T, clipper_num_associations=n, clipper_percent_associations=n / 10,
+                            associated_objs_mat=[[None] * S1 for _ in range(S0)], status_mat=np.zeros((S0, S1), dtype=np.int32))
+    lcs = loop_closures(res, meta0, meta1, lc_association_thresh=4)
+    assert [(c["i"], c["j"]) for c in lcs] == [(0, 0), (1, 0), (1, 1)]
+    c = lcs[2]
+    expect = np.linalg.inv(meta0[1].pose_flu) @ meta0[1].pose_gravity_aligned @ T[1, 1] @ np.linalg.inv(meta1[1].pose_gravity_aligned) @ meta1[1].pose_flu
+    assert np.allclose(c["T_pi_pj"], expect)
+    assert np.allclose(Rot.from_quat(c["q"]).as_matrix(), expect[:3, :3]) and np.allclose(c["t"], expect[:3, 3])
+    # single-robot runs drop pairs that are close in time: (0,0) 20.25 s, (1,0) 9.75 s, (1,1) 20.25 s apart
+    assert loop_closures(res, meta0, meta1, single_robot_lc=True, single_robot_lc_time_thresh=25.0) == []
+    assert [(c["i"], c["j"]) for c in loop_closures(res, meta0, meta1, single_robot_lc=True, single_robot_lc_time_thresh=15.0)] == [(0, 0), (1, 1)]
+    g2o, js = tmp_path / "align.g2o", tmp_path / "align.json"
+    write_g2o(str(g2o), lcs)
+    write_lc_json(str(js), lcs, robot_names=["sparkal1", "sparkal2"])
+    lines = g2o.read_text().split("\n")
+    assert lines[0] == "# LC: 5" and lines[2] == "# LC: 4" and lines[6] == ""
+    head, tpart, qpart, *info = lines[1].split("\t")
+    assert head == "EDGE_SE3:QUAT a0 b1 "
+    assert np.allclose([float(x) for x in tpart.split()], lcs[0]["t"]) and np.allclose([float(x) for x in qpart.split()], lcs[0]["q"])
+    assert [len(x.split()) for x in info[:6]] == [6, 5, 4, 3, 2, 1]
+    assert float(info[0].split()[0]) == 1 / 0.5 ** 2 and abs(float(info[5].split()[0]) - 1 / np.deg2rad(0.5) ** 2) < 1e-6
+    rec = json.loads(js.read_text())
+    assert len(rec) == 3 and rec[0]["rotation_convention"] == "xyzw" and rec[0]["names"] == ["sparkal1", "sparkal2"]
+    assert rec[0]["seconds"] == [100, 120] and rec[0]["nanoseconds"] == [250000000, 500000000]
