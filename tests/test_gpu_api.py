@@ -332,3 +332,22 @@ def test_all_pairs_single_robot_common_ids_removed(engine):
     back1 = np.array([k for k, o in enumerate(sub0[0]) if o.id != 4])
     back2 = np.array([k for k, o in enumerate(sub1[0]) if o.id != 4])
     assert np.array_equal(np.stack([back1[direct[:, 0]], back2[direct[:, 1]]], axis=1), a)
+
+
+def test_register_pairs_distributed_single_rank(engine):
+    """roman_b200.dist with world size 1 (no process group): same records as register_batch, in pair order."""
+    from roman_b200 import dist as rd
+    from roman_b200.align import SubmapAlignParams
+    reg = SubmapAlignParams(method="roman", semantics_dim=16).get_object_registration()
+    pairs, u0s = [], []
+    for s in range(5):
+        p = synth.make_pair(80 + s, 12 + s, 15, method="roman", semantics_dim=16, desc_common=1.0)
+        pairs.append((_objects(p.D1, "roman", 16), _objects(p.D2, "roman", 16)))
+        u0s.append(p.u0)
+    out = rd.register_pairs_distributed(reg, pairs, u0s, max_k=32)
+    assoc, T, status = reg.register_batch(pairs, u0s)
+    assert out["status"].tolist() == status.tolist()
+    assert out["n_inliers"].tolist() == [len(a) for a in assoc]
+    for g in range(5):
+        assert np.array_equal(out["inliers"][g], assoc[g])
+        assert np.array_equal(out["T"][g], T[g], equal_nan=True)
