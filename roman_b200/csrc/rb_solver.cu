@@ -28,6 +28,14 @@
 //     is resolved on the device from block-wide reductions with a fixed tree.
 //   - M x and C x of the accepted iterate are kept, so the d update and the new gradient need
 //     no extra pass (the reference recomputes them; the values are identical).
+//   - tile-skip format (rb_set_tile_skip): only tiles flagged as holding a non-zero are fetched
+//     (per-warp tile lists built once per problem), and a problem whose edges fit shared memory is
+//     solved "resident": a CSR over both directions is built in the space of the TMA rings — from
+//     the edge list K1 wrote, or from one pass over the stored tiles — and every pass is a CSR
+//     product out of shared memory, with u and g resident too.
+//   - misc[] slots: 0 queue index, 1 NONZERO count, 2 candidate counter, 4..12 tiles per warp +
+//     live tile-rows, 14 triple counter, 15 resident vote; red[] slots: 0..31 reductions, 40 k-th
+//     value, 48..51 scan scratch.
 #include <cooperative_groups.h>
 
 #include "rb_kernels.cuh"
@@ -699,6 +707,19 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
     }
 
     t_build += clock64() - tb0;
+
+    // one fused (M x, C x) evaluation for the vector currently in S.x, incl. the cluster-wide combine
+    // (the cycle counters feed rb_debug_solver_cycles)
+    auto run_pass = [&]() {
+      const long long t0 = clock64();
+      matvec_pass(S, tiles, nb, phase, C, crank, compact);
+      const long long t1 = clock64();
+      ++passes;
+      cluster_combine(S, mp, C, crank);
+      t_mv += t1 - t0;
+      t_cb += clock64() - t1;
+    };
+
     // ---- init (clipper.cpp:263-269): u = M u0 + u0 (optional), u /= ||u||
     for (int i = tid; i < mp; i += NT) {
       S.x[i] = (i < m) ? u0[i] : 0.0;
@@ -707,9 +728,7 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
     }
     __syncthreads();
     if (sp.rescale_u0) {
-      { long long t0 = clock64(); matvec_pass(S, tiles, nb, phase, C, crank, compact); long long t1 = clock64();
-        ++passes;
-        cluster_combine(S, mp, C, crank); t_mv += t1 - t0; t_cb += clock64() - t1; }
+      run_pass();
     }
     double nrm2 = 0.0;
     for (int i = tid; i < mp; i += NT) {
@@ -731,10 +750,7 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
       }
     }
     sum_u = R.sum1(sum_u);
-    { long long t0 = clock64(); matvec_pass(S, tiles, nb, phase, C, crank, compact);  // (M u, C u) of the normalised start vector
-      long long t1 = clock64();
-      ++passes;
-      cluster_combine(S, mp, C, crank); t_mv += t1 - t0; t_cb += clock64() - t1; }
+    run_pass();  // (M u, C u) of the normalised start vector
 
     // ---- initial d (clipper.cpp:271-280)
     double d = 0.0;
@@ -785,9 +801,7 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
             S.accC[i] = 0.0;
           }
           __syncthreads();
-          { long long t0 = clock64(); matvec_pass(S, tiles, nb, phase, C, crank, compact); long long t1 = clock64();
-            ++passes;
-            cluster_combine(S, mp, C, crank); t_mv += t1 - t0; t_cb += clock64() - t1; }
+          run_pass();
           // gradFnew, Fnew (clipper.cpp:309-315) and, speculatively, ||unew - u||^2
           double f = 0.0, dd = 0.0;
           for (int i = tid; i < m; i += NT) {
