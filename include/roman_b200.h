@@ -159,6 +159,17 @@ int rb_align_batch(rb_handle* h, const double* D1, const double* D2, const int32
                    const double* u0, int32_t* sel, int32_t* n_sel, double* T, int32_t* status,
                    double* score, int32_t* n_passes, void* stream);
 
+/* Submap-descriptor prefilter of the pair loop.  Replaces Submap.similarity (roman/map/map.py:145-162)
+ * as called per pair at roman/align/submap_align.py:131-134: sim[i * S1 + j] = max over (frame a of
+ * submap i in run 0, frame b of submap j in run 1) of cos(F0[a], F1[b]), a term being 0 when the
+ * product of the two norms is within 1e-9 of zero; NaN terms propagate like numpy's max.
+ * off0 (S0 + 1) / off1 (S1 + 1): device int64 row offsets of each submap's stacked frame
+ * descriptors in F0 / F1 (device, row-major, D doubles per row; a mean descriptor is one row).
+ * Every submap must have at least one row (numpy raises on an empty max).  sim: device S0 x S1. */
+int rb_submap_similarity(rb_handle* h, int32_t S0, int32_t S1, int32_t D, const int64_t* off0,
+                         const int64_t* off1, const double* F0, const double* F1, double* sim,
+                         void* stream);
+
 /* Replaces CLIPPER::getAffinityMatrix / getConstraintMatrix (clipper/src/clipper.cpp:202-216):
  * dense m x m row-major M + I and C + I of problem b into device buffers (either may be NULL). */
 int rb_get_dense(rb_handle* h, int32_t b, double* M_out, double* C_out, void* stream);

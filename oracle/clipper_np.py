@@ -331,3 +331,25 @@ def align_pair(ip: InvariantParams, sp: SolverParams, D1, D2, u0, A=None, dim: i
         T = T_align(np.asarray(D1)[sel[:, 0], :dim], np.asarray(D2)[sel[:, 1], :dim])
         status = 0
     return dict(M=M, single=single, A=A, sel=sel, T=T, status=status, **sol)
+
+
+# ---------------------------------------------------------------- pair-loop prefilters
+def submap_similarity(desc1: np.ndarray, desc2: np.ndarray) -> float:
+    """Submap.similarity (roman/map/map.py:145-162): max over frame pairs of the cosine of their
+    descriptors; a pair whose norm product is within 1e-9 of zero scores 0.  1-d inputs (mean
+    descriptors, :149-152) are the one-frame case of the same formula."""
+    d1 = np.atleast_2d(np.asarray(desc1, dtype=np.float64))
+    d2 = np.atleast_2d(np.asarray(desc2, dtype=np.float64))
+    dots = np.einsum("ad,bd->ab", d1, d2)
+    norm_prod = np.sqrt(np.einsum("ad,ad->a", d1, d1))[:, None] * np.sqrt(np.einsum("bd,bd->b", d2, d2))[None, :]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        sims = dots / norm_prod
+    sims[np.abs(norm_prod) <= 1e-9] = 0.0
+    return float(np.max(sims))
+
+
+def aabb_intersects(p1: np.ndarray, p2: np.ndarray) -> bool:
+    """roman/utils.py:160-169: do the axis-aligned bounding boxes of two point sets overlap (closed intervals)."""
+    lo1, hi1 = np.min(p1, axis=0), np.max(p1, axis=0)
+    lo2, hi2 = np.min(p2, axis=0), np.max(p2, axis=0)
+    return bool(np.all(lo1[:3] <= hi2[:3]) and np.all(hi1[:3] >= lo2[:3]))

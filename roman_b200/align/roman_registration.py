@@ -166,3 +166,35 @@ class ROMANRegistration(ObjectRegistration):
             T3[status != 0] = np.nan
             T = T3
         return assoc, T, status
+
+    def register_multistart(self, map1: List, map2: List, u0s: Sequence[np.ndarray]):
+        """
+        K solver restarts on ONE pair (CLIPPER is a local method and the reference
+        draws a single random start per pair, clipper/src/utils.cpp:22-29).  The K problems reference the
+        same two object tables (rb_plan_indexed) and run as one batch.  Returns a dict with the best-scoring
+        start's `associations` (k, 2), `T`, `status`, its index `best`, and the `scores` of all starts.
+        """
+        from ..engine import Engine, default_solver_params
+        K = len(u0s)
+        if K == 0 or len(map1) == 0 or len(map2) == 0:
+            raise ValueError("register_multistart needs at least one start vector and two non-empty maps")
+        D1, D2 = self.rows(map1), self.rows(map2)
+        n1, n2 = len(map1), len(map2)
+        if self._batch_engine is None:
+            self._batch_engine = Engine()
+        e = self._batch_engine
+        e.set_invariant_params(clipperpy.invariants.ROMAN(self.iparams)._rb_params())
+        e.set_solver_params(default_solver_params())
+        zeros = np.zeros(K, dtype=np.int64)
+        e.plan(D1.shape[1], [n1] * K, [n2] * K, obj1_offsets=zeros, obj2_offsets=zeros, total_obj1=n1, total_obj2=n2)
+        u0cat = np.concatenate([np.asarray(u, dtype=np.float64).reshape(-1) for u in u0s])
+        assert u0cat.size == K * n1 * n2
+        out = e.align_batch_host(np.ascontiguousarray(D1), np.ascontiguousarray(D2), u0cat)
+        best = int(np.argmax(out["score"]))
+        o = int(e.offsets[best])
+        T = out["T"][best].copy()
+        if out["status"][best] != 0:
+            T[:] = np.nan
+        return dict(associations=out["sel"][o:o + int(out["n_sel"][best])].copy(), T=T, status=int(out["status"][best]),
+                    best=best, scores=out["score"].copy())
+

@@ -9,8 +9,13 @@ uploaded once (rb_plan_indexed: problems reference row ranges of shared tables),
 pairs are registered in one launch sequence, and the post-filters of submap_align.py:166-184 run
 vectorised on the returned poses.
 
+The tests the reference makes before registering a pair — centre distance against `skip_distance`
+(:136) and the submap-descriptor similarity against `submap_descriptor_thresh` (:131-134, :144) — are
+evaluated for all pairs at once (roman_b200.align.prefilter; the similarity on the device) and
+produce the work list.
+
 Out of scope (other subsystems of the reference): loading ROMANMap pickles, cutting submaps,
-ground-truth pose handling, the result writers (roman/align/results.py).
+ground-truth pose handling.  Result writers: roman_b200.align.results.
 """
 from __future__ import annotations
 
@@ -19,6 +24,7 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
+from . import prefilter
 from .dist_reg_with_pruning import zyx_euler
 from .params import SubmapAlignParams
 from .roman_registration import ROMANRegistration
@@ -32,7 +38,10 @@ class SubmapPairResults:
     clipper_num_associations: np.ndarray     # (S0, S1) float64, NaN where the pair was not attempted
     clipper_percent_associations: np.ndarray # (S0, S1)
     associated_objs_mat: List[List[np.ndarray]]
-    status_mat: np.ndarray                   # (S0, S1) int32: -1 skipped, 0 ok, 1 insufficient, 2 gravity-rejected
+    status_mat: np.ndarray                   # (S0, S1) int32: -1 skipped, 0 ok, 1 insufficient, 2 gravity-rejected,
+                                             #   3 beyond skip_distance, 4 similarity below the threshold
+    similarity_mat: Optional[np.ndarray] = None  # (S0, S1) submap-descriptor similarity (None: no descriptor in use)
+    submap_distance_mat: Optional[np.ndarray] = None
     pairs: np.ndarray = field(default_factory=lambda: np.zeros((0, 2), dtype=np.int64))
 
 
@@ -56,13 +65,20 @@ def roll_pitch(T: np.ndarray):
 
 def align_submap_pairs(sm_params: SubmapAlignParams, submaps0: Sequence[List], submaps1: Sequence[List],
                        pair_mask: Optional[np.ndarray] = None, u0: Optional[dict] = None,
-                       exclude_common_ids: Optional[bool] = None, rank: int = 0, world: int = 1) -> SubmapPairResults:
+                       exclude_common_ids: Optional[bool] = None, rank: int = 0, world: int = 1,
+                       positions0=None, positions1=None, skip_distance: float = np.inf,
+                       descriptors0=None, descriptors1=None) -> SubmapPairResults:
     """
     Register every masked (i, j) pair of object lists.  `u0[(i, j)]` optionally fixes the solver's start
     vector of a pair (the reference draws it at random).  `exclude_common_ids` (default:
     sm_params.single_robot_lc) drops objects whose `id` occurs in both submaps of a pair before
     registering it (submap_align.py:108-115).  With world > 1 only the pairs g with g mod world == rank
     are computed (see roman_b200.dist for the all-gather of the records).
+
+    Prefilters (all optional): `positions0/1` (S, 3) submap centres + `skip_distance` reproduce the skip of
+    submap_align.py:136-142 (0 associations, NaN pose); `descriptors0/1` (per submap: (N, D) stacked frame
+    descriptors or a (D,) mean descriptor) with `sm_params.submap_descriptor` set reproduce the similarity
+    gate of :131-134, :144-149.  Both are evaluated for every pair before anything is registered.
     """
     from ..engine import Engine, default_solver_params
     from .. import clipperpy
@@ -76,6 +92,17 @@ def align_submap_pairs(sm_params: SubmapAlignParams, submaps0: Sequence[List], s
     S0, S1 = len(submaps0), len(submaps1)
     mask = np.ones((S0, S1), dtype=bool) if pair_mask is None else np.asarray(pair_mask, dtype=bool)
 
+    dist = sim = None
+    if positions0 is not None and positions1 is not None:
+        dist = prefilter.submap_distances(positions0, positions1)
+    if sm_params.submap_descriptor is not None:
+        if descriptors0 is None or descriptors1 is None:
+            raise ValueError("sm_params.submap_descriptor is set: descriptors0 / descriptors1 are required")
+        reg._batch_engine = reg._batch_engine or Engine()
+        sim = prefilter.submap_similarities(descriptors0, descriptors1, engine=reg._batch_engine)
+    too_far = (dist > skip_distance) if dist is not None else np.zeros((S0, S1), dtype=bool)
+    dissimilar = (sim < sm_params.submap_descriptor_thresh) if sim is not None else np.zeros((S0, S1), dtype=bool)
+
     D1, n1_all = reg.pack(submaps0)   # every submap packed once
     D2, n2_all = reg.pack(submaps1)
     off1 = np.concatenate([[0], np.cumsum(n1_all)]).astype(np.int64)
@@ -85,7 +112,12 @@ def align_submap_pairs(sm_params: SubmapAlignParams, submaps0: Sequence[List], s
         T_ij_hat_mat=np.full((S0, S1, 4, 4), np.nan), clipper_num_associations=np.full((S0, S1), np.nan),
         clipper_percent_associations=np.full((S0, S1), np.nan),
         associated_objs_mat=[[np.zeros((0, 2), dtype=np.int32) for _ in range(S1)] for _ in range(S0)],
-        status_mat=np.full((S0, S1), -1, dtype=np.int32))
+        status_mat=np.full((S0, S1), -1, dtype=np.int32), similarity_mat=sim, submap_distance_mat=dist)
+    for code, gate in ((3, mask & too_far), (4, mask & ~too_far & dissimilar)):   # attempted by the reference, not registered
+        res.status_mat[gate] = code
+        res.clipper_num_associations[gate] = 0
+        res.clipper_percent_associations[gate] = 0.0
+    mask = mask & ~too_far & ~dissimilar
 
     cand = [(i, j) for i in range(S0) for j in range(S1) if mask[i, j]]
     cand = cand[rank::world]

@@ -598,6 +598,18 @@ int rb_arun(rb_handle* h, const double* D1, const double* D2, const int32_t* sel
   return arun_range(h, 0, h->B, D1, D2, sel, n_sel, T, status, st);
 }
 
+int rb_submap_similarity(rb_handle* h, int32_t S0, int32_t S1, int32_t D, const int64_t* off0, const int64_t* off1,
+                         const double* F0, const double* F1, double* sim, void* stream) {
+  if (!h) return RB_ERR_ARG;
+  if (S0 < 0 || S1 < 0 || D < 1) return fail(h, RB_ERR_ARG, "rb_submap_similarity: bad sizes");
+  if (S0 > 65535) return fail(h, RB_ERR_TOO_LARGE, "rb_submap_similarity: more than 65535 submaps in run 0");
+  if (S0 == 0 || S1 == 0) return RB_OK;
+  if (!off0 || !off1 || !F0 || !F1 || !sim) return fail(h, RB_ERR_ARG, "rb_submap_similarity: null pointer");
+  cudaError_t e = rb_launch_similarity(S0, S1, D, off0, off1, F0, F1, sim, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(h, RB_ERR_CUDA, std::string("rb_submap_similarity: ") + cudaGetErrorString(e));
+  return RB_OK;
+}
+
 int rb_align_batch(rb_handle* h, const double* D1, const double* D2, const int32_t* A, const double* u0,
                    int32_t* sel, int32_t* n_sel, double* T, int32_t* status, double* score, int32_t* n_passes,
                    void* stream) {

@@ -233,6 +233,31 @@ class Engine:
                                        _ptr(out["n_passes"]), self._stream()))
         return out
 
+    def submap_similarity(self, frames0: Sequence, frames1: Sequence):
+        """(S0, S1) float64 device tensor: max pairwise cosine between the stacked frame descriptors of every
+        submap of run 0 and every submap of run 1 (rb_submap_similarity; reference roman/map/map.py:145-162).
+        frames0[i]: (N_i, D) or (D,) array-like."""
+        def table(frames):
+            rows = [np.atleast_2d(np.asarray(f, dtype=np.float64)) for f in frames]
+            if any(r.shape[0] == 0 for r in rows):
+                raise ValueError("submap without a descriptor (numpy raises on the empty max as well)")
+            off = np.concatenate([[0], np.cumsum([r.shape[0] for r in rows])]).astype(np.int64)
+            return (np.concatenate(rows) if rows else np.zeros((0, 1))), off
+        F0, off0 = table(frames0)
+        F1, off1 = table(frames1)
+        S0, S1 = len(off0) - 1, len(off1) - 1
+        sim = torch.empty((S0, S1), dtype=torch.float64, device=self.device)
+        if S0 == 0 or S1 == 0:
+            return sim
+        if F0.shape[1] != F1.shape[1]:
+            raise ValueError("descriptor lengths differ")
+        t = [self._dev(F0, torch.float64), self._dev(F1, torch.float64), self._dev(off0, torch.int64),
+             self._dev(off1, torch.int64)]
+        self._check(self._lib.rb_submap_similarity(self._h, S0, S1, int(F0.shape[1]), _ptr(t[2]), _ptr(t[3]),
+                                                   _ptr(t[0]), _ptr(t[1]), _ptr(sim), self._stream()))
+        self._keep_sim = t
+        return sim
+
     def arun(self, D1, D2, sel, n_sel):
         D1 = self._dev(D1, torch.float64)
         D2 = self._dev(D2, torch.float64)

@@ -1,0 +1,160 @@
+"""
+CPU tests against tests/golden/reference_py_vectors.json — outputs of the reference's own Python code
+(tests/golden/make_reference_py_golden.py imports it from /root/reference and runs it unmodified, with the
+C oracle standing in for the compiled clipperpy).  They pin (i) the host layer of this repository
+(parameter factory, feature packing, pruning mask, post-filter helpers) and (ii) the oracle's restatement
+of the Python-side numerics (Arun/SVD, submap similarity, bounding boxes) to the real thing.
+The GPU counterparts are in tests/test_gpu_reference_py.py.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import clipper_np as cn
+from roman_b200 import synth
+from roman_b200.align import DistRegWithPruning, ROMANRegistration, SubmapAlignParams
+from roman_b200.align import prefilter
+from roman_b200.align.objects import objects_from_rows
+from roman_b200.align.submap_align import rm_roll_pitch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import golden_inputs  # noqa: E402
+
+TUNED = dict(sigma=0.3, epsilon=0.5, mindist=0.1, epsilon_shape=0.2, cosine_min=0.6, cosine_max=0.9,
+             semantics_dim=64, gravity_unc_ang_rad=0.05)
+
+
+@pytest.fixture(scope="module")
+def gold():
+    with open(os.path.join(HERE, "golden", "reference_py_vectors.json")) as f:
+        return json.load(f)
+
+
+def test_factory_equals_reference_factory(gold):
+    """SubmapAlignParams.get_object_registration -> the invariant parameters the reference builds
+    (roman/params/submap_align_params.py:86-150 + roman/align/roman_registration.py:38-80)."""
+    assert len(gold["factory"]) == 22
+    for key, want in gold["factory"].items():
+        name, tag = key.split("/")
+        reg = SubmapAlignParams(method=name, **(TUNED if tag == "tuned" else {})).get_object_registration()
+        if want["cls"] == "DistRegWithPruning":
+            assert isinstance(reg, DistRegWithPruning)
+            for k in ("sigma", "epsilon", "mindist", "shape_epsilon", "cos_min", "use_gravity", "dim"):
+                assert getattr(reg, k) == want[k], (key, k)
+            assert float(reg.roll_pitch_thresh) == want["roll_pitch_thresh"]
+            continue
+        assert isinstance(reg, ROMANRegistration)
+        for k in ("dim", "volume", "extent", "pca", "semantics"):
+            assert getattr(reg, k) == want[k], (key, k)
+        for k, v in want["iparams"].items():
+            got = getattr(reg.iparams, k)
+            if k == "ratio_epsilon":
+                assert np.array_equal(np.asarray(got, dtype=np.float64), np.asarray(v, dtype=np.float64)), key
+            else:
+                assert got == v, (key, k, got, v)
+
+
+def test_feature_rows_equal_reference_packing(gold):
+    """_object_to_clipper_list / rows() / pack() against roman_registration.py:98-108."""
+    for case in gold["registration"]:
+        sem = case["semantics_dim"]
+        p = synth.make_pair(case["seed"], case["n1"], case["n2"], method=case["method"], semantics_dim=sem)
+        m1 = objects_from_rows(p.D1, case["method"], sem)
+        reg = SubmapAlignParams(method=case["method"], semantics_dim=sem).get_object_registration()
+        want = np.array(case["packed_rows"])
+        assert np.array_equal(np.array([reg._object_to_clipper_list(o) for o in m1[:2]]), want)
+        assert np.array_equal(reg.rows(m1)[:2], want)
+        table, counts = reg.pack([m1, m1[:3]])
+        assert counts.tolist() == [len(m1), 3] and np.array_equal(table[:2], want)
+
+
+def test_oracle_end_to_end_equals_reference_python_flow(gold, coracle):
+    """The oracle's one-call pair alignment == reference register() + T_align() (numpy LAPACK SVD)."""
+    for case in gold["registration"]:
+        sem = case["semantics_dim"]
+        p = synth.make_pair(case["seed"], case["n1"], case["n2"], method=case["method"], semantics_dim=sem)
+        reg = SubmapAlignParams(method=case["method"], semantics_dim=sem).get_object_registration()
+        ip = cn.InvariantParams(kind=0, **{k: getattr(reg.iparams, k) for k in (
+            "point_dim", "ratio_feature_dim", "cos_feature_dim", "sigma", "epsilon", "mindist", "cosine_min",
+            "cosine_max", "gravity_guided", "gravity_unc_ang_rad")})
+        ip.ratio_epsilon = np.asarray(reg.iparams.ratio_epsilon, dtype=np.float64)
+        u0 = np.random.default_rng(case["u0_seed"]).uniform(0.0, 1.0, case["n1"] * case["n2"])
+        for res in (coracle.align_pair(ip, cn.SolverParams(), p.D1, p.D2, u0),
+                    cn.align_pair(ip, cn.SolverParams(), p.D1, p.D2, u0)):
+            assert np.asarray(res["sel"]).tolist() == case["associations"], case["method"]
+            T = np.asarray(case["T"])
+            assert np.linalg.norm(np.asarray(res["T"]) - T) / np.linalg.norm(T) < 1e-10
+
+
+def test_oracle_arun_equals_reference_t_align(gold, coracle):
+    """orc_arun (Jacobi) and the numpy restatement against ObjectRegistration.T_align
+    (object_registration.py:88-129) incl. the reflection fix and rank-deficient inputs."""
+    seen = set()
+    for case in gold["t_align"]:
+        if case["dim"] != 3 or case["T"] is None:
+            continue
+        corr = np.asarray(case["correspondences"])
+        P1 = np.asarray(case["pts1"])[corr[:, 0]]
+        P2 = np.asarray(case["pts2"])[corr[:, 1]]
+        T = np.asarray(case["T"])
+        rc, Tc = coracle.arun(P1, P2)
+        assert rc == 0
+        for got in (Tc, cn.T_align(P1, P2)):
+            assert np.linalg.norm(got - T) / np.linalg.norm(T) < 1e-9, case["name"]
+        assert abs(np.linalg.det(T[:3, :3]) - 1.0) < 1e-9
+        seen.add(case["name"])
+    assert {"rigid_k3", "rigid_k40", "mirror_z", "coplanar"} <= seen
+
+
+def test_prune_mask_equals_reference_pruning(gold):
+    """DistRegWithPruning.putative_associations against the reference's two np.delete passes
+    (dist_reg_with_pruning.py:70-91), executed by the reference itself."""
+    for case in gold["clipper_prune"]:
+        p = synth.make_pair(case["seed"], case["n1"], case["n2"], method="roman", semantics_dim=case["semantics_dim"],
+                            desc_common=case["desc_common"])
+        m1 = objects_from_rows(p.D1, "roman", case["semantics_dim"])
+        m2 = objects_from_rows(p.D2, "roman", case["semantics_dim"])
+        reg = SubmapAlignParams(method="clipper+prune", semantics_dim=case["semantics_dim"],
+                                **case["params"]).get_object_registration()
+        A = reg.putative_associations(m1, m2)
+        assert A.tolist() == case["putative"]
+        assert 0 < len(A) < case["n1"] * case["n2"]
+
+
+def test_yaw_only_projection_equals_scipy_path(gold):
+    """rm_roll_pitch against roman.utils.transform_rm_roll_pitch (scipy as_euler('ZYX')[0] -> Rz)."""
+    for case in gold["helpers"]["rm_roll_pitch"]:
+        got = rm_roll_pitch(np.asarray(case["T"]))
+        assert np.allclose(got, np.asarray(case["out"]), rtol=0, atol=1e-12)
+
+
+def test_similarity_and_aabb_restatements(gold):
+    sims = gold["helpers"]["similarity"]
+    n_seeded = len(golden_inputs.SIMILARITY_SHAPES)
+    for case in sims[:n_seeded]:
+        d1, d2 = golden_inputs.similarity_inputs(case["case"])
+        assert abs(cn.submap_similarity(d1, d2) - case["similarity"]) < 1e-12
+    for case in sims[n_seeded:]:   # 1-d (mean) descriptors, one of them all-zero
+        assert abs(cn.submap_similarity(case["desc1"], case["desc2"]) - case["similarity"]) < 1e-12
+    assert sims[-1]["similarity"] == 0.0
+    hits = 0
+    for case in gold["helpers"]["aabb"]:
+        p1, p2 = np.asarray(case["p1"]), np.asarray(case["p2"])
+        assert cn.aabb_intersects(p1, p2) == case["intersects"]
+        assert bool(prefilter.aabb_overlap([p1], [p2])[0, 0]) == case["intersects"]
+        hits += case["intersects"]
+    assert 0 < hits < len(gold["helpers"]["aabb"])
+
+
+def test_candidate_mask_follows_the_reference_gates():
+    sp = SubmapAlignParams(submap_descriptor="stacked_frame_descriptors", submap_descriptor_thresh=0.8)
+    dist = np.array([[1.0, 50.0], [5.0, 5.0]])
+    sim = np.array([[0.9, 0.9], [0.79, 0.8]])
+    mask = prefilter.candidate_mask(sp, 2, 2, dist=dist, skip_distance=20.0, similarity=sim)
+    assert mask.tolist() == [[True, False], [False, True]]       # `>` and `<` are strict in the reference
+    assert prefilter.candidate_mask(SubmapAlignParams(), 2, 2, dist=dist, similarity=sim).all()
+    assert prefilter.nearby_mask(sp, dist).tolist() == [[True, False], [True, True]]   # < 2 * submap_radius
