@@ -16,10 +16,15 @@ Reference lines followed (paths relative to /root/reference; clipper/ = dependen
   k_largest              clipper/src/utils.cpp:33-55
   T_align                roman/align/object_registration.py:88-129
   rm_roll_pitch          roman/utils.py:128-130; upside-down gate roman/align/submap_align.py:167-170
+  submap_similarity      roman/map/map.py:145-162
+  aabb_intersects        roman/utils.py:160-169
 
 Parity pin status: identical to clipper_oracle.c — pinned by the reference KATs for the
-Euclidean affinity build and the end-to-end solve; PARITY UNPINNED for the ROMAN invariant,
-solver iterates, top-k tie order and T_align (no golden vector exists in the reference).
+Euclidean affinity build and the end-to-end solve; T_align, submap_similarity and aabb_intersects
+are pinned by outputs of the reference's own Python functions (tests/golden/reference_py_vectors.json,
+made by tests/golden/make_reference_py_golden.py); PARITY UNPINNED for the ROMAN invariant, the
+solver iterates and the top-k tie order (C++ code that cannot be built here; no golden vector
+exists in the reference).
 """
 from __future__ import annotations
 

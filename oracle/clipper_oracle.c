@@ -28,10 +28,13 @@
  * Parity pin status (see DESIGN.md "Oracle"): the Euclidean affinity build and the
  * end-to-end solve are pinned by the reference's own known-answer tests
  * (clipper/test/affinity_test.cpp:94-107, clipper/test/clipper_test.cpp:62-66,
- * committed as tests/golden/ JSON files).  The ROMAN invariant, the solver iterates for a
- * fixed u0, the top-k tie order and T_align have NO golden vector anywhere in the
- * reference: for those, PARITY IS UNPINNED and this restatement (cross-checked against
- * the independent numpy restatement oracle/clipper_np.py) is the sole pin.
+ * committed as tests/golden/ JSON files).  orc_arun is pinned by outputs of the reference's
+ * own ObjectRegistration.T_align, executed from /root/reference by
+ * tests/golden/make_reference_py_golden.py (tests/golden/reference_py_vectors.json).  The
+ * ROMAN invariant, the solver iterates for a fixed u0 and the top-k tie order have NO golden
+ * vector anywhere in the reference and their C++ cannot be built here: for those, PARITY IS
+ * UNPINNED and this restatement (cross-checked against the independent numpy restatement
+ * oracle/clipper_np.py) is the sole pin.
  *
  * Compile: gcc -O3 -march=native -fopenmp -ffp-contract=off -shared -fPIC (oracle/Makefile).
  * -ffp-contract=off keeps a*b+c as two roundings so the arithmetic is well defined.

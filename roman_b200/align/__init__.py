@@ -8,6 +8,7 @@ Host-side mirror of the reference's roman.align registration interface for the C
   dist_reg_with_pruning.py <- roman/align/dist_reg_with_pruning.py
   params.py                <- roman/params/submap_align_params.py (registration-related part)
   submap_align.py          <- the pair loop of roman/align/submap_align.py:93-200, batched (all pairs in one launch)
+  prefilter.py             <- the tests made before a pair is registered (submap_align.py:96-149; map.py:145-162)
   results.py               <- the loop-closure writers of roman/align/results.py:149-197 (align.g2o, align.json)
 """
 from .object_registration import InsufficientAssociationsException, ObjectRegistration  # noqa: F401
