@@ -42,6 +42,7 @@ class SubmapPairResults:
                                              #   3 beyond skip_distance, 4 similarity below the threshold
     similarity_mat: Optional[np.ndarray] = None  # (S0, S1) submap-descriptor similarity (None: no descriptor in use)
     submap_distance_mat: Optional[np.ndarray] = None
+    robots_nearby_mat: Optional[np.ndarray] = None  # centre distance where the submaps are "nearby" (:101-103), else NaN
     pairs: np.ndarray = field(default_factory=lambda: np.zeros((0, 2), dtype=np.int64))
 
 
@@ -69,8 +70,9 @@ def align_submap_pairs(sm_params: SubmapAlignParams, submaps0: Sequence[List], s
                        positions0=None, positions1=None, skip_distance: float = np.inf,
                        descriptors0=None, descriptors1=None) -> SubmapPairResults:
     """
-    Register every masked (i, j) pair of object lists.  `u0[(i, j)]` optionally fixes the solver's start
-    vector of a pair (the reference draws it at random).  `exclude_common_ids` (default:
+    Register every masked (i, j) pair of object lists.  `u0` optionally fixes the solver's start vectors (the
+    reference draws them at random): a dict {(i, j): vector} or a callable (i, j, m) -> vector, called once per
+    registered pair in the reference's loop order (i outer, j inner).  `exclude_common_ids` (default:
     sm_params.single_robot_lc) drops objects whose `id` occurs in both submaps of a pair before
     registering it (submap_align.py:108-115).  With world > 1 only the pairs g with g mod world == rank
     are computed (see roman_b200.dist for the all-gather of the records).
@@ -113,6 +115,8 @@ def align_submap_pairs(sm_params: SubmapAlignParams, submaps0: Sequence[List], s
         clipper_percent_associations=np.full((S0, S1), np.nan),
         associated_objs_mat=[[np.zeros((0, 2), dtype=np.int32) for _ in range(S1)] for _ in range(S0)],
         status_mat=np.full((S0, S1), -1, dtype=np.int32), similarity_mat=sim, submap_distance_mat=dist)
+    if dist is not None and not sm_params.force_fill_submaps and sm_params.submap_radius is not None:
+        res.robots_nearby_mat = np.where(prefilter.nearby_mask(sm_params, dist), dist, np.nan)
     for code, gate in ((3, mask & too_far), (4, mask & ~too_far & dissimilar)):   # attempted by the reference, not registered
         res.status_mat[gate] = code
         res.clipper_num_associations[gate] = 0
@@ -136,7 +140,7 @@ def align_submap_pairs(sm_params: SubmapAlignParams, submaps0: Sequence[List], s
             res.status_mat[i, j] = 1
             continue
         pairs.append((i, j))
-        kept[(i, j)] = (len(k1), len(k2))
+        kept[(i, j)] = (k1, k2)
         if exclude_common_ids:  # all-to-all over the kept objects, as an explicit association list
             A_list.append(np.stack([np.repeat(k1, len(k2)), np.tile(k2, len(k1))], axis=1).astype(np.int32))
     res.pairs = np.array(pairs, dtype=np.int64).reshape(-1, 2)
@@ -152,9 +156,17 @@ def align_submap_pairs(sm_params: SubmapAlignParams, submaps0: Sequence[List], s
              total_obj1=int(off1[-1]), total_obj2=int(off2[-1]))
     msz = np.diff(eng.offsets)
     rng = np.random.default_rng()
-    u0cat = np.concatenate([np.asarray(u0[(int(i), int(j))], dtype=np.float64).reshape(-1)
-                            if (u0 is not None and (int(i), int(j)) in u0) else rng.uniform(0.0, 1.0, int(msz[b]))
-                            for b, (i, j) in enumerate(pairs)])
+    def start_vector(b, i, j):
+        if callable(u0):
+            v = u0(i, j, int(msz[b]))
+        elif u0 is not None and (i, j) in u0:
+            v = u0[(i, j)]
+        else:
+            return rng.uniform(0.0, 1.0, int(msz[b]))
+        v = np.asarray(v, dtype=np.float64).reshape(-1)
+        assert v.size == msz[b], f"start vector of pair ({i}, {j}) must have {msz[b]} entries"
+        return v
+    u0cat = np.concatenate([start_vector(b, int(i), int(j)) for b, (i, j) in enumerate(pairs)])
     A_cat = np.ascontiguousarray(np.concatenate(A_list)) if exclude_common_ids else None
     out = eng.align_batch_host(np.ascontiguousarray(D1), np.ascontiguousarray(D2), u0cat, A=A_cat)
 
@@ -174,10 +186,14 @@ def align_submap_pairs(sm_params: SubmapAlignParams, submaps0: Sequence[List], s
     for b, (i, j) in enumerate(pairs):
         o = int(eng.offsets[b])
         a = out["sel"][o:o + int(n_sel[b])].copy() if ok[b] else np.zeros((0, 2), dtype=np.int32)
+        k1, k2 = kept[(i, j)]
+        if exclude_common_ids and len(a):   # the reference indexes the submaps AFTER the common-id removal
+            a[:, 0] = np.searchsorted(k1, a[:, 0])
+            a[:, 1] = np.searchsorted(k2, a[:, 1])
         res.associated_objs_mat[i][j] = a
         res.T_ij_hat_mat[i, j] = T[b]
         res.clipper_num_associations[i, j] = len(a)
-        mean_len = 0.5 * (kept[(i, j)][0] + kept[(i, j)][1])  # lengths after the common-id removal
+        mean_len = 0.5 * (len(k1) + len(k2))  # lengths after the common-id removal
         res.clipper_percent_associations[i, j] = len(a) / mean_len if mean_len > 0 else 0.0
         res.status_mat[i, j] = status[b]
     return res

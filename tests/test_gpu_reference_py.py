@@ -157,3 +157,51 @@ def test_multistart_equals_best_of_independent_solves(engine, coracle):
     ip = cn.InvariantParams(kind=0, sigma=0.4, epsilon=0.6, mindist=0.2, gravity_guided=True, gravity_unc_ang_rad=0.0872665)
     want = [coracle.align_pair(ip, cn.SolverParams(), p.D1, p.D2, u)["score"] for u in u0s]
     assert np.abs(ms["scores"] - np.array(want)).max() < 1e-9 and ms["best"] == int(np.argmax(want))
+
+
+@pytest.mark.parametrize("name", golden_inputs.PAIR_LOOP_SCENARIOS)
+def test_pair_loop_equals_reference_submap_align(engine, gold, name):
+    """align_submap_pairs against the result matrices of the reference's own submap_align() pair loop
+    (roman/align/submap_align.py:93-200) run on the same submaps with the same start vectors."""
+    want = next(c for c in gold["pair_loop"] if c["name"] == name)
+    sc = golden_inputs.pair_loop_scenario(name)
+    runs = []
+    for run in sc["runs"]:
+        subs = []
+        for sm in run:
+            objs = objects_from_rows(sm["rows"], sc["method"], sc["sem"])
+            for o, sid in zip(objs, sm["ids"]):
+                o.id = sid
+            subs.append(objs)
+        runs.append(subs)
+    pos = [np.array([sm["pose_flu"][:3, 3] for sm in run]) for run in sc["runs"]]
+    desc = [[sm["descriptor"] for sm in run] for run in sc["runs"]]
+    has_desc = desc[0][0] is not None
+    rng = np.random.default_rng(want["u0_seed"])
+    sizes = []
+
+    def u0(i, j, m):
+        sizes.append(m)
+        return rng.uniform(0.0, 1.0, m)
+    res = align_submap_pairs(SubmapAlignParams(**sc["sm_kwargs"]), runs[0], runs[1], u0=u0, positions0=pos[0],
+                             positions1=pos[1], skip_distance=sc["skip_distance"],
+                             descriptors0=desc[0] if has_desc else None, descriptors1=desc[1] if has_desc else None)
+    assert sizes == want["u0_sizes"]                       # same pairs reach the solver, in the same order
+    assert res.clipper_num_associations.tolist() == want["clipper_num_associations"]
+    if want["similarity_mat"] is not None:
+        assert np.abs(res.similarity_mat - np.asarray(want["similarity_mat"])).max() < 1e-12
+    for row_got, row_want in zip(res.robots_nearby_mat, want["robots_nearby_mat"]):
+        for g, w in zip(row_got, row_want):
+            assert (np.isnan(g) and w is None) or abs(g - w) < 1e-12
+    S0, S1 = res.status_mat.shape
+    n_pose = 0
+    for i in range(S0):
+        for j in range(S1):
+            assert res.associated_objs_mat[i][j].tolist() == want["associated_objs_mat"][i][j], (i, j)
+            Tw = want["T_ij_hat_mat"][i][j]
+            if Tw is None:
+                assert np.isnan(res.T_ij_hat_mat[i, j]).all(), (i, j)
+            else:
+                assert rel(res.T_ij_hat_mat[i, j], Tw) < 1e-9, (i, j)
+                n_pose += 1
+    assert n_pose >= 1

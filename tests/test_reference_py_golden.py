@@ -158,3 +158,34 @@ def test_candidate_mask_follows_the_reference_gates():
     assert mask.tolist() == [[True, False], [False, True]]       # `>` and `<` are strict in the reference
     assert prefilter.candidate_mask(SubmapAlignParams(), 2, 2, dist=dist, similarity=sim).all()
     assert prefilter.nearby_mask(sp, dist).tolist() == [[True, False], [True, True]]   # < 2 * submap_radius
+
+
+def test_wire_formats_equal_reference_writer(gold, tmp_path):
+    """align.g2o / align.json byte-for-byte against the reference's save_submap_align_results
+    (roman/align/results.py:149-197) run on the same result matrices."""
+    from roman_b200.align.results import SubmapMeta, loop_closures, write_g2o, write_lc_json
+    from roman_b200.align.submap_align import SubmapPairResults
+    w = gold["wire_formats"]
+    n = np.asarray(w["n_assoc"])
+    S0, S1 = n.shape
+    meta = []
+    for run in range(2):
+        traj = np.asarray(w["traj_times"][run])
+        meta.append([SubmapMeta(time=t, pose_gravity_aligned=np.asarray(w["pose_gravity_aligned"][run][k]),
+                                pose_flu=np.asarray(w["pose_flu"][run][k]), pose_index=int(np.argmin(np.abs(traj - t))))
+                     for k, t in enumerate(w["times"][run])])
+    res = SubmapPairResults(T_ij_hat_mat=np.asarray(w["T_hat"]), clipper_num_associations=n,
+                            clipper_percent_associations=n / 10, associated_objs_mat=[[None] * S1 for _ in range(S0)],
+                            status_mat=np.zeros((S0, S1), dtype=np.int32))
+    edges = []
+    for out in w["outputs"]:
+        lcs = loop_closures(res, meta[0], meta[1], lc_association_thresh=out["lc_association_thresh"],
+                            single_robot_lc=out["single_robot_lc"],
+                            single_robot_lc_time_thresh=out["single_robot_lc_time_thresh"])
+        g2o, js = tmp_path / "a.g2o", tmp_path / "a.json"
+        write_g2o(str(g2o), lcs, g2o_t_std=out["g2o_t_std"], g2o_r_std=out["g2o_r_std"])
+        write_lc_json(str(js), lcs, robot_names=out["robot_names"])
+        assert g2o.read_text() == out["g2o"]
+        assert js.read_text() == out["json"]
+        edges.append(len(lcs))
+    assert edges == [7, 2]
