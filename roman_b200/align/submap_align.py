@@ -40,7 +40,8 @@ class SubmapPairResults:
     associated_objs_mat: List[List[np.ndarray]]
     status_mat: np.ndarray                   # (S0, S1) int32: -1 skipped, 0 ok, 1 insufficient, 2 gravity-rejected,
                                              #   3 beyond skip_distance, 4 similarity below the threshold
-    similarity_mat: Optional[np.ndarray] = None  # (S0, S1) submap-descriptor similarity (None: no descriptor in use)
+    similarity_mat: Optional[np.ndarray] = None  # (S0, S1) submap-descriptor similarity (None: no descriptor in use;
+                                                 #   NaN beyond skip_distance, as in the reference)
     submap_distance_mat: Optional[np.ndarray] = None
     robots_nearby_mat: Optional[np.ndarray] = None  # centre distance where the submaps are "nearby" (:101-103), else NaN
     pairs: np.ndarray = field(default_factory=lambda: np.zeros((0, 2), dtype=np.int64))
@@ -114,7 +115,8 @@ def align_submap_pairs(sm_params: SubmapAlignParams, submaps0: Sequence[List], s
         T_ij_hat_mat=np.full((S0, S1, 4, 4), np.nan), clipper_num_associations=np.full((S0, S1), np.nan),
         clipper_percent_associations=np.full((S0, S1), np.nan),
         associated_objs_mat=[[np.zeros((0, 2), dtype=np.int32) for _ in range(S1)] for _ in range(S0)],
-        status_mat=np.full((S0, S1), -1, dtype=np.int32), similarity_mat=sim, submap_distance_mat=dist)
+        status_mat=np.full((S0, S1), -1, dtype=np.int32), submap_distance_mat=dist,
+        similarity_mat=None if sim is None else np.where(too_far, np.nan, sim))   # :136-142 `continue`s before :196
     if dist is not None and not sm_params.force_fill_submaps and sm_params.submap_radius is not None:
         res.robots_nearby_mat = np.where(prefilter.nearby_mask(sm_params, dist), dist, np.nan)
     for code, gate in ((3, mask & too_far), (4, mask & ~too_far & dissimilar)):   # attempted by the reference, not registered
