@@ -244,3 +244,35 @@ def test_loop_closure_wire_formats(tmp_path):
     rec = json.loads(js.read_text())
     assert len(rec) == 3 and rec[0]["rotation_convention"] == "xyzw" and rec[0]["names"] == ["sparkal1", "sparkal2"]
     assert rec[0]["seconds"] == [100, 120] and rec[0]["nanoseconds"] == [250000000, 500000000]
+
+
+def test_shim_covers_every_clipperpy_use_of_the_reference():
+    """tests/golden/clipperpy_surface.json is an AST scan of the reference's Python sources for every use of the
+    compiled `clipperpy` module; roman_b200.clipperpy must offer each of them (zero-change drop-in)."""
+    import inspect
+    import json
+    from roman_b200 import clipperpy
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "clipperpy_surface.json")) as f:
+        surf = json.load(f)
+    assert len(surf["chains"]) >= 11 and len(surf["methods"]) >= 8
+    for chain in surf["chains"]:
+        obj = clipperpy
+        for part in chain.split(".")[1:]:
+            assert hasattr(obj, part), f"roman_b200.clipperpy lacks {chain}"
+            obj = getattr(obj, part)
+    for cls in (clipperpy.CLIPPER, clipperpy.CLIPPERPairwiseAndSingle):
+        for m in surf["methods"]:
+            if m == "score_pairwise_and_single_consistency" and cls is clipperpy.CLIPPER:
+                continue
+            assert callable(getattr(cls, m, None)), f"{cls.__name__}.{m} missing"
+    rp = clipperpy.invariants.ROMANParams()
+    for a in surf["params"]:
+        assert hasattr(rp, a), f"ROMANParams.{a} missing"
+    ep = clipperpy.invariants.EuclideanDistanceParams()
+    assert all(hasattr(ep, a) for a in ("sigma", "epsilon", "mindist"))
+    sol = clipperpy.Solution() if not inspect.signature(clipperpy.Solution).parameters else None
+    fields = getattr(clipperpy.Solution, "__dataclass_fields__", None) or (vars(sol) if sol is not None else {})
+    for a in surf["solution"]:
+        assert a in fields or hasattr(clipperpy.Solution, a), f"Solution.{a} missing"
+    # solve() takes the start vector as an optional argument, like the binding (py_clipper.cpp:289-297)
+    assert "u0" in inspect.signature(clipperpy.CLIPPER.solve).parameters
