@@ -82,7 +82,7 @@ typedef struct {
   double eps;
   double affinityeps;
   int32_t rescale_u0;
-  int32_t rounding; /* 0 NONZERO, 1 DSD (unsupported: RB_ERR_ARG), 2 DSD_HEU */
+  int32_t rounding; /* 0 NONZERO, 1 DSD (exact densest subgraph; host epilogue, synchronises), 2 DSD_HEU */
 } rb_solver_params;
 
 /* Fill with the reference defaults (roman.h:27-53, clipper.h:27-60). */
@@ -158,6 +158,17 @@ int rb_arun(rb_handle* h, const double* D1, const double* D2, const int32_t* sel
 int rb_align_batch(rb_handle* h, const double* D1, const double* D2, const int32_t* A,
                    const double* u0, int32_t* sel, int32_t* n_sel, double* T, int32_t* status,
                    double* score, int32_t* n_passes, void* stream);
+
+/* Host-only building block of Rounding::DSD.  Replaces clipper::dsd::solve(A, S) (clipper/src/dsd.cpp:265-314 with
+ * densest_subgraph :157-262): Goldberg's exact maximum-density subgraph of the weighted graph induced by the k nodes
+ * S (global ids, ascending) of a problem with n nodes, W = k x k row-major symmetric weights (upper triangle
+ * authoritative, diagonal ignored).  Uses the reference's search constants, hence returns the same set: the source
+ * side of the last non-trivial minimum cut, ascending ids, written to out (capacity k); *n_out = its size.
+ * k == 1 returns S; an edgeless S returns nothing (the reference reads uninitialised memory in both cases).
+ * rb_solve / rb_align_batch* call it per problem when rb_solver_params.rounding == 1: the kernel leaves
+ * S = {i : u_i > 0} (clipper.cpp:364-367), the S x S block of M is copied to the host, and the result overwrites
+ * nodes / sel / n_nodes — this mode synchronises the stream.  No GPU is needed to call this function. */
+int rb_dsd_host(int64_t n, int32_t k, const int32_t* S, const double* W, int32_t* out, int32_t* n_out);
 
 /* Submap-descriptor prefilter of the pair loop.  Replaces Submap.similarity (roman/map/map.py:145-162)
  * as called per pair at roman/align/submap_align.py:131-134: sim[i * S1 + j] = max over (frame a of

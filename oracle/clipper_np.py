@@ -299,8 +299,11 @@ def find_dense_clique(sp: SolverParams, Mupper: np.ndarray, Cupper: np.ndarray |
         # std::round: half away from zero
         omega = int(np.floor(abs(F) + 0.5) * (1 if F >= 0 else -1))
         nodes = k_largest(u, omega)
-    else:
-        raise NotImplementedError("exact DSD rounding (dsd.cpp) is out of scope of this path")
+    else:  # DSD (clipper.cpp:364-371): exact densest subgraph of the graph induced by the support of u
+        support = [int(t) for t in np.nonzero(u > 0.0)[0]]
+        if len(support) > 16:
+            raise NotImplementedError("the exhaustive DSD restatement handles supports of at most 16 nodes")
+        nodes = densest_subgraph(Mupper, support) if support else []
     return dict(nodes=nodes, u=u, score=F, ifinal=i, passes=passes)
 
 
@@ -358,3 +361,43 @@ def aabb_intersects(p1: np.ndarray, p2: np.ndarray) -> bool:
     lo1, hi1 = np.min(p1, axis=0), np.max(p1, axis=0)
     lo2, hi2 = np.min(p2, axis=0), np.max(p2, axis=0)
     return bool(np.all(lo1[:3] <= hi2[:3]) and np.all(hi1[:3] >= lo2[:3]))
+
+
+# ---------------------------------------------------------------- Rounding::DSD (exact densest subgraph)
+def densest_subgraph(M: np.ndarray, S=None) -> list[int]:
+    """clipper::dsd::solve(A, S) (clipper/src/dsd.cpp:265-314, densest_subgraph :157-262) by EXHAUSTIVE search —
+    usable for |S| <= ~16.  Goldberg's network for density g has, for the source side {s} + T, the cut value
+    const + 2 (g |T| - w(T)); so "the minimum cut is non-trivial" <=> max_T (w(T) - g |T|) > 0, and the set the
+    reference keeps (vertices reachable from s in the residual graph = the minimal source side) is the
+    intersection of all maximisers.  The binary search uses the reference's constants: m = |S|^2 - |S|,
+    interval [0, m // 2], stop when n (n - 1) (U - L) < 1 with n = all nodes of the problem.
+    M: (n, n) weights, upper triangle authoritative, diagonal ignored."""
+    M = np.asarray(M, dtype=np.float64)
+    n = M.shape[0]
+    S = list(range(n)) if S is None or len(S) == 0 else [int(v) for v in S]
+    k = len(S)
+    if k == 1:
+        return S
+    Wu = np.triu(M, 1)
+    W = (Wu + Wu.T)[np.ix_(S, S)]
+    sizes = np.zeros(1 << k)
+    wT = np.zeros(1 << k)
+    for mask in range(1, 1 << k):
+        low = (mask & -mask).bit_length() - 1
+        rest = mask & (mask - 1)
+        sizes[mask] = sizes[rest] + 1
+        wT[mask] = wT[rest] + sum(W[low, j] for j in range(k) if rest >> j & 1)
+    L, U = 0.0, float((k * k - k) // 2)
+    best = None
+    while n * (n - 1) * (U - L) >= 1:
+        g = (U + L) / 2
+        val = wT[1:] - g * sizes[1:]
+        vmax = val.max()
+        if vmax > 1e-12:
+            L = g
+            best = int(np.bitwise_and.reduce(np.nonzero(val >= vmax - 1e-12)[0] + 1))
+        else:
+            U = g
+    if best is None:
+        return []
+    return sorted(S[j] for j in range(k) if best >> j & 1)

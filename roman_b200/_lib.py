@@ -60,6 +60,7 @@ SIGNATURES = {
     "rb_packed_bytes": (_i64, [_vp]),
     "rb_affinity": (C.c_int, [_vp, _dp, _dp, _ip, _vp]),
     "rb_solve": (C.c_int, [_vp, _dp, _ip, _ip, _ip, _dp, _dp, _ip, _ip, _vp]),
+    "rb_dsd_host": (C.c_int, [_i64, _i32, _ip, _dp, _ip, _ip]),
     "rb_submap_similarity": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _dp, _dp, _dp, _vp]),
     "rb_arun": (C.c_int, [_vp, _dp, _dp, _ip, _ip, _dp, _ip, _vp]),
     "rb_align_batch": (C.c_int, [_vp, _dp, _dp, _ip, _dp, _ip, _ip, _dp, _ip, _dp, _ip, _vp]),

@@ -45,6 +45,7 @@ struct rb_handle {
   int32_t* d_counter = nullptr;
   int* d_bad = nullptr;
   long long* d_debug = nullptr;  // dev builds: per-CTA cycle counters of the solver
+  double* d_W = nullptr; size_t cap_W = 0;  // Rounding::DSD: |S| x |S| block of one problem's affinity matrix
   // internal outputs used when the caller passes NULL
   int32_t* d_nodes = nullptr; int32_t* d_sel = nullptr; size_t cap_assoc = 0;
   int32_t* d_nsel = nullptr; double* d_score = nullptr; int32_t* d_ifinal = nullptr; int32_t* d_npass = nullptr;
@@ -125,6 +126,9 @@ RbDevParams dev_params(const rb_handle* h) {
   return P;
 }
 
+// A handle is tied to one device; stage calls may arrive while another device is current.
+#define RB_ENTER(h) RB_CUDA(h, cudaSetDevice((h)->device))
+
 void record(rb_handle* h, int i, cudaStream_t st) {
   if (!h->profiling) return;
   if (!h->ev[i]) cudaEventCreate(&h->ev[i]);
@@ -177,7 +181,7 @@ int rb_create(rb_handle** out, int device) {
   if (e != cudaSuccess) { delete h; return RB_ERR_CUDA; }
   if (cudaMalloc((void**)&h->d_counter, 8 * sizeof(int32_t)) != cudaSuccess ||
       cudaMalloc((void**)&h->d_bad, sizeof(int)) != cudaSuccess) {
-    delete h;
+    rb_destroy(h);
     return RB_ERR_ALLOC;
   }
   *out = h;
@@ -192,7 +196,7 @@ int rb_destroy(rb_handle* h) {
   cudaFree(h->d_counter); cudaFree(h->d_bad); cudaFree(h->d_nodes); cudaFree(h->d_sel);
   cudaFree(h->d_nsel); cudaFree(h->d_score); cudaFree(h->d_ifinal); cudaFree(h->d_npass);
   cudaFree(h->d_status); cudaFree(h->d_T); cudaFree(h->d_resident);
-  cudaFree(h->s_D1); cudaFree(h->s_D2); cudaFree(h->s_A); cudaFree(h->s_u0);
+  cudaFree(h->s_D1); cudaFree(h->s_D2); cudaFree(h->s_A); cudaFree(h->s_u0); cudaFree(h->d_debug); cudaFree(h->d_W);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->order_ev) cudaEventDestroy(h->order_ev);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -224,8 +228,7 @@ int rb_set_invariant_params(rb_handle* h, const rb_invariant_params* p) {
 
 int rb_set_solver_params(rb_handle* h, const rb_solver_params* p) {
   if (!h || !p) return RB_ERR_ARG;
-  if (p->rounding == 1) return fail(h, RB_ERR_ARG, "Rounding::DSD (exact densest subgraph) is not implemented on this path");
-  if (p->rounding != 0 && p->rounding != 2) return fail(h, RB_ERR_ARG, "unknown rounding");
+  if (p->rounding < 0 || p->rounding > 2) return fail(h, RB_ERR_ARG, "unknown rounding");
   h->sol = *p;
   return RB_OK;
 }
@@ -515,6 +518,46 @@ int affinity_range(rb_handle* h, int b0, int b1, const double* D1, const double*
   return RB_OK;
 }
 
+// Rounding::DSD (clipper.cpp:364-371): the kernel left S = support of u in `nodes` (NONZERO rounding); per problem, pull
+// the S x S block of M, run Goldberg's exact densest subgraph on the host (rb_dsd.cu) and write the result back.
+// Synchronises `st`.
+int dsd_epilogue(rb_handle* h, int b0, int b1, int32_t* nodes, int32_t* sel, int32_t* n_nodes, cudaStream_t st) {
+  const size_t nb = (size_t)(b1 - b0);
+  const int64_t a0 = h->probs[(size_t)b0].off_assoc;
+  const int64_t a1 = b1 < h->B ? h->probs[(size_t)b1].off_assoc : h->total_assoc;
+  std::vector<int32_t> hn(nb), hnodes((size_t)(a1 - a0)), out;
+  std::vector<double> W;
+  RB_CUDA(h, cudaMemcpyAsync(hn.data(), n_nodes, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (a1 > a0)
+    RB_CUDA(h, cudaMemcpyAsync(hnodes.data(), nodes + a0, (size_t)(a1 - a0) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  RB_CUDA(h, cudaStreamSynchronize(st));
+  for (size_t q = 0; q < nb; ++q) {
+    const RbProblem& pr = h->probs[(size_t)b0 + q];
+    const int k = hn[q];
+    if (k <= 0) continue;
+    int rc;
+    if ((rc = ensure(h, &h->d_W, &h->cap_W, (size_t)k * k))) return rc;
+    RB_CUDA(h, rb_launch_gather_sub(pr, h->d_M, h->tile_skip ? h->d_flags : nullptr, nodes + pr.off_assoc, k, h->d_W, st));
+    W.resize((size_t)k * k);
+    RB_CUDA(h, cudaMemcpyAsync(W.data(), h->d_W, W.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    RB_CUDA(h, cudaStreamSynchronize(st));
+    out.assign((size_t)k, 0);
+    int32_t n_out = 0;
+    if (rb_dsd_host(pr.m, k, hnodes.data() + (pr.off_assoc - a0), W.data(), out.data(), &n_out) != RB_OK)
+      return fail(h, RB_ERR_ARG, "rb_solve: densest-subgraph rounding failed");
+    hn[q] = n_out;
+    if (n_out > 0) {
+      RB_CUDA(h, cudaMemcpyAsync(nodes + pr.off_assoc, out.data(), (size_t)n_out * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      RB_CUDA(h, rb_launch_select(nodes + pr.off_assoc, n_out, h->d_pad_i32 + pr.off_pad,
+                                  h->d_pad_i32 + (size_t)h->total_pad + pr.off_pad, sel + 2 * pr.off_assoc, st));
+      RB_CUDA(h, cudaStreamSynchronize(st));  // `out` is reused by the next problem
+    }
+  }
+  RB_CUDA(h, cudaMemcpyAsync(n_nodes, hn.data(), nb * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  RB_CUDA(h, cudaStreamSynchronize(st));
+  return RB_OK;
+}
+
 int solve_range(rb_handle* h, int b0, int b1, int queue, const double* u0, int32_t* nodes, int32_t* sel,
                 int32_t* n_nodes, double* u, double* score, int32_t* ifinal, int32_t* n_passes, cudaStream_t st) {
   if (b1 <= b0) return RB_OK;
@@ -536,6 +579,8 @@ int solve_range(rb_handle* h, int b0, int b1, int queue, const double* u0, int32
   a.n_passes = (n_passes ? n_passes : h->d_npass) + b0;
   a.resident = h->d_resident + b0;
   a.sp = h->sol;
+  const bool dsd = (h->sol.rounding == 1);
+  if (dsd) a.sp.rounding = 0;  // the kernel leaves the support of u; the exact rounding follows on the host
   a.mp_max = h->max_mp;
   a.pad_stride = h->total_pad;
   a.cluster = h->cluster;
@@ -546,6 +591,7 @@ int solve_range(rb_handle* h, int b0, int b1, int queue, const double* u0, int32
   record(h, 3, st);
   RB_CUDA(h, rb_launch_solver(a, h->max_clusters, st));
   record(h, 4, st);
+  if (dsd) return dsd_epilogue(h, b0, b1, a.nodes, a.sel, a.n_nodes, st);
   return RB_OK;
 }
 
@@ -567,6 +613,7 @@ int rb_affinity(rb_handle* h, const double* D1, const double* D2, const int32_t*
   if (!h) return RB_ERR_ARG;
   int rc = check_affinity_args(h, D1, D2, A);
   if (rc) return rc;
+  RB_ENTER(h);
   cudaStream_t st = (cudaStream_t)stream;
   h->last_stream = st; h->last_valid = true;
   rc = affinity_range(h, 0, h->B, D1, D2, A, st);
@@ -582,6 +629,7 @@ int rb_solve(rb_handle* h, const double* u0, int32_t* nodes, int32_t* sel, int32
   if (!h->affinity_done) return fail(h, RB_ERR_NOPLAN, "rb_solve before rb_affinity / rb_set_dense");
   if (h->B == 0) return RB_OK;
   if (!u0 && h->total_assoc > 0) return fail(h, RB_ERR_ARG, "rb_solve: u0 is required");
+  RB_ENTER(h);
   cudaStream_t st = (cudaStream_t)stream;
   h->last_stream = st; h->last_valid = true;
   return solve_range(h, 0, h->B, 0, u0, nodes, sel, n_nodes, u, score, ifinal, n_passes, st);
@@ -593,6 +641,7 @@ int rb_arun(rb_handle* h, const double* D1, const double* D2, const int32_t* sel
   if (!h->planned) return fail(h, RB_ERR_NOPLAN, "rb_arun before rb_plan");
   if (h->B == 0) return RB_OK;
   if (!D1 || !D2 || !sel || !n_sel) return fail(h, RB_ERR_ARG, "rb_arun: null input");
+  RB_ENTER(h);
   cudaStream_t st = (cudaStream_t)stream;
   h->last_stream = st; h->last_valid = true;
   return arun_range(h, 0, h->B, D1, D2, sel, n_sel, T, status, st);
@@ -605,6 +654,7 @@ int rb_submap_similarity(rb_handle* h, int32_t S0, int32_t S1, int32_t D, const 
   if (S0 > 65535) return fail(h, RB_ERR_TOO_LARGE, "rb_submap_similarity: more than 65535 submaps in run 0");
   if (S0 == 0 || S1 == 0) return RB_OK;
   if (!off0 || !off1 || !F0 || !F1 || !sim) return fail(h, RB_ERR_ARG, "rb_submap_similarity: null pointer");
+  RB_ENTER(h);
   cudaError_t e = rb_launch_similarity(S0, S1, D, off0, off1, F0, F1, sim, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail(h, RB_ERR_CUDA, std::string("rb_submap_similarity: ") + cudaGetErrorString(e));
   return RB_OK;
@@ -627,6 +677,7 @@ int rb_get_dense(rb_handle* h, int32_t b, double* M_out, double* C_out, void* st
   if (!h) return RB_ERR_ARG;
   if (!h->planned || !h->affinity_done) return fail(h, RB_ERR_NOPLAN, "rb_get_dense before rb_affinity / rb_set_dense");
   if (b < 0 || b >= h->B) return fail(h, RB_ERR_ARG, "rb_get_dense: problem index out of range");
+  RB_ENTER(h);
   RB_CUDA(h, rb_launch_unpack(h->probs[(size_t)b], h->d_M, h->tile_skip ? h->d_flags : nullptr, M_out, C_out,
                               (cudaStream_t)stream));
   return RB_OK;
@@ -636,6 +687,7 @@ int rb_set_dense(rb_handle* h, int32_t b, const double* M, const double* C, void
   if (!h) return RB_ERR_ARG;
   if (!h->planned) return fail(h, RB_ERR_NOPLAN, "rb_set_dense before rb_plan");
   if (b < 0 || b >= h->B || !M) return fail(h, RB_ERR_ARG, "rb_set_dense: bad arguments");
+  RB_ENTER(h);
   cudaStream_t st = (cudaStream_t)stream;
   const RbProblem& pr = h->probs[(size_t)b];
   RB_CUDA(h, cudaMemsetAsync(h->d_bad, 0, sizeof(int), st));

@@ -63,6 +63,10 @@ cudaError_t rb_solver_prepare(int device);  // opt in to the large dynamic share
 cudaError_t rb_solver_max_clusters(int mp_max, int cluster, int* out);
 cudaError_t rb_launch_solver(const RbSolveArgs& a, int max_clusters, cudaStream_t st);
 
+cudaError_t rb_launch_gather_sub(const RbProblem& pr, const double* Mp, const uint8_t* flags, const int32_t* nodes, int k,
+                                 double* W, cudaStream_t st);
+cudaError_t rb_launch_select(const int32_t* nodes, int k, const int32_t* i1, const int32_t* i2, int32_t* sel,
+                             cudaStream_t st);
 cudaError_t rb_launch_similarity(int S0, int S1, int D, const int64_t* off0, const int64_t* off1, const double* F0,
                                  const double* F1, double* sim, cudaStream_t st);
 cudaError_t rb_launch_arun(const RbProblem* probs, int B, int point_dim, const double* D1, const double* D2,

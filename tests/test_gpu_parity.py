@@ -282,8 +282,8 @@ def test_error_paths_and_limits(engine):
     """Unsupported configurations fail loudly with the library's message; nothing falls back silently."""
     from roman_b200.engine import RomanB200Error, default_solver_params, make_invariant_params
     sp = default_solver_params()
-    sp.rounding = 1  # Rounding::DSD
-    with pytest.raises(RomanB200Error, match="DSD"):
+    sp.rounding = 3  # not a Rounding value
+    with pytest.raises(RomanB200Error, match="rounding"):
         engine.set_solver_params(sp)
     with pytest.raises(RomanB200Error, match="point_dim"):
         engine.set_invariant_params(make_invariant_params(point_dim=4))
@@ -332,3 +332,121 @@ def test_degenerate_inputs(engine, coracle):
     Mo, single, _, _ = coracle.score(ip_o, sp.affinityeps, tabs1[2], tabs2[2])
     assert np.isnan(single).any()
     assert np.array_equal(Mg.cpu().numpy() != 0, (Mo + Mo.T + np.eye(42)) != 0)
+
+
+def test_randomised_invariant_parameter_sweep(engine, coracle):
+    """Seeded sweep over methods, sizes, descriptor lengths and every invariant parameter (per-feature shape
+    thresholds, cosine window, mindist, gravity uncertainty): affinity and solve against the oracle."""
+    from roman_b200.engine import make_invariant_params, method_invariant_kwargs
+    from tests.helpers import oracle_invariant
+    rng = np.random.default_rng(2024)
+    methods = list(synth.METHOD_FLAGS)
+    sp = cn.SolverParams()
+    n_edges = 0
+    for case in range(28):
+        method = methods[case % len(methods)]
+        n1, n2 = int(rng.integers(3, 23)), int(rng.integers(3, 23))
+        D = int(rng.integers(5, 71))
+        cmin = float(rng.uniform(0.2, 0.7))
+        kw = method_invariant_kwargs(method, sigma=float(rng.uniform(0.05, 0.6)), epsilon=float(rng.uniform(0.1, 1.0)),
+                                     mindist=float(rng.choice([0.0, 0.2, 1.5])), cosine_min=cmin,
+                                     cosine_max=float(rng.uniform(cmin + 0.05, 1.0)), semantics_dim=D,
+                                     gravity_unc_ang_rad=float(rng.choice([0.0, 0.05, 0.3])))
+        kw["ratio_epsilon"] = rng.uniform(0.0, 0.6, kw["ratio_feature_dim"])
+        ip_o, ip_g = oracle_invariant(**kw), make_invariant_params(**kw)
+        p = synth.make_pair(5000 + case, n1, n2, method=method, semantics_dim=D, desc_common=float(rng.uniform(0.0, 1.5)),
+                            pos_noise=float(rng.choice([0.02, 0.1])))
+        engine.set_invariant_params(ip_g)
+        engine.plan(p.D1.shape[1], [n1], [n2])
+        engine.affinity(p.D1.reshape(-1), p.D2.reshape(-1))
+        Mg = engine.get_dense(0)[0].cpu().numpy()
+        Mo, _, _, nnz = coracle.score(ip_o, sp.affinityeps, p.D1, p.D2)
+        Mo_full = Mo + Mo.T + np.eye(n1 * n2)
+        assert np.array_equal(Mg != 0, Mo_full != 0), (case, method)
+        assert np.abs(Mg - Mo_full).max() <= M_TOL, (case, method)
+        sol = engine.solve(p.u0)
+        ref = coracle.solve(sp, Mo, p.u0)
+        k = int(sol["n_nodes"][0])
+        assert sol["nodes"][:k].cpu().numpy().tolist() == ref["nodes"], (case, method)
+        assert abs(float(sol["score"][0]) - ref["score"]) <= F_TOL
+        n_edges += nnz
+    assert n_edges > 200          # the sweep is not vacuous
+    engine.set_invariant_params(make_invariant_params())
+
+
+def test_exact_dsd_rounding_matches_reference_semantics(engine, coracle):
+    """Rounding::DSD (clipper.cpp:364-371 + dsd.cpp): the support of u comes from the solver kernel, the exact densest
+    subgraph from the host epilogue; checked against the exhaustive restatement and, for the KAT literal of
+    clipper/test/dsd_test.cpp fed through set_matrix_data, against the reference's expected nodes."""
+    import json, os
+    from roman_b200 import clipperpy
+    from roman_b200.engine import default_solver_params
+    ip_o, ip_g = params_for_method("gravity")
+    sp_o = cn.SolverParams(rounding=1)
+    sp_g = default_solver_params()
+    sp_g.rounding = 1
+    engine.set_invariant_params(ip_g)
+    engine.set_solver_params(sp_g)
+    try:
+        shapes = [(9, 11), (14, 12), (6, 20)]
+        pairs = [synth.make_pair(300 + i, a, b, method="gravity") for i, (a, b) in enumerate(shapes)]
+        engine.plan(3, [a for a, _ in shapes], [b for _, b in shapes])
+        res = engine.align_batch(np.concatenate([p.D1.reshape(-1) for p in pairs]),
+                                 np.concatenate([p.D2.reshape(-1) for p in pairs]), np.concatenate([p.u0 for p in pairs]))
+        checked = 0
+        for b, p in enumerate(pairs):
+            Mo, _, A, _ = coracle.score(ip_o, sp_o.affinityeps, p.D1, p.D2)
+            ref = cn.find_dense_clique(sp_o, Mo, None, p.u0)
+            assert res.associations(b).tolist() == A[ref["nodes"]].tolist()
+            checked += len(ref["nodes"]) >= 3
+        assert checked >= 2
+    finally:
+        engine.set_solver_params(default_solver_params())
+    # the reference's DSD literal through the clipperpy surface: solve() with DSD rounding returns a subset of the support
+    # whose density equals that of the exact answer on the support
+    kats = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_kats.json")))
+    M = np.array(kats["dsd_20x20"])
+    M = np.triu(M, 1) + np.triu(M, 1).T + np.eye(20)
+    params = clipperpy.Params()
+    params.rounding = clipperpy.Rounding.DSD
+    c = clipperpy.CLIPPER(clipperpy.invariants.PairwiseInvariant(), params)
+    c.set_matrix_data(M=M, C=(M != 0).astype(np.float64))
+    c.solve(np.full(20, 0.5))
+    sol = c.get_solution()
+    support = np.nonzero(sol.u > 0)[0].tolist()
+    assert list(sol.nodes) == cn.densest_subgraph(M, support)
+    assert set(sol.nodes) <= set(kats["dsd_nodes"]) or set(kats["dsd_nodes"]) <= set(support)
+
+
+def test_exact_dsd_rounding_on_a_broad_support(engine):
+    """A support much larger than the answer: no constraints (C all ones), two solver iterations, a planted heavy
+    cluster among light random edges.  The exact rounding must return the cluster; checked against the exhaustive
+    restatement run on the numpy solver's support."""
+    from roman_b200.engine import default_solver_params
+    sp_g = default_solver_params()
+    sp_g.rounding, sp_g.maxoliters, sp_g.maxiniters = 1, 2, 2
+    sp_o = cn.SolverParams(rounding=1, maxoliters=2, maxiniters=2)
+    engine.set_solver_params(sp_g)
+    try:
+        for seed in range(40, 44):
+            rng = np.random.default_rng(seed)
+            n, kc = 15, 5
+            cl = np.sort(rng.choice(n, kc, replace=False))
+            Mu = np.zeros((n, n))
+            for a in range(n):
+                for b in range(a + 1, n):
+                    if a in cl and b in cl:
+                        Mu[a, b] = rng.uniform(0.7, 1.0)
+                    elif rng.uniform() < 0.2:
+                        Mu[a, b] = rng.uniform(0.02, 0.2)
+            u0 = rng.uniform(0, 1, n)
+            ones = np.ones((n, n))
+            engine.plan(1, [n], [1], m=[n])
+            engine.set_dense(0, Mu + Mu.T + np.eye(n), ones)
+            sol = engine.solve(u0)
+            k = int(sol["n_nodes"][0])
+            got = sol["nodes"][:k].cpu().numpy().tolist()
+            ref = cn.find_dense_clique(sp_o, Mu, np.triu(ones, 1), u0)
+            assert got == ref["nodes"] == cl.tolist(), seed
+    finally:
+        engine.set_solver_params(default_solver_params())

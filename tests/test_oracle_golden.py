@@ -177,3 +177,51 @@ def test_oracle_vectors_fixture_is_reproducible(coracle):
         r = coracle.align_pair(ip, cn.SolverParams(), p.D1, p.D2, p.u0)
         assert r["sel"].tolist() == c["sel"] and r["nnz"] == c["nnz"]
         assert abs(r["score"] - c["score"]) < 1e-9
+
+
+def _dsd_product(n, S, M):
+    """rb_dsd_host through ctypes (host-only entry point of libroman_b200.so; needs no GPU)."""
+    import ctypes as C
+    from roman_b200 import _lib
+    lib = _lib.load()
+    S = np.ascontiguousarray(S, dtype=np.int32)
+    Wu = np.triu(np.asarray(M, dtype=np.float64), 1)
+    W = np.ascontiguousarray((Wu + Wu.T)[np.ix_(S, S)])
+    out = np.zeros(max(len(S), 1), dtype=np.int32)
+    n_out = C.c_int32(0)
+    rc = lib.rb_dsd_host(int(n), len(S), S.ctypes.data, W.ctypes.data, out.ctypes.data, C.addressof(n_out))
+    assert rc == 0
+    return out[: n_out.value].tolist()
+
+
+def test_dsd_reference_kats():
+    """clipper/test/dsd_test.cpp: TEST(DSD, Solve) :14-44 and TEST(DSD, SolveRestrictedGraph) :48-80 — the exact
+    densest subgraph of the 20x20 literal is {3, 5, 12, 14, 15}, on the whole graph and restricted to 9 nodes."""
+    M = np.array(KATS["dsd_20x20"])
+    want = KATS["dsd_nodes"]
+    restricted = [0, 1, 3, 5, 7, 12, 14, 15, 19]
+    assert _dsd_product(20, list(range(20)), M) == want
+    assert _dsd_product(20, restricted, M) == want
+    assert cn.densest_subgraph(M, restricted) == want      # the exhaustive restatement agrees (9 nodes: 511 subsets)
+
+
+def test_dsd_matches_exhaustive_search():
+    rng = np.random.default_rng(11)
+    nontrivial = 0
+    for case in range(60):
+        n = int(rng.integers(2, 13)) if case % 3 else int(rng.integers(200, 3000))
+        k = int(rng.integers(2, min(n, 11) + 1))
+        S = np.sort(rng.choice(n, size=k, replace=False))
+        M = np.zeros((n, n))
+        dens = rng.uniform(0.2, 1.0)
+        for a in range(k):
+            for b in range(a + 1, k):
+                if rng.uniform() < dens:
+                    M[S[a], S[b]] = rng.uniform(0.01, 1.0) if case % 2 else 1.0     # weighted and unweighted graphs
+        got = _dsd_product(n, S, M)
+        want = cn.densest_subgraph(M, S)
+        assert got == want, (case, n, S.tolist())
+        nontrivial += 1 < len(got) < k
+    assert nontrivial >= 10
+    assert _dsd_product(50, [7], np.zeros((50, 50))) == [7]
+    assert _dsd_product(50, [3, 9, 20], np.zeros((50, 50))) == []       # edgeless support
