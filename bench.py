@@ -217,9 +217,11 @@ def run_b200(args):
 
     eng = Engine(local)
     eng.set_invariant_params(make_invariant_params(**method_invariant_kwargs(METHOD, semantics_dim=SEM_DIM)))
+    if args.promote >= 0:
+        eng.set_solver_promote(args.promote)
     eng.plan(d_row, [N1] * B, [N2] * B)
     # problems are partitioned round-robin over ranks: global pair g = b*world + rank
-    D1h, D2h, u0h = make_inputs(1000 + rank * B, B)
+    D1h, D2h, u0h = make_inputs(1000 + (rank + args.rank_offset) * B, B)
     pin = lambda a: torch.from_numpy(a).pin_memory()
     D1p, D2p, u0p = pin(D1h.reshape(-1)), pin(D2h.reshape(-1)), pin(u0h.reshape(-1))
     D1d, D2d, u0d = D1p.to(dev), D2p.to(dev), u0p.to(dev)
@@ -292,6 +294,8 @@ def run_b200(args):
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * K / (ms * 1e-3)
     passes = res.n_passes.cpu().numpy().astype(np.int64)
+    streamed = eng.solver_streamed_passes().cpu().numpy().astype(np.int64)   # passes that read M from HBM
+    promoted = int((eng.solver_resident().cpu().numpy()[:B] == 3).sum())
     cluster_dense = eng.solver_cluster
     e2e_value, out_h = e2e_run()
     h2d = (D1p.numel() + D2p.numel() + u0p.numel()) * 8
@@ -319,7 +323,9 @@ def run_b200(args):
         # algorithmic bytes, dense format (SURVEY 8d with the packed-upper layout, s = 8): K1 writes and K2 reads per
         # pass s*m(m-1)/2; K1 also reads both feature tables and writes the single scores
         tri = 8.0 * m * (m - 1) / 2
-        k2_bytes = float(passes.sum()) * (tri + 24.0 * m)
+        # K2: only passes that stream the matrix count (a problem still iterating after 8 streamed passes is extracted
+        # into shared memory — rb_set_solver_promote — and its remaining passes move no HBM bytes)
+        k2_bytes = float(streamed.sum()) * (tri + 24.0 * m)
         k1_bytes = B * tri + in_bytes
         k1_ms = stage["prep"] + stage["affinity"]
         n_tiles = (m // 32 + (m % 32 > 0)) * (m // 32 + (m % 32 > 0) + 1) // 2
@@ -333,7 +339,9 @@ def run_b200(args):
             "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "parallelism": f"round-robin pairs over {world} GPU(s)",
                        "l2": f"inputs larger than L2: packed affinity working set {eng.packed_bytes / 1e9:.2f} GB per GPU per step",
                        "layout": "packed upper triangle, 32x32 fp64 tiles, dense format (every tile written by K1 and streamed by K2 each pass)",
-                       "mean_passes": float(passes.mean()), "solver_cluster": int(cluster_dense)},
+                       "mean_passes": float(passes.mean()), "max_passes": int(passes.max()),
+                       "mean_streamed_passes": float(streamed.mean()), "promoted_problems": promoted,
+                       "promote_after_streamed_passes": 8, "solver_cluster": int(cluster_dense)},
             "roofline": {"kernel": "rb_solver_kernel (K2)", "bound": "hbm", "achieved": gbs(k2_bytes, stage["solve"]),
                          "peak": peak, "unit": "GB/s", "frac": gbs(k2_bytes, stage["solve"]) / peak, "traffic": traffic,
                          "peak_source": which, "algorithmic_bytes_per_launch": k2_bytes, "ms_per_launch": stage["solve"]},
@@ -385,6 +393,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=592, help="submap pairs per GPU per step (4 x 148 SMs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--rank-offset", type=int, default=0,
+                    help="dev: shift the synthetic seeds by this many ranks (run another rank's batch on this GPU)")
+    ap.add_argument("--promote", type=int, default=-1, help="dev: rb_set_solver_promote value (-1 = library default)")
     ap.add_argument("--format", default="both", choices=["both", "dense"],
                     help="both: also time the opt-in sparse fast path (fast_path block); dense: default format only")
     args = ap.parse_args()

@@ -210,6 +210,19 @@ int rb_set_tile_skip(rb_handle* h, int32_t on);
  * list K1 wrote (no tile read at all). */
 int rb_solver_resident(rb_handle* h, int32_t* out, void* stream);
 
+/* Dense format only — late residency.  A problem that is still iterating after `passes` streamed passes of K2 reads its
+ * tiles once more to extract the non-zero words into a shared-memory CSR and runs every later pass from there (if
+ * they fit; otherwise it keeps streaming).  Slow-converging problems — tens of passes where a batch averages ~5 —
+ * would otherwise pin a cluster to tens of full streams of a matrix holding a few hundred edges.  Default 8;
+ * 0 = never.  rb_solver_resident reports 3 for promoted problems.  Results agree with the unpromoted solve to
+ * rounding (summation order), like the two storage formats do. */
+int rb_set_solver_promote(rb_handle* h, int32_t passes);
+
+/* After rb_solve: device int32[B] — how many passes of each problem read the packed matrix from HBM (every pass of a
+ * streamed problem; the passes before promotion plus the extraction pass of a promoted one; 1 or 0 for problems
+ * resident from the start).  n_passes of rb_solve counts ALL (M x, C x) evaluations regardless of where M came from. */
+int rb_solver_streamed_passes(rb_handle* h, int32_t* out, void* stream);
+
 /* Tile-skip format, after rb_affinity: edges (non-zero words of the strict upper triangle) K1 found per problem,
  * device int32[B]; a count above the list capacity (32 * ceil(m/32)) means the list overflowed and is not used. */
 int rb_edge_counts(rb_handle* h, int32_t* out, void* stream);

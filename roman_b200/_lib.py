@@ -73,6 +73,8 @@ SIGNATURES = {
     "rb_edge_counts": (C.c_int, [_vp, _ip, _vp]),
     "rb_stored_tiles": (C.c_int, [_vp, _ip, _vp]),
     "rb_solver_resident": (C.c_int, [_vp, _ip, _vp]),
+    "rb_solver_streamed_passes": (C.c_int, [_vp, _ip, _vp]),
+    "rb_set_solver_promote": (C.c_int, [_vp, _i32]),
     "rb_set_profiling": (C.c_int, [_vp, _i32]),
     "rb_get_stage_ms": (C.c_int, [_vp, _fp]),
     "rb_align_batch_host": (C.c_int, [_vp, _dp, _dp, _ip, _dp, _ip, _ip, _dp, _ip, _dp, _ip]),

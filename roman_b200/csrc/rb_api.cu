@@ -50,6 +50,8 @@ struct rb_handle {
   int32_t* d_nodes = nullptr; int32_t* d_sel = nullptr; size_t cap_assoc = 0;
   int32_t* d_nsel = nullptr; double* d_score = nullptr; int32_t* d_ifinal = nullptr; int32_t* d_npass = nullptr;
   int32_t* d_resident = nullptr;
+  int32_t* d_streamed = nullptr;
+  int32_t promote_after = 8;  // dense format: streamed passes before a still-iterating problem is made resident
   int32_t* d_status = nullptr; double* d_T = nullptr; size_t cap_B = 0;
   // staging for the host entry point
   double* s_D1 = nullptr; double* s_D2 = nullptr; size_t cap_sD1 = 0, cap_sD2 = 0;
@@ -195,7 +197,7 @@ int rb_destroy(rb_handle* h) {
   cudaFree(h->d_pad_i32); cudaFree(h->d_masks); cudaFree(h->d_edge_ij); cudaFree(h->d_edge_v); cudaFree(h->d_edge_cnt);
   cudaFree(h->d_counter); cudaFree(h->d_bad); cudaFree(h->d_nodes); cudaFree(h->d_sel);
   cudaFree(h->d_nsel); cudaFree(h->d_score); cudaFree(h->d_ifinal); cudaFree(h->d_npass);
-  cudaFree(h->d_status); cudaFree(h->d_T); cudaFree(h->d_resident);
+  cudaFree(h->d_status); cudaFree(h->d_T); cudaFree(h->d_resident); cudaFree(h->d_streamed);
   cudaFree(h->s_D1); cudaFree(h->s_D2); cudaFree(h->s_A); cudaFree(h->s_u0); cudaFree(h->d_debug); cudaFree(h->d_W);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->order_ev) cudaEventDestroy(h->order_ev);
@@ -282,6 +284,21 @@ int rb_solver_resident(rb_handle* h, int32_t* out, void* stream) {
   if (!h->planned) return fail(h, RB_ERR_NOPLAN, "rb_solver_resident before rb_plan");
   if (h->B > 0)
     RB_CUDA(h, cudaMemcpyAsync(out, h->d_resident, (size_t)h->B * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return RB_OK;
+}
+
+int rb_solver_streamed_passes(rb_handle* h, int32_t* out, void* stream) {
+  if (!h || !out) return RB_ERR_ARG;
+  if (!h->planned) return fail(h, RB_ERR_NOPLAN, "rb_solver_streamed_passes before rb_plan");
+  if (h->B > 0)
+    RB_CUDA(h, cudaMemcpyAsync(out, h->d_streamed, (size_t)h->B * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return RB_OK;
+}
+
+int rb_set_solver_promote(rb_handle* h, int32_t passes) {
+  if (!h) return RB_ERR_ARG;
+  if (passes < 0) return fail(h, RB_ERR_ARG, "rb_set_solver_promote: passes must be >= 0 (0 = never)");
+  h->promote_after = passes;
   return RB_OK;
 }
 
@@ -442,6 +459,7 @@ static int plan_impl(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, cons
   if ((size_t)B > h->cap_B || !h->d_nsel) {
     cudaFree(h->d_nsel); cudaFree(h->d_score); cudaFree(h->d_ifinal); cudaFree(h->d_npass); cudaFree(h->d_status); cudaFree(h->d_T);
     cudaFree(h->d_resident); h->d_resident = nullptr;
+    cudaFree(h->d_streamed); h->d_streamed = nullptr;
     h->d_nsel = h->d_ifinal = h->d_npass = h->d_status = nullptr; h->d_score = h->d_T = nullptr; h->cap_B = 0;
     const size_t n = B ? (size_t)B : 1;
     RB_CUDA(h, cudaMalloc((void**)&h->d_nsel, n * sizeof(int32_t)));
@@ -449,6 +467,7 @@ static int plan_impl(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, cons
     RB_CUDA(h, cudaMalloc((void**)&h->d_ifinal, n * sizeof(int32_t)));
     RB_CUDA(h, cudaMalloc((void**)&h->d_npass, n * sizeof(int32_t)));
     RB_CUDA(h, cudaMalloc((void**)&h->d_resident, n * sizeof(int32_t)));
+    RB_CUDA(h, cudaMalloc((void**)&h->d_streamed, n * sizeof(int32_t)));
     cudaFree(h->d_edge_cnt); h->d_edge_cnt = nullptr;
     RB_CUDA(h, cudaMalloc((void**)&h->d_edge_cnt, n * sizeof(int)));
     RB_CUDA(h, cudaMalloc((void**)&h->d_status, n * sizeof(int32_t)));
@@ -578,6 +597,8 @@ int solve_range(rb_handle* h, int b0, int b1, int queue, const double* u0, int32
   a.ifinal = (ifinal ? ifinal : h->d_ifinal) + b0;
   a.n_passes = (n_passes ? n_passes : h->d_npass) + b0;
   a.resident = h->d_resident + b0;
+  a.streamed = h->d_streamed + b0;
+  a.promote_after = h->tile_skip ? 0 : h->promote_after;
   a.sp = h->sol;
   const bool dsd = (h->sol.rounding == 1);
   if (dsd) a.sp.rounding = 0;  // the kernel leaves the support of u; the exact rounding follows on the host

@@ -38,7 +38,10 @@ struct RbSolveArgs {
   double* score;
   int32_t* ifinal;
   int32_t* n_passes;
-  int32_t* resident;       // per problem: 1 if the solve ran from the shared-memory CSR (tiles read once), else 0
+  int32_t* resident;       // per problem: 0 tiles streamed every pass; 1 / 2 resident from the start (tile-skip format);
+                           // 3 promoted: streamed `promote_after` passes, then extracted into the shared-memory CSR
+  int32_t* streamed;       // per problem: passes (incl. an extraction pass) that read the packed matrix from HBM
+  int promote_after;       // dense format: after this many streamed passes try to make the problem resident (0 = never)
   rb_solver_params sp;
   int32_t mp_max;          // max padded m over the batch (sizes the shared-memory vectors)
 };

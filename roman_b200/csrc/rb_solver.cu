@@ -399,6 +399,73 @@ __device__ __forceinline__ void build_tile_lists(const Smem& S, const uint8_t* _
   if (w == 0 && lane == 0) S.wcnt[NW] = nlive;
 }
 
+// Second half of the resident build: the staged triples (accM: values, accC: i << 16 | j; count in misc[14]) become a
+// CSR over both directions in the ring space.  Returns false (all threads agree) if they exceed the capacity.
+__device__ __forceinline__ bool finish_compact(const Smem& S, int mp) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, tid = threadIdx.x;
+  const double* tv = S.accM;
+  const unsigned* tij = reinterpret_cast<const unsigned*>(S.accC);
+  const int cap = S.c_cap;
+  const int n = S.misc[14];
+  if (n > cap) return false;
+
+  // CSR over directed entries: count, scan, fill, sort rows by column
+  int* rowptr = S.c_rowptr;                       // [mp + 1]
+  int* cursor = S.c_rowptr + (mp + 1);            // [mp]
+  for (int i = tid; i <= mp; i += NT) rowptr[i] = 0;
+  for (int i = tid; i < mp; i += NT) cursor[i] = 0;
+  __syncthreads();
+  for (int e = tid; e < n; e += NT) {
+    const unsigned ij = tij[e];
+    atomicAdd(&rowptr[(ij >> 16) + 1], 1);
+    atomicAdd(&rowptr[(ij & 0xffffu) + 1], 1);
+  }
+  __syncthreads();
+  {  // inclusive scan of rowptr[1..mp]: each thread owns a contiguous run; warp scan of the run totals; warp offsets
+    const int per = (mp + NT - 1) / NT;
+    const int lo = 1 + tid * per, hi = (lo + per <= mp + 1) ? lo + per : mp + 1;
+    int run = 0;
+    for (int i = lo; i < hi; ++i) run += rowptr[i];
+    int v = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += up;
+    }
+    int* wsum = reinterpret_cast<int*>(S.red + 48);  // 8 ints of scratch; no reduction is in flight here
+    if (lane == 31) wsum[w] = v;
+    __syncthreads();
+    int acc = v - run;  // exclusive prefix inside the warp ...
+#pragma unroll
+    for (int ww = 0; ww < NW; ++ww)
+      if (ww < w) acc += wsum[ww];  // ... plus the warps before
+    for (int i = lo; i < hi; ++i) { acc += rowptr[i]; rowptr[i] = acc; }
+  }
+  __syncthreads();
+  for (int e = tid; e < n; e += NT) {
+    const unsigned ij = tij[e];
+    const int i = ij >> 16, j = ij & 0xffffu;
+    const double v = tv[e];
+    int p = rowptr[i] + atomicAdd(&cursor[i], 1);
+    S.c_col[p] = (uint16_t)j; S.c_val[p] = v;
+    p = rowptr[j] + atomicAdd(&cursor[j], 1);
+    S.c_col[p] = (uint16_t)i; S.c_val[p] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < mp; i += NT) {  // insertion sort of each row by column: fixed summation order
+    const int b = rowptr[i], e = rowptr[i + 1];
+    for (int a = b + 1; a < e; ++a) {
+      const uint16_t c = S.c_col[a];
+      const double v = S.c_val[a];
+      int q = a - 1;
+      while (q >= b && S.c_col[q] > c) { S.c_col[q + 1] = S.c_col[q]; S.c_val[q + 1] = S.c_val[q]; --q; }
+      S.c_col[q + 1] = c; S.c_val[q + 1] = v;
+    }
+  }
+  __syncthreads();
+  return true;
+}
+
 // ---- resident (compact) form --------------------------------------------------------------------
 // In the tile-skip format a problem often has only a few hundred edges.  Then this CTA's share of
 // the matrix is read from HBM exactly once: the stored tiles are streamed through the TMA rings a
@@ -474,64 +541,70 @@ __device__ __forceinline__ bool build_compact(const Smem& S, const double* __res
     slot = (slot + 1 == SLOTS) ? 0 : slot + 1;
   }
   __syncthreads();
-  const int n = *n_coo;
-  if (n > cap) return false;
+  return finish_compact(S, mp);
+}
 
-  // CSR over directed entries: count, scan, fill, sort rows by column
-  int* rowptr = S.c_rowptr;                       // [mp + 1]
-  int* cursor = S.c_rowptr + (mp + 1);            // [mp]
-  for (int i = tid; i <= mp; i += NT) rowptr[i] = 0;
-  for (int i = tid; i < mp; i += NT) cursor[i] = 0;
+// Dense format, late residency ("promotion"): a problem that is still iterating after `promote_after` streamed passes
+// reads its share of the tiles ONE more time — the same tile sequence as matvec_pass_dense — to pull out the non-zero
+// words, and runs every later pass from the shared-memory CSR.  Slow-converging problems (tens of passes where the
+// batch mean is ~5) otherwise pin a cluster to tens of full streams of a matrix that holds a few hundred edges.
+// accM / accC must be free (they stage the triples); the caller re-zeroes them if this returns false.
+__device__ __forceinline__ bool build_compact_dense(const Smem& S, const double* __restrict__ tiles, int nb, int mp,
+                                                    uint32_t& phase_bits, int C, int crank) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, tid = threadIdx.x;
+  const int SLOTS = S.slots;
+  uint64_t* bar = S.bar + w * MAX_SLOTS;
+  double* ring = S.ring + (size_t)w * SLOTS * RB_TILE_ELEMS;
+  double* tv = S.accM;
+  unsigned* tij = reinterpret_cast<unsigned*>(S.accC);
+  const int cap = S.c_cap;
+  int* n_coo = S.misc + 14;
+  if (tid == 0) *n_coo = 0;
   __syncthreads();
-  for (int e = tid; e < n; e += NT) {
-    const unsigned ij = tij[e];
-    atomicAdd(&rowptr[(ij >> 16) + 1], 1);
-    atomicAdd(&rowptr[(ij & 0xffffu) + 1], 1);
-  }
-  __syncthreads();
-  {  // inclusive scan of rowptr[1..mp]: each thread owns a contiguous run; warp scan of the run totals; warp offsets
-    const int per = (mp + NT - 1) / NT;
-    const int lo = 1 + tid * per, hi = (lo + per <= mp + 1) ? lo + per : mp + 1;
-    int run = 0;
-    for (int i = lo; i < hi; ++i) run += rowptr[i];
-    int v = run;
+  TileIter pf, it;
+  pf.init(nb, C, crank, w);
+  it.init(nb, C, crank, w);
+  auto pf_issue = [&](int sl) {
+    if (lane == 0)
+      tma_load_tile(ring + sl * RB_TILE_ELEMS, tiles + rb_tile_index(pf.I, pf.J, nb) * RB_TILE_ELEMS, bar + sl);
+    pf.next();
+  };
+  for (int s2 = 0; s2 < SLOTS; ++s2)
+    if (pf.ok) pf_issue(s2);
+  int slot = 0;
+  while (it.ok) {
+    const int I = it.I, J = it.J;
+    mbar_wait(bar + slot, (phase_bits >> slot) & 1u);
+    phase_bits ^= (1u << slot);
+    const double* rowp = ring + slot * RB_TILE_ELEMS + lane * RB_TILE;  // lane = row
+    unsigned rowmask = 0u;
+    {
+      const ulonglong2* rp2 = reinterpret_cast<const ulonglong2*>(rowp);
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int up = __shfl_up_sync(0xffffffffu, v, o);
-      if (lane >= o) v += up;
+      for (int t = 0; t < RB_TILE / 2; ++t) {
+        const int ch = t ^ (lane & 15);
+        const ulonglong2 q = rp2[ch];
+        if (q.x != 0ull) rowmask |= 1u << ((2 * ch) ^ lane);
+        if (q.y != 0ull) rowmask |= 1u << ((2 * ch + 1) ^ lane);
+      }
     }
-    int* wsum = reinterpret_cast<int*>(S.red + 48);  // 8 ints of scratch; no reduction is in flight here
-    if (lane == 31) wsum[w] = v;
-    __syncthreads();
-    int acc = v - run;  // exclusive prefix inside the warp ...
-#pragma unroll
-    for (int ww = 0; ww < NW; ++ww)
-      if (ww < w) acc += wsum[ww];  // ... plus the warps before
-    for (int i = lo; i < hi; ++i) { acc += rowptr[i]; rowptr[i] = acc; }
-  }
-  __syncthreads();
-  for (int e = tid; e < n; e += NT) {
-    const unsigned ij = tij[e];
-    const int i = ij >> 16, j = ij & 0xffffu;
-    const double v = tv[e];
-    int p = rowptr[i] + atomicAdd(&cursor[i], 1);
-    S.c_col[p] = (uint16_t)j; S.c_val[p] = v;
-    p = rowptr[j] + atomicAdd(&cursor[j], 1);
-    S.c_col[p] = (uint16_t)i; S.c_val[p] = v;
-  }
-  __syncthreads();
-  for (int i = tid; i < mp; i += NT) {  // insertion sort of each row by column: fixed summation order
-    const int b = rowptr[i], e = rowptr[i + 1];
-    for (int a = b + 1; a < e; ++a) {
-      const uint16_t c = S.c_col[a];
-      const double v = S.c_val[a];
-      int q = a - 1;
-      while (q >= b && S.c_col[q] > c) { S.c_col[q + 1] = S.c_col[q]; S.c_val[q + 1] = S.c_val[q]; --q; }
-      S.c_col[q + 1] = c; S.c_val[q + 1] = v;
+    if (J == I) rowmask &= ~((2u << lane) - 1u);  // diagonal tiles hold both triangles: keep the strict upper one
+    while (rowmask) {
+      const int t = __ffs(rowmask) - 1;
+      rowmask &= rowmask - 1;
+      const int pos = atomicAdd(n_coo, 1);
+      if (pos < cap) {
+        tv[pos] = rowp[t ^ lane];
+        tij[pos] = ((unsigned)(I * RB_TILE + lane) << 16) | (unsigned)(J * RB_TILE + t);
+      }
     }
+    __syncwarp();
+    if (pf.ok) pf_issue(slot);
+    slot = (slot + 1 == SLOTS) ? 0 : slot + 1;
+    it.next();
   }
   __syncthreads();
-  return true;
+  return finish_compact(S, mp);
 }
 
 // One pass out of the resident CSR: accM = M x, accC = C x (this CTA's share).
@@ -629,7 +702,7 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
       int cap = (int)(room / (2 * (8 + 2)));       // 2 directed entries of (double + uint16) per edge
       if (cap > (int)mp) cap = (int)mp;
       if (cap > 32767) cap = 32767;
-      S.c_cap = A.flags ? cap : 0;
+      S.c_cap = (A.flags || A.promote_after > 0) ? cap : 0;
       S.c_val = (double*)(q + head);
       S.c_col = (uint16_t*)(q + head + (size_t)2 * cap * 8);
       S.c_ug = ug_fits ? (double*)(q + head + ((((size_t)2 * cap * (8 + 2)) + 15) / 16) * 16) : nullptr;
@@ -682,7 +755,7 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
 
     if (m == 0) {
       if (lead && tid == 0) {
-        A.n_nodes[b] = 0; A.score[b] = 0.0; A.ifinal[b] = 0; A.n_passes[b] = 0; A.resident[b] = 0;
+        A.n_nodes[b] = 0; A.score[b] = 0.0; A.ifinal[b] = 0; A.n_passes[b] = 0; A.resident[b] = 0; A.streamed[b] = 0;
       }
       continue;
     }
@@ -710,11 +783,34 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
 
     // one fused (M x, C x) evaluation for the vector currently in S.x, incl. the cluster-wide combine
     // (the cycle counters feed rb_debug_solver_cycles)
+    int streamed = 0;      // passes that read the packed matrix from HBM
+    bool promoted = false;
     auto run_pass = [&]() {
+      // dense format: a problem still iterating after `promote_after` streamed passes becomes resident (see
+      // build_compact_dense).  accM / accC were cleared for this pass, so they are free to stage the triples.
+      if (!compact && !A.flags && A.promote_after > 0 && passes == A.promote_after) {
+        const long long tb = clock64();
+        bool ok = build_compact_dense(S, tiles, nb, mp, phase, C, crank);
+        ++streamed;
+        if (C > 1) {  // all CTAs of the cluster must run the same kind of pass
+          cluster.sync();
+          if (tid == 0) S.misc[15] = ok ? 1 : 0;
+          cluster.sync();
+          bool all = true;
+          for (int r = 0; r < C; ++r) all = all && (*cluster.map_shared_rank(S.misc + 15, r) != 0);
+          cluster.sync();
+          ok = all;
+        }
+        for (int i = tid; i < mp; i += NT) { S.accM[i] = 0.0; S.accC[i] = 0.0; }
+        __syncthreads();
+        compact = promoted = ok;
+        t_build += clock64() - tb;
+      }
       const long long t0 = clock64();
       matvec_pass(S, tiles, nb, phase, C, crank, compact);
       const long long t1 = clock64();
       ++passes;
+      if (!compact) ++streamed;
       cluster_combine(S, mp, C, crank);
       t_mv += t1 - t0;
       t_cb += clock64() - t1;
@@ -947,7 +1043,8 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
       A.score[b] = F;
       A.ifinal[b] = i_ol;
       A.n_passes[b] = passes;
-      A.resident[b] = compact ? (listed ? 2 : 1) : 0;
+      A.resident[b] = promoted ? 3 : (compact ? (listed ? 2 : 1) : 0);
+      A.streamed[b] = streamed + ((compact && !promoted && !listed) ? 1 : 0);  // + the one tile pass of build_compact
     }
     t_round += clock64() - tr0;
   }

@@ -150,6 +150,16 @@ class Engine:
     def set_profiling(self, on: bool):
         self._check(self._lib.rb_set_profiling(self._h, int(on)))
 
+    def solver_streamed_passes(self) -> torch.Tensor:
+        """(B,) int32: passes of the last solve that read the packed matrix from HBM (rb_solver_streamed_passes)."""
+        out = torch.zeros(max(self.B, 1), dtype=torch.int32, device=self.device)
+        self._check(self._lib.rb_solver_streamed_passes(self._h, _ptr(out), self._stream()))
+        return out[:self.B]
+
+    def set_solver_promote(self, passes: int):
+        """Dense format: streamed passes after which a still-iterating problem is made resident (0 = never; default 8)."""
+        self._check(self._lib.rb_set_solver_promote(self._h, int(passes)))
+
     def stage_ms(self) -> dict:
         ms = (C.c_float * 4)()
         self._check(self._lib.rb_get_stage_ms(self._h, ms))

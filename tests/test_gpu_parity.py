@@ -450,3 +450,59 @@ def test_exact_dsd_rounding_on_a_broad_support(engine):
             assert got == ref["nodes"] == cl.tolist(), seed
     finally:
         engine.set_solver_params(default_solver_params())
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4])
+def test_late_residency_promotion_in_the_dense_format(engine, coracle, cluster):
+    """rb_set_solver_promote: after N streamed passes a still-iterating problem is extracted into the shared-memory CSR.
+    Same answers as the oracle; the resident / streamed-pass reports say what happened; problems whose edges do not fit
+    keep streaming."""
+    if engine.default_tile_skip:
+        pytest.skip("promotion belongs to the dense format (the tile-skip format is resident from the start)")
+    ip_o, ip_g = params_for_method("roman", semantics_dim=40)
+    sp = cn.SolverParams()
+    shapes = [(12, 14), (30, 31), (40, 50), (9, 40), (33, 18), (40, 40)]
+    pairs = [synth.make_pair(70 + i, a, b, method="roman", semantics_dim=40, desc_common=0.9) for i, (a, b) in enumerate(shapes)]
+    D1 = np.concatenate([p.D1.reshape(-1) for p in pairs]); D2 = np.concatenate([p.D2.reshape(-1) for p in pairs])
+    u0 = np.concatenate([p.u0 for p in pairs])
+    engine.set_invariant_params(ip_g)
+    engine.set_solver_cluster(cluster)
+    try:
+        outs = {}
+        for promote in (2, 0):
+            engine.set_solver_promote(promote)
+            engine.plan(pairs[0].D1.shape[1], [a for a, _ in shapes], [b for _, b in shapes])
+            engine.affinity(D1, D2)
+            sol = engine.solve(u0, want_u=True)
+            outs[promote] = ({k: v.cpu().numpy() for k, v in sol.items() if v is not None},
+                             engine.solver_resident().cpu().numpy()[:len(pairs)], engine.solver_streamed_passes().cpu().numpy())
+        (s2, res2, str2), (s0, res0, str0) = outs[2], outs[0]
+        assert (res0 == 0).all() and np.array_equal(str0, s0["n_passes"])
+        assert np.array_equal(s2["n_passes"], s0["n_passes"]) and np.array_equal(s2["n_nodes"], s0["n_nodes"])
+        long_running = s0["n_passes"] > 2
+        assert long_running.any() and (res2[long_running] == 3).all() and (str2[long_running] == 3).all()
+        assert np.abs(s2["u"] - s0["u"]).max() <= 1e-9 and np.abs(s2["score"] - s0["score"]).max() <= F_TOL
+        for b, p in enumerate(pairs):
+            Mo, _, _, _ = coracle.score(ip_o, sp.affinityeps, p.D1, p.D2)
+            ref = coracle.solve(sp, Mo, p.u0)
+            o, n = int(engine.offsets[b]), int(s2["n_nodes"][b])
+            assert s2["nodes"][o:o + n].tolist() == ref["nodes"]
+            assert np.abs(s2["u"][o:o + len(p.u0)] - ref["u"]).max() <= 1e-9
+        # a geometry-only graph is far too dense for the shared-memory CSR: the extraction fails, streaming goes on
+        ip_o2, ip_g2 = params_for_method("clipper")
+        p = synth.make_pair(3, 30, 30, method="clipper")
+        engine.set_invariant_params(ip_g2)
+        engine.set_solver_promote(3)
+        engine.plan(3, [30], [30])
+        engine.affinity(p.D1.reshape(-1), p.D2.reshape(-1))
+        sol = engine.solve(p.u0)
+        Mo, _, _, nnz = coracle.score(ip_o2, sp.affinityeps, p.D1, p.D2)
+        ref = coracle.solve(sp, Mo, p.u0)
+        k = int(sol["n_nodes"][0])
+        assert nnz > 2000 and sol["nodes"][:k].cpu().numpy().tolist() == ref["nodes"]
+        assert int(engine.solver_resident()[0]) == 0
+        assert int(engine.solver_streamed_passes()[0]) == int(sol["n_passes"][0]) + 1      # + the failed extraction pass
+    finally:
+        engine.set_solver_promote(8)
+        engine.set_solver_cluster(0)
+        engine.plan(3, [1], [1])
