@@ -330,8 +330,8 @@ def run_b200(args):
         k1_ms = stage["prep"] + stage["affinity"]
         n_tiles = (m // 32 + (m % 32 > 0)) * (m // 32 + (m % 32 > 0) + 1) // 2
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
-        # kernel at this configuration (profiles/r1_solver_final_dense_B592_summary.txt); null for other batch sizes
-        traffic = 53.054540e9 + 170.393088e6 if (B == 592 and world == 1) else None
+        # kernel at this configuration (profiles/r1_solver_final5_dense_B592_summary.txt); null for other batch sizes
+        traffic = 52.599338e9 + 170.937856e6 if (B == 592 and world == 1 and args.rank_offset == 0 and args.promote < 0) else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
