@@ -168,7 +168,7 @@ def run_reference(args):
                        "(oracle/clipper_oracle.c, kind=port: the reference needs Eigen3 which is absent); one pair per host thread"},
             "cpu_baseline": cb,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def host_threads():
@@ -380,12 +380,27 @@ def run_b200(args):
         if world == 1 and not args.no_cpu:
             cb, _ = cpu_baseline(16)
             line["cpu_baseline"] = cb
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_OUT = None
+
+
+def emit(line: dict):
+    """The ONE line of stdout: main() points fd 1 at stderr for the whole run (NCCL, torchrun and library banners would
+    otherwise land on stdout next to the result) and keeps the real stdout for this call."""
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
