@@ -33,6 +33,9 @@
 //     solved "resident": a CSR over both directions is built in the space of the TMA rings — from
 //     the edge list K1 wrote, or from one pass over the stored tiles — and every pass is a CSR
 //     product out of shared memory, with u and g resident too.
+//   - dense format, late residency (rb_set_solver_promote): a problem still iterating after N streamed passes reads its
+//     tiles once more to extract the non-zero words (build_compact_dense) and finishes from the same shared-memory CSR;
+//     slow-converging problems would otherwise stream tens of full passes alone at the end of the launch.
 //   - misc[] slots: 0 queue index, 1 NONZERO count, 2 candidate counter, 4..12 tiles per warp +
 //     live tile-rows, 14 triple counter, 15 resident vote; red[] slots: 0..31 reductions, 40 k-th
 //     value, 48..51 scan scratch.
