@@ -352,7 +352,7 @@ def run_b200(args):
                                       "ms_per_launch": stage["solve"]},
                         "K3_arun_ms": stage["arun"]},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": "rb_align_batch_host (pinned host buffers; H2D pipelined with K1a/K1/K2/K3 over 4 problem ranges, then D2H)"},
+                    "api": "rb_align_batch_host (pinned host buffers; H2D pipelined with K1a/K1/K2/K3 over up to 5 problem ranges, then D2H)"},
             "gpu_launches": 5 * K,
             "clocks": clocks,
         }

@@ -1,6 +1,7 @@
 // rb_api.cu — handle, batch planning and the extern "C" entry points of include/roman_b200.h.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -61,7 +62,7 @@ struct rb_handle {
   cudaStream_t own_stream2 = nullptr;  // second compute stream: consecutive ranges alternate, so the next range's
                                        // kernels fill the SMs the previous range's solver tail leaves idle
   cudaEvent_t join_ev = nullptr;
-  cudaEvent_t chunk_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaStream_t last_stream = nullptr;  // stream of the most recent device-pointer stage call
   bool last_valid = false;
   cudaEvent_t order_ev = nullptr;
@@ -759,10 +760,40 @@ int rb_align_batch_host(rb_handle* h, const double* D1, const double* D2, const 
 
   // Pipeline: the batch is cut into up to RB_HOST_CHUNKS contiguous problem ranges; the copy stream uploads
   // range c+1 while the compute stream runs K1a/K1/K2/K3 of range c (inputs are consumed in place, no reordering).
-  constexpr int RB_HOST_CHUNKS = 4;
+  constexpr int RB_HOST_CHUNKS = 8;
   int nch = h->B / (2 * (h->max_clusters > 0 ? h->max_clusters : 1));  // keep >= 2 solver waves per range
   if (nch < 1) nch = 1;
-  if (nch > RB_HOST_CHUNKS) nch = RB_HOST_CHUNKS;
+  if (nch > 4) nch = 4;
+  // Range boundaries.  Big batches use 5 ranges growing from a small first one — the kernels cannot start before the
+  // first range has arrived, and a range must not finish computing before the next one has been copied (measured on
+  // B200, 592 pairs of m = 2000: 52.1k alignments/s against 49.2k with 4 equal ranges).  Smaller batches: equal ranges
+  // of at least two solver waves.  RB_HOST_SPLIT="w0,w1,..." (dev) overrides the relative sizes.
+  int bounds[RB_HOST_CHUNKS + 1];
+  {
+    double wts[RB_HOST_CHUNKS] = {0.6, 1.0, 1.4, 1.4, 1.4, 0.0, 0.0, 0.0};
+    int nw = (h->B >= 5 * (h->max_clusters > 0 ? h->max_clusters : 1)) ? 5 : 0;
+    if (const char* env = getenv("RB_HOST_SPLIT")) {
+      nw = 0;
+      const char* q = env;
+      while (*q && nw < RB_HOST_CHUNKS) {
+        char* endp = nullptr;
+        const double v = strtod(q, &endp);
+        if (endp == q) break;
+        if (v > 0.0) wts[nw++] = v;
+        q = (*endp == ',') ? endp + 1 : endp;
+      }
+    }
+    if (nw >= 1 && h->B >= 2 * nw) nch = nw;
+    else { nw = 0; }
+    double tot = 0.0, acc = 0.0;
+    for (int c = 0; c < nch; ++c) tot += nw ? wts[c] : 1.0;
+    bounds[0] = 0;
+    for (int c = 0; c < nch; ++c) {
+      acc += nw ? wts[c] : 1.0;
+      bounds[c + 1] = (c + 1 == nch) ? h->B : (int)((double)h->B * acc / tot);
+      if (bounds[c + 1] < bounds[c]) bounds[c + 1] = bounds[c];
+    }
+  }
   for (int c = 0; c < nch; ++c)
     if (!h->chunk_ev[c]) RB_CUDA(h, cudaEventCreateWithFlags(&h->chunk_ev[c], cudaEventDisableTiming));
   if (h->last_valid) {  // the copy stream must not overwrite staging buffers the previous call's kernels still read
@@ -776,7 +807,7 @@ int rb_align_batch_host(rb_handle* h, const double* D1, const double* D2, const 
     RB_CUDA(h, cudaMemcpyAsync(h->s_D2, D2, nD2 * sizeof(double), cudaMemcpyHostToDevice, cs));
   }
   for (int c = 0; c < nch; ++c) {
-    const int b0 = (int)((int64_t)h->B * c / nch), b1 = (int)((int64_t)h->B * (c + 1) / nch);
+    const int b0 = bounds[c], b1 = bounds[c + 1];
     const RbProblem& p0 = h->probs[(size_t)b0];
     const size_t o1 = (size_t)p0.off_obj1 * d, o2 = (size_t)p0.off_obj2 * d, oa = (size_t)p0.off_assoc;
     const size_t e1 = (b1 < h->B ? (size_t)h->probs[(size_t)b1].off_obj1 : (size_t)h->total_obj1) * d;
