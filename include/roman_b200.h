@@ -140,7 +140,8 @@ int rb_affinity(rb_handle* h, const double* D1, const double* D2, const int32_t*
  *     clipper/src/utils.cpp:22-29; callers wanting that behaviour fill u0 with U[0,1)).
  * Outputs (device; any may be NULL): nodes (sum m int32, first n_nodes[b] valid per problem,
  * ordered as the reference: descending u), sel (sum m x 2 int32: rows of A at nodes),
- * n_nodes (B), u (sum m), score (B), ifinal (B), n_passes (B: M passes streamed). */
+ * n_nodes (B), u (sum m), score (B), ifinal (B), n_passes (B: fused (M x, C x) evaluations = 2 + line-search trials;
+ * see rb_solver_streamed_passes for how many of them read M from HBM). */
 int rb_solve(rb_handle* h, const double* u0, int32_t* nodes, int32_t* sel, int32_t* n_nodes,
              double* u, double* score, int32_t* ifinal, int32_t* n_passes, void* stream);
 
