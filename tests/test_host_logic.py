@@ -276,3 +276,21 @@ def test_shim_covers_every_clipperpy_use_of_the_reference():
         assert a in fields or hasattr(clipperpy.Solution, a), f"Solution.{a} missing"
     # solve() takes the start vector as an optional argument, like the binding (py_clipper.cpp:289-297)
     assert "u0" in inspect.signature(clipperpy.CLIPPER.solve).parameters
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU restatement timed on the host cores) needs no GPU, prints exactly one JSON
+    line on stdout and carries the keys the driver reads."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "alignments/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert "workload" in d["config"]
