@@ -44,6 +44,11 @@ class SubmapPairResults:
                                                  #   NaN beyond skip_distance, as in the reference)
     submap_distance_mat: Optional[np.ndarray] = None
     robots_nearby_mat: Optional[np.ndarray] = None  # centre distance where the submaps are "nearby" (:101-103), else NaN
+    # filled when the submap poses are given (pair_error_metrics): the reference's evaluation matrices
+    T_ij_mat: Optional[np.ndarray] = None           # (S0, S1, 4, 4) relative pose of the two submap frames from their poses
+    clipper_angle_mat: Optional[np.ndarray] = None  # registration rotation error, nearby pairs only
+    clipper_dist_mat: Optional[np.ndarray] = None   # registration translation error, nearby pairs only
+    submap_yaw_diff_mat: Optional[np.ndarray] = None
     pairs: np.ndarray = field(default_factory=lambda: np.zeros((0, 2), dtype=np.int64))
 
 
@@ -65,11 +70,46 @@ def roll_pitch(T: np.ndarray):
     return roll, pitch
 
 
+def pair_error_metrics(T_ij_hat_mat: np.ndarray, poses0: np.ndarray, poses1: np.ndarray, nearby: np.ndarray,
+                       attempted: np.ndarray):
+    """
+    The evaluation matrices of the reference loop (roman/align/submap_align.py:117-129, 158-192) from the estimated
+    poses: T_ij = inv(T_wi) T_wj of the (gravity-aligned, possibly ground-truth) submap poses; for NEARBY pairs the
+    absolute relative yaw in degrees, and — for pairs that went through the loop body (`attempted`: not beyond
+    skip_distance) — the rotation / translation error of T_ij_hat against T_ij.  Pairs without a pose get the
+    reference's sentinels theta = 180.0 and dist = 1e6; theta then passes through the same rad2deg as a real angle
+    (:187), so the matrix holds 10313.24 for them — kept as is.
+    Returns (T_ij_mat, clipper_angle_mat, clipper_dist_mat, submap_yaw_diff_mat).
+    """
+    from scipy.spatial.transform import Rotation as Rot
+    poses0, poses1 = np.asarray(poses0, dtype=np.float64), np.asarray(poses1, dtype=np.float64)
+    S0, S1 = len(poses0), len(poses1)
+    T_ij = np.einsum("iab,jbc->ijac", np.linalg.inv(poses0), poses1)
+    angle = np.full((S0, S1), np.nan)
+    dist = np.full((S0, S1), np.nan)
+    yaw = np.full((S0, S1), np.nan)
+    yaw[nearby] = np.abs(np.rad2deg(np.arctan2(T_ij[..., 1, 0], T_ij[..., 0, 0])))[nearby]
+    for i in range(S0):
+        for j in range(S1):
+            if not (nearby[i, j] and attempted[i, j]):
+                continue
+            That = T_ij_hat_mat[i, j]
+            if np.isnan(That).any():
+                theta, dd = 180.0, 1e6
+            else:
+                T_err = np.linalg.inv(That) @ T_ij[i, j]
+                theta = Rot.from_matrix(T_err[:3, :3]).magnitude()
+                dd = np.linalg.norm(T_err[:3, 3])
+            angle[i, j] = np.abs(np.rad2deg(theta))
+            dist[i, j] = dd
+    return T_ij, angle, dist, yaw
+
+
 def align_submap_pairs(sm_params: SubmapAlignParams, submaps0: Sequence[List], submaps1: Sequence[List],
                        pair_mask: Optional[np.ndarray] = None, u0: Optional[dict] = None,
                        exclude_common_ids: Optional[bool] = None, rank: int = 0, world: int = 1,
                        positions0=None, positions1=None, skip_distance: float = np.inf,
-                       descriptors0=None, descriptors1=None) -> SubmapPairResults:
+                       descriptors0=None, descriptors1=None, poses0=None, poses1=None) -> SubmapPairResults:
     """
     Register every masked (i, j) pair of object lists.  `u0` optionally fixes the solver's start vectors (the
     reference draws them at random): a dict {(i, j): vector} or a callable (i, j, m) -> vector, called once per
@@ -82,6 +122,8 @@ def align_submap_pairs(sm_params: SubmapAlignParams, submaps0: Sequence[List], s
     submap_align.py:136-142 (0 associations, NaN pose); `descriptors0/1` (per submap: (N, D) stacked frame
     descriptors or a (D,) mean descriptor) with `sm_params.submap_descriptor` set reproduce the similarity
     gate of :131-134, :144-149.  Both are evaluated for every pair before anything is registered.
+    `poses0/1` (S, 4, 4): gravity-aligned submap poses T_odom_centre (ground truth where available) — with them (and
+    positions) the result also carries the reference's evaluation matrices, see pair_error_metrics.
     """
     from ..engine import Engine, default_solver_params
     from .. import clipperpy
@@ -146,8 +188,14 @@ def align_submap_pairs(sm_params: SubmapAlignParams, submaps0: Sequence[List], s
         if exclude_common_ids:  # all-to-all over the kept objects, as an explicit association list
             A_list.append(np.stack([np.repeat(k1, len(k2)), np.tile(k2, len(k1))], axis=1).astype(np.int32))
     res.pairs = np.array(pairs, dtype=np.int64).reshape(-1, 2)
-    if not pairs:
+    def finish(res):
+        if poses0 is not None and poses1 is not None and res.robots_nearby_mat is not None:
+            (res.T_ij_mat, res.clipper_angle_mat, res.clipper_dist_mat, res.submap_yaw_diff_mat) = pair_error_metrics(
+                res.T_ij_hat_mat, poses0, poses1, ~np.isnan(res.robots_nearby_mat), ~too_far)
         return res
+
+    if not pairs:
+        return finish(res)
 
     pi, pj = res.pairs[:, 0], res.pairs[:, 1]
     eng = reg._batch_engine = reg._batch_engine or Engine()
@@ -198,4 +246,4 @@ def align_submap_pairs(sm_params: SubmapAlignParams, submaps0: Sequence[List], s
         mean_len = 0.5 * (len(k1) + len(k2))  # lengths after the common-id removal
         res.clipper_percent_associations[i, j] = len(a) / mean_len if mean_len > 0 else 0.0
         res.status_mat[i, j] = status[b]
-    return res
+    return finish(res)

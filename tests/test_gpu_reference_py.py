@@ -185,7 +185,9 @@ def test_pair_loop_equals_reference_submap_align(engine, gold, name):
         return rng.uniform(0.0, 1.0, m)
     res = align_submap_pairs(SubmapAlignParams(**sc["sm_kwargs"]), runs[0], runs[1], u0=u0, positions0=pos[0],
                              positions1=pos[1], skip_distance=sc["skip_distance"],
-                             descriptors0=desc[0] if has_desc else None, descriptors1=desc[1] if has_desc else None)
+                             descriptors0=desc[0] if has_desc else None, descriptors1=desc[1] if has_desc else None,
+                             poses0=np.array([sm["pose_flu"] for sm in sc["runs"][0]]),
+                             poses1=np.array([sm["pose_flu"] for sm in sc["runs"][1]]))
     assert sizes == want["u0_sizes"]                       # same pairs reach the solver, in the same order
     assert res.clipper_num_associations.tolist() == want["clipper_num_associations"]
     if want["similarity_mat"] is not None:
@@ -207,3 +209,10 @@ def test_pair_loop_equals_reference_submap_align(engine, gold, name):
                 assert rel(res.T_ij_hat_mat[i, j], Tw) < 1e-9, (i, j)
                 n_pose += 1
     assert n_pose >= 1
+    # evaluation matrices of the loop (relative pose, yaw difference, registration errors with the reference's sentinels)
+    assert np.abs(res.T_ij_mat - np.asarray(want["T_ij_mat"])).max() < 1e-12
+    for got, key in ((res.clipper_angle_mat, "clipper_angle_mat"), (res.clipper_dist_mat, "clipper_dist_mat"),
+                     (res.submap_yaw_diff_mat, "submap_yaw_diff_mat")):
+        w = np.array([[np.nan if v is None else v for v in row] for row in want[key]], dtype=np.float64)
+        assert np.array_equal(np.isnan(got), np.isnan(w)), key
+        assert np.nanmax(np.abs(got - w) / np.maximum(1.0, np.abs(w))) < 1e-6, key

@@ -189,3 +189,23 @@ def test_wire_formats_equal_reference_writer(gold, tmp_path):
         assert js.read_text() == out["json"]
         edges.append(len(lcs))
     assert edges == [7, 2]
+
+
+def test_pair_error_metrics_equal_reference_loop(gold):
+    """The evaluation matrices of the pair loop (relative pose, yaw difference, rotation / translation error incl. the
+    reference's sentinel values) recomputed from the reference's own T_ij_hat."""
+    from roman_b200.align import prefilter
+    from roman_b200.align.submap_align import pair_error_metrics
+    for case in gold["pair_loop"]:
+        sc = golden_inputs.pair_loop_scenario(case["name"])
+        poses = [np.asarray(p) for p in case["poses"]]
+        That = np.array([[np.full((4, 4), np.nan) if T is None else np.asarray(T) for T in row] for row in case["T_ij_hat_mat"]])
+        dist = prefilter.submap_distances(poses[0][:, :3, 3], poses[1][:, :3, 3])
+        nearby = prefilter.nearby_mask(SubmapAlignParams(**sc["sm_kwargs"]), dist)
+        attempted = ~(dist > sc["skip_distance"])
+        T_ij, ang, dd, yaw = pair_error_metrics(That, poses[0], poses[1], nearby, attempted)
+        assert np.abs(T_ij - np.asarray(case["T_ij_mat"])).max() < 1e-12
+        for got, key in ((ang, "clipper_angle_mat"), (dd, "clipper_dist_mat"), (yaw, "submap_yaw_diff_mat")):
+            want = np.array([[np.nan if v is None else v for v in row] for row in case[key]], dtype=np.float64)
+            assert np.array_equal(np.isnan(got), np.isnan(want)), (case["name"], key)
+            assert np.nanmax(np.abs(got - want) / np.maximum(1.0, np.abs(want))) < 1e-9, (case["name"], key)
