@@ -90,3 +90,42 @@ def write_lc_json(path: str, closures: Sequence[dict], robot_names: Sequence[str
     } for c in closures]
     with open(path, "w") as f:
         json.dump(recs, f, indent=4)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Submap description file (`<robot>.sm.json`, reference roman/align/results.py:199-246)
+def _secs_nsecs(t: float) -> dict:
+    """reference results.py:47-53 (time_to_secs_nsecs, as_dict=True)"""
+    return {"seconds": int(t), "nanoseconds": int((t - int(t)) * 1e9)}
+
+
+def write_submaps_json(path: str, robot_name: str, segments: Sequence[dict], submaps: Sequence[dict]):
+    """
+    `segments`: one dict per map segment with keys id, centroid_odom (3,), volume, linearity, planarity, scattering,
+    first_seen, last_seen.  `submaps`: one dict per submap with keys time, pose_gravity_aligned (4x4, T_odom_submap),
+    segment_ids.  Layout, key order and the time splitting follow the reference writer, so that downstream consumers
+    of `*.sm.json` read either file.
+    """
+    doc = {"segments": [], "submaps": []}
+    for sg in segments:
+        doc["segments"].append({
+            "robot_name": robot_name,
+            "segment_index": sg["id"],
+            "centroid_odom": np.asarray(sg["centroid_odom"], dtype=np.float64).tolist(),
+            "shape_attributes": {"volume": sg["volume"], "linearity": sg["linearity"], "planarity": sg["planarity"],
+                                 "scattering": sg["scattering"]},
+            "first_seen": _secs_nsecs(sg["first_seen"]),
+            "last_seen": _secs_nsecs(sg["last_seen"]),
+        })
+    for j, sm in enumerate(submaps):
+        t, q = transform_to_xyz_quat(sm["pose_gravity_aligned"])
+        doc["submaps"].append({
+            "submap_index": j,
+            "T_odom_submap": {"tx": t[0], "ty": t[1], "tz": t[2], "qx": q[0], "qy": q[1], "qz": q[2], "qw": q[3]},
+            "robot_name": robot_name,
+            "seconds": int(sm["time"]),
+            "nanoseconds": int((sm["time"] % 1) * 1e9),
+            "segment_indices": list(sm["segment_ids"]),
+        })
+    with open(path, "w") as f:
+        json.dump(doc, f, indent=4)

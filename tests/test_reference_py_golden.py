@@ -209,3 +209,39 @@ def test_pair_error_metrics_equal_reference_loop(gold):
             want = np.array([[np.nan if v is None else v for v in row] for row in case[key]], dtype=np.float64)
             assert np.array_equal(np.isnan(got), np.isnan(want)), (case["name"], key)
             assert np.nanmax(np.abs(got - want) / np.maximum(1.0, np.abs(want))) < 1e-9, (case["name"], key)
+
+
+def test_submap_json_equals_reference_writer(gold, tmp_path):
+    """`<robot>.sm.json` byte-for-byte against the reference writer (roman/align/results.py:199-246)."""
+    from roman_b200.align.results import write_submaps_json
+    w = gold["wire_formats"]
+    want = w["outputs"][0]["sm_json"]
+    assert want is not None
+    segs = [dict(id=s["id"], centroid_odom=np.mean(np.asarray(s["points"]), axis=0), volume=s["volume"],
+                 linearity=s["linearity"], planarity=s["planarity"], scattering=s["scattering"],
+                 first_seen=s["first_seen"], last_seen=s["last_seen"]) for s in w["map_segments"]]
+    subs = [dict(time=t, pose_gravity_aligned=np.asarray(w["pose_gravity_aligned"][0][k]),
+                 segment_ids=[s["id"] for s in w["map_segments"][:k + 1]]) for k, t in enumerate(w["times"][0])]
+    path = tmp_path / "r0.sm.json"
+    write_submaps_json(str(path), w["outputs"][0]["robot_names"][0], segs, subs)
+    assert path.read_text() == want
+
+
+def test_g2o_fusion_equals_reference_tool(gold, tmp_path):
+    """create_config + g2o_file_fusion byte-for-byte against roman/offline_rpgo/g2o_file_fusion.py on the same input
+    files (two odometry files, one multi-robot and two single-robot loop-closure files), with and without the
+    association threshold."""
+    from roman_b200.align import g2o_fusion as gf
+    g = gold["g2o_fusion"]
+    for rel, text in g["files"].items():
+        dst = tmp_path / rel
+        dst.parent.mkdir(parents=True, exist_ok=True)
+        dst.write_text(text)
+    assert gf.create_config(["r1", "r2"], "ODOM", "ALIGN", "align") == g["config"]
+    cfg = gf.create_config(["r1", "r2"], str(tmp_path / "odom"), str(tmp_path / "align"), "align")
+    for key, want in g["fused"].items():
+        out = tmp_path / f"fused_{key}.g2o"
+        gf.g2o_file_fusion(cfg, str(out), thresh=None if key == "None" else int(key))
+        assert out.read_text() == want, key
+    assert g["fused"]["None"].count("\n") > g["fused"]["5"].count("\n") > 0
+    assert gf.gtsam_symbol("a", 7) == (97 << 56) + 7
