@@ -8,6 +8,7 @@ Host-side mirror of the reference's roman.align registration interface for the C
   dist_reg_with_pruning.py <- roman/align/dist_reg_with_pruning.py
   params.py                <- roman/params/submap_align_params.py (registration-related part)
   submap_align.py          <- the pair loop of roman/align/submap_align.py:93-200, batched (all pairs in one launch)
+  submaps.py               <- submaps_from_roman_map / extract_submap_descriptors of roman/map/map.py:210-357 (cutting a map into submaps)
   prefilter.py             <- the tests made before a pair is registered (submap_align.py:96-149; map.py:145-162)
   results.py               <- the writers of roman/align/results.py:149-246 (align.g2o, align.json, <robot>.sm.json)
   g2o_fusion.py            <- roman/offline_rpgo/g2o_file_fusion.py (odometry + loop-closure g2o files -> one pose graph file)
@@ -20,3 +21,4 @@ from .objects import SimpleObject  # noqa: F401
 from .submap_align import align_submap_pairs, SubmapPairResults  # noqa: F401
 from .results import SubmapMeta, loop_closures, write_g2o, write_lc_json, write_submaps_json  # noqa: F401
 from .g2o_fusion import create_config, g2o_file_fusion  # noqa: F401
+from .submaps import MapData, SubmapData, cut_submaps  # noqa: F401

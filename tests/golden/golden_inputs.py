@@ -70,3 +70,41 @@ def pair_loop_scenario(name: str) -> dict:
         return dict(method=method, sem=0, skip_distance=np.inf, runs=runs,
                     sm_kwargs=dict(method=method, single_robot_lc=True))
     raise KeyError(name)
+
+
+MAP_CUT_CASES = {
+    "default": dict(),
+    "time_pruning_small": dict(submap_pruning_method="time", submap_max_size=6, submap_center_time=8.0),
+    "no_radius": dict(submap_radius=None, submap_max_size=12, submap_center_dist=14.0),
+    "force_fill": dict(force_fill_submaps=True, submap_max_size=10, submap_overlap=4),
+    "mean_semantic": dict(submap_descriptor="mean_semantic", submap_max_size=8),
+    "mean_frame": dict(submap_descriptor="mean_frame_descriptor"),
+    "stacked": dict(submap_descriptor="stacked_frame_descriptors", submap_radius=8.0),
+    "stacked_thinned": dict(submap_descriptor="stacked_frame_descriptors", frame_descriptor_dist=3.0),
+}
+
+
+def map_scenario() -> dict:
+    """A robot's object map for the submap-cutting fixtures: 70 trajectory poses along a bending path (with some roll and
+    pitch), 55 objects scattered around it with sighting intervals, 8-d semantic and frame descriptors."""
+    from scipy.spatial.transform import Rotation as Rot
+    rng = np.random.default_rng(900)
+    n = 70
+    s = np.linspace(0.0, 1.0, n)
+    pos = np.stack([60.0 * s, 12.0 * np.sin(3.0 * s), 0.3 * np.cos(5.0 * s)], axis=1)
+    traj = np.tile(np.eye(4), (n, 1, 1))
+    for k in range(n):
+        yaw = 0.6 * np.cos(3.0 * s[k])
+        traj[k, :3, :3] = Rot.from_euler("ZYX", [yaw, 0.05 * np.sin(9 * s[k]), 0.04 * np.cos(7 * s[k])]).as_matrix()
+        traj[k, :3, 3] = pos[k]
+    times = 100.0 + 1.7 * np.arange(n) + rng.uniform(0, 0.3, n)
+    segs = []
+    for j in range(55):
+        k = int(rng.integers(0, n))
+        c = pos[k] + rng.normal(0, 5.0, 3) * np.array([1.0, 1.0, 0.2])
+        first = times[k] - rng.uniform(0, 6)
+        segs.append(dict(id=j, center=c, volume=float(rng.uniform(0.1, 3)), linearity=float(rng.uniform(0, 1)),
+                         planarity=float(rng.uniform(0, 1)), scattering=float(rng.uniform(0, 1)),
+                         extent=rng.uniform(0.2, 2, 3), semantic_descriptor=rng.normal(size=8),
+                         first_seen=float(first), last_seen=float(first + rng.uniform(1, 15))))
+    return dict(trajectory=traj, times=times, segments=segs, descriptors=rng.normal(size=(n, 8)))

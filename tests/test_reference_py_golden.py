@@ -245,3 +245,38 @@ def test_g2o_fusion_equals_reference_tool(gold, tmp_path):
         assert out.read_text() == want, key
     assert g["fused"]["None"].count("\n") > g["fused"]["5"].count("\n") > 0
     assert gf.gtsam_symbol("a", 7) == (97 << 56) + 7
+
+
+@pytest.mark.parametrize("name", list(golden_inputs.MAP_CUT_CASES))
+def test_submap_cutting_equals_reference_function(gold, name):
+    """cut_submaps against roman.map.map.submaps_from_roman_map run on the same map: which submaps exist, their poses,
+    which objects they hold IN ORDER, the objects' centres in the submap frame, the submap descriptors."""
+    from roman_b200.align.objects import SimpleObject
+    from roman_b200.align.submaps import MapData, cut_submaps
+
+    class Seg(SimpleObject):
+        pass
+    sc = golden_inputs.map_scenario()
+    segs = []
+    for g in sc["segments"]:
+        o = Seg(center=g["center"].copy(), volume=g["volume"], linearity=g["linearity"], planarity=g["planarity"],
+                scattering=g["scattering"], extent=g["extent"], semantic_descriptor=g["semantic_descriptor"], id=g["id"])
+        o.first_seen, o.last_seen = g["first_seen"], g["last_seen"]
+        segs.append(o)
+    traj0 = sc["trajectory"].copy()
+    subs = cut_submaps(MapData(segments=segs, trajectory=sc["trajectory"], times=sc["times"], descriptors=sc["descriptors"]),
+                       SubmapAlignParams(**golden_inputs.MAP_CUT_CASES[name]))
+    want = gold["submap_cutting"][name]
+    assert [sm.id for sm in subs] == [w["id"] for w in want]
+    for sm, w in zip(subs, want):
+        assert sm.time == w["time"]
+        assert np.abs(sm.pose_gravity_aligned - np.asarray(w["pose_gravity_aligned"])).max() < 1e-12
+        assert [s.id for s in sm.segments] == w["segment_ids"], (name, sm.id)
+        assert np.abs(np.array([np.asarray(s.center).reshape(-1) for s in sm.segments]) - np.asarray(w["centers"])).max() < 1e-9
+        if w["descriptor"] is not None:
+            assert np.abs(sm.descriptor - np.asarray(w["descriptor"])).max() < 1e-12
+        elif w["descriptor_frames"] is not None:
+            assert np.array_equal(sm.descriptor, sc["descriptors"][w["descriptor_frames"]])
+        else:
+            assert sm.descriptor is None
+    assert np.array_equal(traj0, sc["trajectory"]) and np.array_equal(segs[0].center, sc["segments"][0]["center"])   # inputs untouched
