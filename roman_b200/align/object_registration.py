@@ -16,12 +16,9 @@ class InsufficientAssociationsException(Exception):
     """reference object_registration.py:8-15"""
 
     def __init__(self, map1_len, map2_len, n_associations=None):
-        self.map1_len = map1_len
-        self.map2_len = map2_len
-        self.n_associations = n_associations
-        message = (f"Insufficient associations. Map 1 length: {map1_len}. Map 2 length: {map2_len}. "
-                   f"Associations: {n_associations}")
-        super().__init__(message)
+        self.map1_len, self.map2_len, self.n_associations = map1_len, map2_len, n_associations
+        super().__init__("Insufficient associations. " + " ".join(
+            (f"Map 1 length: {map1_len}.", f"Map 2 length: {map2_len}.", f"Associations: {n_associations}")))
 
 
 class ObjectRegistration:
@@ -33,11 +30,11 @@ class ObjectRegistration:
     def register(self, map1: List, map2: List, u0=None):
         """Returns the (k, 2) int32 inlier associations.  `u0` (optional, not in the reference
         signature) fixes the solver's start vector, which the reference draws at random."""
-        if len(map1) == 0 or len(map2) == 0:
-            return np.array([[]])
-        clipper, _ = self._clipper_score_all_to_all(self._setup_clipper(), map1, map2)
-        clipper.solve(u0)
-        return clipper.get_selected_associations()
+        if min(len(map1), len(map2)) == 0:
+            return np.array([[]])      # what the reference returns for an empty map
+        solver, _ = self._clipper_score_all_to_all(self._setup_clipper(), map1, map2)
+        solver.solve(u0)
+        return solver.get_selected_associations()
 
     def _setup_clipper(self):
         raise NotImplementedError
@@ -49,21 +46,20 @@ class ObjectRegistration:
         return
 
     # -- reference object_registration.py:40-48
+    def _feature_rows(self, objects: List) -> np.ndarray:
+        return np.array([self._object_to_clipper_list(o) for o in objects])
+
     def _clipper_score_all_to_all(self, clipper, map1: List, map2: List):
-        A_init = clipperpy.utils.create_all_to_all(len(map1), len(map2))
-        map1_cl = np.array([self._object_to_clipper_list(p) for p in map1])
-        map2_cl = np.array([self._object_to_clipper_list(p) for p in map2])
-        self._check_clipper_arrays(map1_cl, map2_cl)
-        clipper.score_pairwise_consistency(map1_cl.T, map2_cl.T, A_init)
-        return clipper, A_init
+        rows1, rows2 = self._feature_rows(map1), self._feature_rows(map2)
+        self._check_clipper_arrays(rows1, rows2)
+        every_pair = clipperpy.utils.create_all_to_all(len(map1), len(map2))
+        clipper.score_pairwise_consistency(rows1.T, rows2.T, every_pair)   # the binding takes (d, n) matrices
+        return clipper, every_pair
 
     # -- reference object_registration.py:50-55
     def get_MCA(self, map1: List, map2: List):
-        clipper = self._setup_clipper()
-        clipper, A_init = self._clipper_score_all_to_all(clipper, map1, map2)
-        M = clipper.get_affinity_matrix()
-        C = clipper.get_constraint_matrix()
-        return M, C, A_init
+        scored, assoc = self._clipper_score_all_to_all(self._setup_clipper(), map1, map2)
+        return scored.get_affinity_matrix(), scored.get_constraint_matrix(), assoc
 
     # -- reference object_registration.py:57-86
     def mno_clipper(self, map1: List, map2: List, num_solutions=2, u0s=None):
@@ -72,12 +68,12 @@ class ObjectRegistration:
         is the Rayleigh quotient of the clique-restricted u on the ORIGINAL affinity matrix."""
         M, C, A = self.get_MCA(map1, map2)
         M_first = M.copy()
-        clipper = clipperpy.CLIPPER(clipperpy.invariants.PairwiseInvariant(), clipperpy.Params())
+        resolver = clipperpy.CLIPPER(clipperpy.invariants.PairwiseInvariant(), clipperpy.Params())
         found = []
         for k in range(num_solutions):
-            clipper.set_matrix_data(M=M, C=C)
-            clipper.solve(None if u0s is None else u0s[k])
-            sol = clipper.get_solution()
+            resolver.set_matrix_data(M=M, C=C)
+            resolver.solve(u0s[k] if u0s is not None else None)
+            sol = resolver.get_solution()
             nodes = np.asarray(sol.nodes, dtype=np.int64)
             u_clique = np.zeros_like(sol.u)
             u_clique[nodes] = sol.u[nodes]
@@ -90,12 +86,12 @@ class ObjectRegistration:
     # -- reference object_registration.py:88-129
     def T_align(self, map1: List, map2: List, correspondences: np.ndarray = None):
         """Transformation that aligns map2 to map1 (Arun's method on the matched centres)."""
-        if len(map1) == 0 or len(map2) == 0:
-            raise InsufficientAssociationsException(len(map1), len(map2))
-        if correspondences is None:
-            correspondences = self.register(map1, map2)
-        if len(correspondences) < self.dim:
-            raise InsufficientAssociationsException(len(map1), len(map2), len(correspondences))
+        n1, n2 = len(map1), len(map2)
+        if min(n1, n2) == 0:
+            raise InsufficientAssociationsException(n1, n2)
+        correspondences = self.register(map1, map2) if correspondences is None else correspondences
+        if len(correspondences) < self.dim:      # Arun's method needs at least `dim` point pairs
+            raise InsufficientAssociationsException(n1, n2, len(correspondences))
         pts1 = np.array([np.asarray(o.center).reshape(-1)[:self.dim] for o in map1], dtype=np.float64)
         pts2 = np.array([np.asarray(o.center).reshape(-1)[:self.dim] for o in map2], dtype=np.float64)
         T = _arun_gpu(pts1, pts2, np.asarray(correspondences), self.dim)

@@ -294,3 +294,51 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"]
+
+
+def test_object_registration_glue_with_a_recording_clipper():
+    """The Python orchestration of ObjectRegistration (register / get_MCA / mno_clipper / T_align preconditions) driven
+    with a recording stand-in for the clipper object, so that it is exercised without a GPU."""
+    from roman_b200.align import InsufficientAssociationsException, ObjectRegistration, SimpleObject
+    from roman_b200.align import object_registration as oreg
+    calls = []
+
+    class FakeClipper:
+        def score_pairwise_consistency(self, D1, D2, A):
+            calls.append(("score", D1.shape, D2.shape, A.shape))
+            self.A = A
+
+        def solve(self, u0=None):
+            calls.append(("solve", None if u0 is None else len(u0)))
+
+        def get_selected_associations(self):
+            return self.A[[0, 4]]
+
+        def get_affinity_matrix(self):
+            return np.eye(len(self.A))
+
+        def get_constraint_matrix(self):
+            return np.eye(len(self.A))
+
+    class Reg(ObjectRegistration):
+        def _setup_clipper(self):
+            return FakeClipper()
+
+        def _object_to_clipper_list(self, o):
+            return np.asarray(o.center).reshape(-1)[:self.dim].tolist()
+
+    reg = Reg(dim=3)
+    m1 = [SimpleObject(center=np.array([k, 0.0, 1.0])) for k in range(2)]
+    m2 = [SimpleObject(center=np.array([0.0, k, 2.0])) for k in range(3)]
+    sel = reg.register(m1, m2, u0=np.ones(6))
+    assert calls == [("score", (3, 2), (3, 3), (6, 2)), ("solve", 6)]          # (d, n) matrices, all-to-all list
+    assert sel.tolist() == [[0, 0], [1, 1]]
+    assert reg.register([], m2).shape == (1, 0)                                # the reference's np.array([[]])
+    M, C, A = reg.get_MCA(m1, m2)
+    assert M.shape == (6, 6) and A.tolist() == [[i, j] for i in range(2) for j in range(3)]
+    with pytest.raises(InsufficientAssociationsException) as ex:
+        reg.T_align(m1, [], None)
+    assert str(ex.value) == "Insufficient associations. Map 1 length: 2. Map 2 length: 0. Associations: None"
+    with pytest.raises(InsufficientAssociationsException) as ex:
+        reg.T_align(m1, m2, np.array([[0, 0], [1, 1]]))
+    assert ex.value.n_associations == 2 and str(ex.value).endswith("Associations: 2")
