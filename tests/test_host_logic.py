@@ -342,3 +342,23 @@ def test_object_registration_glue_with_a_recording_clipper():
     with pytest.raises(InsufficientAssociationsException) as ex:
         reg.T_align(m1, m2, np.array([[0, 0], [1, 1]]))
     assert ex.value.n_associations == 2 and str(ex.value).endswith("Associations: 2")
+
+
+def test_euler_helpers_match_scipy_zyx():
+    """zyx_euler / roll_pitch / rm_roll_pitch against scipy's Rotation.as_euler('ZYX') — the call the reference makes
+    (roman/align/dist_reg_with_pruning.py:41, roman/utils.py:128-130) — on random rotations incl. large angles."""
+    from scipy.spatial.transform import Rotation as Rot
+    from roman_b200.align.dist_reg_with_pruning import zyx_euler
+    from roman_b200.align.submap_align import rm_roll_pitch, roll_pitch
+    R = Rot.random(200, random_state=7).as_matrix()
+    T = np.tile(np.eye(4), (200, 1, 1))
+    T[:, :3, :3] = R
+    T[:, :3, 3] = np.random.default_rng(1).normal(size=(200, 3))
+    ypr = Rot.from_matrix(R).as_euler("ZYX")
+    roll, pitch = roll_pitch(T)
+    assert np.abs(roll - ypr[:, 2]).max() < 1e-12 and np.abs(pitch - ypr[:, 1]).max() < 1e-12
+    for k in range(0, 200, 17):
+        assert np.allclose(zyx_euler(R[k]), ypr[k], atol=1e-12)
+    yaw_only = rm_roll_pitch(T)
+    want = Rot.from_euler("z", ypr[:, 0]).as_matrix()
+    assert np.abs(yaw_only[:, :3, :3] - want).max() < 1e-12 and np.array_equal(yaw_only[:, :3, 3], T[:, :3, 3])
