@@ -360,5 +360,5 @@ def test_euler_helpers_match_scipy_zyx():
     for k in range(0, 200, 17):
         assert np.allclose(zyx_euler(R[k]), ypr[k], atol=1e-12)
     yaw_only = rm_roll_pitch(T)
-    want = Rot.from_euler("z", ypr[:, 0]).as_matrix()
+    want = Rot.from_euler("z", ypr[:, 0].reshape(-1, 1)).as_matrix()
     assert np.abs(yaw_only[:, :3, :3] - want).max() < 1e-12 and np.array_equal(yaw_only[:, :3, 3], T[:, :3, 3])
