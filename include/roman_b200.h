@@ -12,7 +12,8 @@
  *     reported in `status[b]`, never as a return code (mirrors the Python exceptions caught
  *     per pair in roman/align/submap_align.py:179-184).
  *   - "Device" entry points take DEVICE pointers and a cudaStream_t (passed as void*); they
- *     only enqueue work on that stream and never synchronise.  "Host" entry points (_host
+ *     only enqueue work on that stream and never synchronise (two documented exceptions: rb_set_dense
+ *     reads back a validity flag, and rb_solve with rounding == DSD runs its host epilogue).  "Host" entry points (_host
  *     suffix) take HOST pointers, do the H2D/D2H copies themselves and return after the
  *     results are in the host buffers.
  *   - A batch is B independent submap-pair problems.  Problem b has n1[b], n2[b] objects and
