@@ -30,7 +30,9 @@
  * (clipper/test/affinity_test.cpp:94-107, clipper/test/clipper_test.cpp:62-66,
  * committed as tests/golden/ JSON files).  orc_arun is pinned by outputs of the reference's
  * own ObjectRegistration.T_align, executed from /root/reference by
- * tests/golden/make_reference_py_golden.py (tests/golden/reference_py_vectors.json).  The
+ * tests/golden/make_reference_py_golden.py (tests/golden/reference_py_vectors.json); orc_score's
+ * Euclidean branch additionally by the pure-Python scoring of the reference's example notebook
+ * (tests/golden/notebook_vectors.json).  The
  * ROMAN invariant, the solver iterates for a fixed u0 and the top-k tie order have NO golden
  * vector anywhere in the reference and their C++ cannot be built here: for those, PARITY IS
  * UNPINNED and this restatement (cross-checked against the independent numpy restatement
