@@ -362,3 +362,12 @@ def test_euler_helpers_match_scipy_zyx():
     yaw_only = rm_roll_pitch(T)
     want = Rot.from_euler("z", ypr[:, 0].reshape(-1, 1)).as_matrix()
     assert np.abs(yaw_only[:, :3, :3] - want).max() < 1e-12 and np.array_equal(yaw_only[:, :3, 3], T[:, :3, 3])
+
+
+def test_example_script_dry_run():
+    """examples/all_pairs_loop_closures.py up to (not including) the GPU registration: map synthesis, submap cutting."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "examples", "all_pairs_loop_closures.py"), "--dry-run"],
+                       capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "submap pairs" in r.stdout and "dry run" in r.stdout
