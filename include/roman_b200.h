@@ -229,6 +229,11 @@ int rb_solver_streamed_passes(rb_handle* h, int32_t* out, void* stream);
  * device int32[B]; a count above the list capacity (32 * ceil(m/32)) means the list overflowed and is not used. */
 int rb_edge_counts(rb_handle* h, int32_t* out, void* stream);
 
+/* After rb_affinity: associations per problem that can carry an edge at all (not padding, single score not below
+ * affinityeps — clipper/src/clipper.cpp:104-108), device int32[B].  L live associations give L(L-1)/2 evaluated pairs:
+ * the flop count of K1 (bench.py's fp64 accounting). */
+int rb_live_counts(rb_handle* h, int32_t* out, void* stream);
+
 /* Tile-skip format only: number of stored (flagged) 32x32 tiles of each problem, device int32[B]. */
 int rb_stored_tiles(rb_handle* h, int32_t* out, void* stream);
 
@@ -242,10 +247,17 @@ int rb_get_stage_ms(rb_handle* h, float ms[4]);
 
 /* Same as rb_align_batch with HOST pointers: copies D1, D2, A, u0 to the device, runs the
  * three stages, copies sel, n_sel, T, status, score, n_passes back, synchronises.  Pinned host
- * buffers make the copies asynchronous; pageable ones work too.  Requires a prior rb_plan. */
+ * buffers make the copies asynchronous; pageable ones work too.  Requires a prior rb_plan.
+ * The uploads are pipelined with the kernels over problem ranges fixed by rb_plan (cut by work, so ragged batches
+ * balance).  `sel` keeps the layout of rb_solve ((sum m) x 2, problem b at rb_assoc_offset) but only the first
+ * n_sel[b] rows of each problem are written: the device packs them compactly (at most min(n1, n2) rows per problem
+ * can form a set of distinct associations) and only that block crosses PCIe. */
 int rb_align_batch_host(rb_handle* h, const double* D1, const double* D2, const int32_t* A,
                         const double* u0, int32_t* sel, int32_t* n_sel, double* T,
                         int32_t* status, double* score, int32_t* n_passes);
+
+/* Bytes the last rb_align_batch_host call moved: direction 0 = host to device, 1 = device to host. */
+int64_t rb_host_copy_bytes(const rb_handle* h, int32_t direction);
 
 /* Diagnostics (used by tools/): first call enables per-CTA cycle counters in the solver kernel, later calls copy
  * them out: 8 x int64 per CTA — total, mat-vec, cluster combine, queue wait, rounding, list/CSR build. */

@@ -241,7 +241,9 @@ void orc_create_all_to_all(int n1, int n2, int32_t *A /* (n1*n2) x 2 row-major *
  * clipper.cpp:29-73 (kind==1) / :77-136 (kind==0).
  * D1: n1 objects x d doubles, object-major (one Eigen column = one object = d contiguous
  * doubles).  A: m x 2 int32 row-major.  Output: CSC strict-upper M; optionally the dense
- * scratch (m x m row-major, zeros elsewhere) and single_sim (m) for the tests.
+ * scratch (returned m x m row-major, zeros elsewhere) and single_sim (m) for the tests.
+ * The scratch itself is COLUMN-major, as Eigen's MatrixXd::Zero(m, m) (clipper.cpp:86), so that
+ * the sparseView() scan (clipper.cpp:132) walks memory contiguously like the reference's does.
  * parallelize mirrors CLIPPER::parallelize_ (clipper.h:147).
  */
 int orc_score(const orc_invariant_params *ip, double affinityeps, int d, int n1, const double *D1,
@@ -282,14 +284,14 @@ int orc_score(const orc_invariant_params *ip, double affinityeps, int d, int n1,
     } else {
       scr = orc_euclidean(ip, d, d1i, d1j, d2i, d2j);
     }
-    if (scr > affinityeps) M[i * m + j] = scr; /* M(i,j), i<j */
+    if (scr > affinityeps) M[j * m + i] = scr; /* M(i,j), i<j: column-major like Eigen's MatrixXd */
   }
 
-  /* M_ = M.sparseView(): column-major scan keeping coefficients != 0 */
+  /* M_ = M.sparseView(): column-major scan keeping coefficients != 0 (contiguous, as in Eigen) */
   int64_t nnz = 0;
-  for (int64_t i = 0; i < m; ++i)
-    for (int64_t j = i + 1; j < m; ++j)
-      if (M[i * m + j] != 0.0) ++nnz;
+  for (int64_t j = 0; j < m; ++j)
+    for (int64_t i = 0; i < j; ++i)
+      if (M[j * m + i] != 0.0) ++nnz;
   out->n = m;
   out->nnz = nnz;
   out->colptr = (int64_t *)malloc(sizeof(int64_t) * (size_t)(m + 1));
@@ -299,13 +301,15 @@ int orc_score(const orc_invariant_params *ip, double affinityeps, int d, int n1,
   for (int64_t j = 0; j < m; ++j) {
     out->colptr[j] = q;
     for (int64_t i = 0; i < j; ++i) {
-      const double v = M[i * m + j];
+      const double v = M[j * m + i];
       if (v != 0.0) { out->rowidx[q] = (int32_t)i; out->val[q] = v; ++q; }
     }
   }
   out->colptr[m] = q;
 
-  if (dense_out) memcpy(dense_out, M, sizeof(double) * (size_t)m * (size_t)m);
+  if (dense_out) /* tests only: the scratch as a row-major m x m array, i.e. transposed */
+    for (int64_t j = 0; j < m; ++j)
+      for (int64_t i = 0; i < m; ++i) dense_out[i * m + j] = M[j * m + i];
   if (single_out) memcpy(single_out, single_sim, sizeof(double) * (size_t)m);
   free(M);
   free(single_sim);
@@ -315,23 +319,25 @@ int orc_score(const orc_invariant_params *ip, double affinityeps, int d, int n1,
 /* clipper.cpp:220-229 setMatrixData: strict upper triangle of a dense (row-major) M -> CSC.
  * C is taken as given too; the solver below needs both. */
 int orc_csc_from_dense_upper(int64_t m, const double *dense, orc_csc *out) {
-  int64_t nnz = 0;
+  /* `dense` is row-major (numpy); count per column and fill while walking it row by row (contiguously) */
+  out->n = m;
+  out->colptr = (int64_t *)calloc((size_t)(m + 1), sizeof(int64_t));
   for (int64_t i = 0; i < m; ++i)
     for (int64_t j = i + 1; j < m; ++j)
-      if (dense[i * m + j] != 0.0) ++nnz;
-  out->n = m; out->nnz = nnz;
-  out->colptr = (int64_t *)malloc(sizeof(int64_t) * (size_t)(m + 1));
+      if (dense[i * m + j] != 0.0) ++out->colptr[j + 1];
+  for (int64_t j = 0; j < m; ++j) out->colptr[j + 1] += out->colptr[j];
+  const int64_t nnz = out->colptr[m];
+  out->nnz = nnz;
   out->rowidx = (int32_t *)malloc(sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1));
   out->val = (double *)malloc(sizeof(double) * (size_t)(nnz > 0 ? nnz : 1));
-  int64_t q = 0;
-  for (int64_t j = 0; j < m; ++j) {
-    out->colptr[j] = q;
-    for (int64_t i = 0; i < j; ++i) {
+  int64_t *cur = (int64_t *)malloc(sizeof(int64_t) * (size_t)(m > 0 ? m : 1));
+  for (int64_t j = 0; j < m; ++j) cur[j] = out->colptr[j];
+  for (int64_t i = 0; i < m; ++i) /* ascending i => row indices ascend inside every column */
+    for (int64_t j = i + 1; j < m; ++j) {
       const double v = dense[i * m + j];
-      if (v != 0.0) { out->rowidx[q] = (int32_t)i; out->val[q] = v; ++q; }
+      if (v != 0.0) { const int64_t q = cur[j]++; out->rowidx[q] = (int32_t)i; out->val[q] = v; }
     }
-  }
-  out->colptr[m] = q;
+  free(cur);
   return 0;
 }
 

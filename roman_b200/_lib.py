@@ -72,6 +72,8 @@ SIGNATURES = {
     "rb_set_tile_skip": (C.c_int, [_vp, _i32]),
     "rb_edge_counts": (C.c_int, [_vp, _ip, _vp]),
     "rb_stored_tiles": (C.c_int, [_vp, _ip, _vp]),
+    "rb_live_counts": (C.c_int, [_vp, _ip, _vp]),
+    "rb_host_copy_bytes": (_i64, [_vp, _i32]),
     "rb_solver_resident": (C.c_int, [_vp, _ip, _vp]),
     "rb_solver_streamed_passes": (C.c_int, [_vp, _ip, _vp]),
     "rb_set_solver_promote": (C.c_int, [_vp, _i32]),

@@ -614,7 +614,25 @@ __global__ void rb_count_flags_kernel(const RbProblem* __restrict__ probs, int B
   }
 }
 
+// live associations per problem (those that can carry an edge): popcount of the block live masks
+__global__ void rb_live_counts_kernel(const RbProblem* __restrict__ probs, int B, const uint32_t* __restrict__ masks,
+                                      int32_t* __restrict__ out) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const RbProblem pr = probs[b];
+  int c = 0;
+  for (int I = threadIdx.x & 31; I < pr.nb; I += 32) c += __popc(masks[(pr.off_pad >> 5) + I]);
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) out[b] = c;
+}
+
 }  // namespace
+
+cudaError_t rb_launch_live_counts(const RbProblem* probs, int B, const uint32_t* masks, int32_t* out, cudaStream_t st) {
+  if (B == 0) return cudaSuccess;
+  rb_live_counts_kernel<<<(B + 7) / 8, 256, 0, st>>>(probs, B, masks, out);
+  return cudaGetLastError();
+}
 
 cudaError_t rb_launch_count_flags(const RbProblem* probs, int B, const uint8_t* flags, int32_t* out, cudaStream_t st) {
   if (B == 0) return cudaSuccess;

@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -52,6 +53,15 @@ struct rb_handle {
   int32_t* d_nsel = nullptr; double* d_score = nullptr; int32_t* d_ifinal = nullptr; int32_t* d_npass = nullptr;
   int32_t* d_resident = nullptr;
   int32_t* d_streamed = nullptr;
+  // solver queue order (longest problem first): d_order for whole-batch launches, d_order_chunks for the problem
+  // ranges of the host entry point (entries are indices relative to the start of their range)
+  int32_t* d_order = nullptr; int32_t* d_order_chunks = nullptr; size_t cap_order = 0;
+  int nch = 1;               // problem ranges of rb_align_batch_host (fixed at plan time)
+  int bounds[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  // compact read-back of the inlier associations: the first kcap rows of every problem's `sel`
+  int32_t kcap = 0;
+  int32_t* d_selpad = nullptr; size_t cap_selpad = 0;
+  int32_t* h_selpad = nullptr; int32_t* h_nsel = nullptr; size_t cap_hsel = 0, cap_hnsel = 0;  // pinned host staging
   int32_t promote_after = 8;  // dense format: streamed passes before a still-iterating problem is made resident
   int32_t* d_status = nullptr; double* d_T = nullptr; size_t cap_B = 0;
   // staging for the host entry point
@@ -68,6 +78,8 @@ struct rb_handle {
   cudaEvent_t order_ev = nullptr;
 
   bool affinity_done = false;
+  bool masks_valid = false;   // rb_affinity wrote the block live masks (not after rb_set_dense)
+  int64_t last_h2d = 0, last_d2h = 0;  // bytes the last rb_align_batch_host call copied
   bool edges_valid = false;   // K1 wrote the edge lists of the current packed matrix (not after rb_set_dense)
   bool profiling = false;
   // e0 prep start, e1 prep end = affinity start, e2 affinity end, e3/e4 solve, e5/e6 arun
@@ -200,6 +212,9 @@ int rb_destroy(rb_handle* h) {
   cudaFree(h->d_nsel); cudaFree(h->d_score); cudaFree(h->d_ifinal); cudaFree(h->d_npass);
   cudaFree(h->d_status); cudaFree(h->d_T); cudaFree(h->d_resident); cudaFree(h->d_streamed);
   cudaFree(h->s_D1); cudaFree(h->s_D2); cudaFree(h->s_A); cudaFree(h->s_u0); cudaFree(h->d_debug); cudaFree(h->d_W);
+  cudaFree(h->d_order); cudaFree(h->d_order_chunks); cudaFree(h->d_selpad);
+  if (h->h_selpad) cudaFreeHost(h->h_selpad);
+  if (h->h_nsel) cudaFreeHost(h->h_nsel);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->order_ev) cudaEventDestroy(h->order_ev);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -309,6 +324,19 @@ int rb_stored_tiles(rb_handle* h, int32_t* out, void* stream) {
   if (!h->tile_skip) return fail(h, RB_ERR_ARG, "rb_stored_tiles: the dense format stores every tile (rb_set_tile_skip is off)");
   RB_CUDA(h, rb_launch_count_flags(h->d_probs, h->B, h->d_flags, out, (cudaStream_t)stream));
   return RB_OK;
+}
+
+int rb_live_counts(rb_handle* h, int32_t* out, void* stream) {
+  if (!h || !out) return RB_ERR_ARG;
+  if (!h->planned || !h->affinity_done || !h->masks_valid) return fail(h, RB_ERR_NOPLAN, "rb_live_counts before rb_affinity");
+  RB_ENTER(h);
+  RB_CUDA(h, rb_launch_live_counts(h->d_probs, h->B, h->d_masks, out, (cudaStream_t)stream));
+  return RB_OK;
+}
+
+int64_t rb_host_copy_bytes(const rb_handle* h, int32_t direction) {
+  if (!h) return -1;
+  return direction == 0 ? h->last_h2d : h->last_d2h;
 }
 
 int rb_set_profiling(rb_handle* h, int32_t on) {
@@ -475,6 +503,74 @@ static int plan_impl(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, cons
     RB_CUDA(h, cudaMalloc((void**)&h->d_T, n * 16 * sizeof(double)));
     h->cap_B = n;
   }
+  {
+    // Problem ranges of the host entry point (rb_align_batch_host): the copy stream uploads range c+1 while the compute
+    // streams run K1a/K1/K2/K3 of range c.  Big batches use 5 ranges growing from a small first one — the kernels cannot
+    // start before the first range has arrived, and a range must not finish computing before the next one has been
+    // copied (measured on B200, 592 pairs of m = 2000: 52.1k alignments/s against 49.2k with 4 equal ranges).  Smaller
+    // batches: equal ranges of at least two solver waves.  RB_HOST_SPLIT="w0,w1,..." (dev) overrides the relative sizes.
+    constexpr int RB_HOST_CHUNKS = 8;
+    const int mc = h->max_clusters > 0 ? h->max_clusters : 1;
+    int nch = B / (2 * mc);
+    if (nch < 1) nch = 1;
+    if (nch > 4) nch = 4;
+    double wts[RB_HOST_CHUNKS] = {0.6, 1.0, 1.4, 1.4, 1.4, 0.0, 0.0, 0.0};
+    int nw = (B >= 5 * mc) ? 5 : 0;
+    if (const char* env = getenv("RB_HOST_SPLIT")) {
+      nw = 0;
+      const char* q = env;
+      while (*q && nw < RB_HOST_CHUNKS) {
+        char* endp = nullptr;
+        const double v = strtod(q, &endp);
+        if (endp == q) break;
+        if (v > 0.0) wts[nw++] = v;
+        q = (*endp == ',') ? endp + 1 : endp;
+      }
+    }
+    if (nw >= 1 && B >= 2 * nw) nch = nw;
+    else nw = 0;
+    // ranges are cut by WORK (tiles), not by problem count: ragged batches arrive longest-first
+    double tot = 0.0, acc = 0.0;
+    for (int c = 0; c < nch; ++c) tot += nw ? wts[c] : 1.0;
+    h->bounds[0] = 0;
+    int b = 0;
+    for (int c = 0; c < nch; ++c) {
+      acc += nw ? wts[c] : 1.0;
+      const double target = (double)ot * acc / tot;
+      while (b < B && (double)h->tile_prefix[(size_t)b + 1] <= target + 0.5) ++b;
+      if (c + 1 == nch) b = B;
+      h->bounds[c + 1] = b;
+    }
+    h->nch = nch;
+    // queue orders: descending m (stable), for the whole batch and inside every range
+    if ((rc = ensure(h, &h->d_order, &h->cap_order, (size_t)B))) return rc;
+    {
+      size_t dummy = h->d_order_chunks ? h->cap_order : 0;
+      if ((rc = ensure(h, &h->d_order_chunks, &dummy, (size_t)B))) return rc;
+    }
+    std::vector<int32_t> ord((size_t)B), ordc((size_t)B);
+    auto fill = [&](int b0, int b1, int32_t* out) {
+      for (int i = b0; i < b1; ++i) out[i] = i - b0;
+      std::stable_sort(out + b0, out + b1, [&](int32_t x, int32_t y) { return h->probs[(size_t)(b0 + x)].m > h->probs[(size_t)(b0 + y)].m; });
+    };
+    fill(0, B, ord.data());
+    for (int c = 0; c < nch; ++c) fill(h->bounds[c], h->bounds[c + 1], ordc.data());
+    if (B > 0) {
+      RB_CUDA(h, cudaMemcpy(h->d_order, ord.data(), (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice));
+      RB_CUDA(h, cudaMemcpy(h->d_order_chunks, ordc.data(), (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    // compact read-back: an inlier set respects the distinctness constraint, so it has at most min(n1, n2, m) members
+    // (problems that exceed the capacity anyway are read back in full, see rb_align_batch_host)
+    int32_t kc = 1;
+    for (int i = 0; i < B; ++i) {
+      const RbProblem& p = h->probs[(size_t)i];
+      int32_t k = p.n1 < p.n2 ? p.n1 : p.n2;
+      if (k > p.m) k = p.m;
+      if (k > kc) kc = k;
+    }
+    h->kcap = kc;
+    if ((rc = ensure(h, &h->d_selpad, &h->cap_selpad, (size_t)(B ? B : 1) * kc * 2))) return rc;
+  }
   // Descriptor upload is synchronous on the legacy stream: plan is not part of any timed region.
   if (B > 0) {
     RB_CUDA(h, cudaMemcpy(h->d_probs, h->probs.data(), (size_t)B * sizeof(RbProblem), cudaMemcpyHostToDevice));
@@ -535,6 +631,7 @@ int affinity_range(rb_handle* h, int b0, int b1, const double* D1, const double*
                                 h->d_edge_cnt + b0, P, h->sm_count, st));
   record(h, 2, st);
   h->edges_valid = h->tile_skip;
+  h->masks_valid = true;
   return RB_OK;
 }
 
@@ -578,11 +675,12 @@ int dsd_epilogue(rb_handle* h, int b0, int b1, int32_t* nodes, int32_t* sel, int
   return RB_OK;
 }
 
-int solve_range(rb_handle* h, int b0, int b1, int queue, const double* u0, int32_t* nodes, int32_t* sel,
+int solve_range(rb_handle* h, int b0, int b1, int queue, const int32_t* order, const double* u0, int32_t* nodes, int32_t* sel,
                 int32_t* n_nodes, double* u, double* score, int32_t* ifinal, int32_t* n_passes, cudaStream_t st) {
   if (b1 <= b0) return RB_OK;
   RbSolveArgs a;
   a.probs = h->d_probs + b0; a.B = b1 - b0; a.counter = h->d_counter + queue; a.Mp = h->d_M;
+  a.order = order;
   a.flags = h->tile_skip ? h->d_flags : nullptr;
   a.edge_ij = (h->tile_skip && h->edges_valid) ? h->d_edge_ij : nullptr;
   a.edge_v = h->d_edge_v;
@@ -618,13 +716,14 @@ int solve_range(rb_handle* h, int b0, int b1, int queue, const double* u0, int32
 }
 
 int arun_range(rb_handle* h, int b0, int b1, const double* D1, const double* D2, const int32_t* sel,
-               const int32_t* n_sel, double* T, int32_t* status, cudaStream_t st) {
+               const int32_t* n_sel, double* T, int32_t* status, bool pack_sel, cudaStream_t st) {
   if (b1 <= b0) return RB_OK;
   const int pd = h->inv.kind == RB_INVARIANT_ROMAN ? h->inv.point_dim : (h->d < 3 ? h->d : 3);
   if (pd < 2) return fail(h, RB_ERR_ARG, "rb_arun: point dimension must be 2 or 3");
   record(h, 5, st);
   RB_CUDA(h, rb_launch_arun(h->d_probs + b0, b1 - b0, pd, D1, D2, sel, n_sel + b0, (T ? T : h->d_T) + (size_t)b0 * 16,
-                            (status ? status : h->d_status) + b0, st));
+                            (status ? status : h->d_status) + b0,
+                            pack_sel ? h->d_selpad + (size_t)b0 * h->kcap * 2 : nullptr, h->kcap, st));
   record(h, 6, st);
   return RB_OK;
 }
@@ -654,7 +753,7 @@ int rb_solve(rb_handle* h, const double* u0, int32_t* nodes, int32_t* sel, int32
   RB_ENTER(h);
   cudaStream_t st = (cudaStream_t)stream;
   h->last_stream = st; h->last_valid = true;
-  return solve_range(h, 0, h->B, 0, u0, nodes, sel, n_nodes, u, score, ifinal, n_passes, st);
+  return solve_range(h, 0, h->B, 0, h->d_order, u0, nodes, sel, n_nodes, u, score, ifinal, n_passes, st);
 }
 
 int rb_arun(rb_handle* h, const double* D1, const double* D2, const int32_t* sel, const int32_t* n_sel, double* T,
@@ -666,7 +765,7 @@ int rb_arun(rb_handle* h, const double* D1, const double* D2, const int32_t* sel
   RB_ENTER(h);
   cudaStream_t st = (cudaStream_t)stream;
   h->last_stream = st; h->last_valid = true;
-  return arun_range(h, 0, h->B, D1, D2, sel, n_sel, T, status, st);
+  return arun_range(h, 0, h->B, D1, D2, sel, n_sel, T, status, false, st);
 }
 
 int rb_submap_similarity(rb_handle* h, int32_t S0, int32_t S1, int32_t D, const int64_t* off0, const int64_t* off1,
@@ -720,6 +819,7 @@ int rb_set_dense(rb_handle* h, int32_t b, const double* M, const double* C, void
   RB_CUDA(h, rb_launch_pack(pr, M, C, h->d_M, h->d_bad, st));
   RB_CUDA(h, cudaMemsetAsync(h->d_flags + pr.off_tile, 1, (size_t)pr.n_tiles, st));  // every tile of b is stored
   h->edges_valid = false;  // no edge list for matrices given by the caller: the solver reads the tiles
+  h->masks_valid = false;
   int bad = 0;
   RB_CUDA(h, cudaMemcpyAsync(&bad, h->d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
   RB_CUDA(h, cudaStreamSynchronize(st));
@@ -758,42 +858,10 @@ int rb_align_batch_host(rb_handle* h, const double* D1, const double* D2, const 
   if ((rc = ensure(h, &h->s_u0, &h->cap_su0, nA))) return rc;
   if (!h->all_to_all && (rc = ensure(h, &h->s_A, &h->cap_sA, 2 * nA))) return rc;
 
-  // Pipeline: the batch is cut into up to RB_HOST_CHUNKS contiguous problem ranges; the copy stream uploads
-  // range c+1 while the compute stream runs K1a/K1/K2/K3 of range c (inputs are consumed in place, no reordering).
-  constexpr int RB_HOST_CHUNKS = 8;
-  int nch = h->B / (2 * (h->max_clusters > 0 ? h->max_clusters : 1));  // keep >= 2 solver waves per range
-  if (nch < 1) nch = 1;
-  if (nch > 4) nch = 4;
-  // Range boundaries.  Big batches use 5 ranges growing from a small first one — the kernels cannot start before the
-  // first range has arrived, and a range must not finish computing before the next one has been copied (measured on
-  // B200, 592 pairs of m = 2000: 52.1k alignments/s against 49.2k with 4 equal ranges).  Smaller batches: equal ranges
-  // of at least two solver waves.  RB_HOST_SPLIT="w0,w1,..." (dev) overrides the relative sizes.
-  int bounds[RB_HOST_CHUNKS + 1];
-  {
-    double wts[RB_HOST_CHUNKS] = {0.6, 1.0, 1.4, 1.4, 1.4, 0.0, 0.0, 0.0};
-    int nw = (h->B >= 5 * (h->max_clusters > 0 ? h->max_clusters : 1)) ? 5 : 0;
-    if (const char* env = getenv("RB_HOST_SPLIT")) {
-      nw = 0;
-      const char* q = env;
-      while (*q && nw < RB_HOST_CHUNKS) {
-        char* endp = nullptr;
-        const double v = strtod(q, &endp);
-        if (endp == q) break;
-        if (v > 0.0) wts[nw++] = v;
-        q = (*endp == ',') ? endp + 1 : endp;
-      }
-    }
-    if (nw >= 1 && h->B >= 2 * nw) nch = nw;
-    else { nw = 0; }
-    double tot = 0.0, acc = 0.0;
-    for (int c = 0; c < nch; ++c) tot += nw ? wts[c] : 1.0;
-    bounds[0] = 0;
-    for (int c = 0; c < nch; ++c) {
-      acc += nw ? wts[c] : 1.0;
-      bounds[c + 1] = (c + 1 == nch) ? h->B : (int)((double)h->B * acc / tot);
-      if (bounds[c + 1] < bounds[c]) bounds[c + 1] = bounds[c];
-    }
-  }
+  // Pipeline: the batch is cut into contiguous problem ranges (fixed by rb_plan); the copy stream uploads range c+1
+  // while the compute streams run K1a/K1/K2/K3 of range c (inputs are consumed in place, no reordering).
+  const int nch = h->nch;
+  const int* bounds = h->bounds;
   for (int c = 0; c < nch; ++c)
     if (!h->chunk_ev[c]) RB_CUDA(h, cudaEventCreateWithFlags(&h->chunk_ev[c], cudaEventDisableTiming));
   if (h->last_valid) {  // the copy stream must not overwrite staging buffers the previous call's kernels still read
@@ -802,6 +870,7 @@ int rb_align_batch_host(rb_handle* h, const double* D1, const double* D2, const 
     RB_CUDA(h, cudaStreamWaitEvent(cs, h->order_ev, 0));
   }
   const size_t d = (size_t)h->d;
+  h->last_h2d = (int64_t)((nD1 + nD2 + nA) * sizeof(double) + (h->all_to_all ? 0 : 2 * nA * sizeof(int32_t)));
   if (h->indexed) {  // shared object tables: uploaded once, every range may reference any part of them
     RB_CUDA(h, cudaMemcpyAsync(h->s_D1, D1, nD1 * sizeof(double), cudaMemcpyHostToDevice, cs));
     RB_CUDA(h, cudaMemcpyAsync(h->s_D2, D2, nD2 * sizeof(double), cudaMemcpyHostToDevice, cs));
@@ -824,8 +893,8 @@ int rb_align_batch_host(rb_handle* h, const double* D1, const double* D2, const 
     cudaStream_t ks = cst[c & 1];
     RB_CUDA(h, cudaStreamWaitEvent(ks, h->chunk_ev[c], 0));
     if ((rc = affinity_range(h, b0, b1, h->s_D1, h->s_D2, h->all_to_all ? nullptr : h->s_A, ks))) return rc;
-    if ((rc = solve_range(h, b0, b1, c, h->s_u0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ks))) return rc;
-    if ((rc = arun_range(h, b0, b1, h->s_D1, h->s_D2, h->d_sel, h->d_nsel, nullptr, nullptr, ks))) return rc;
+    if ((rc = solve_range(h, b0, b1, c, h->d_order_chunks + b0, h->s_u0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ks))) return rc;
+    if ((rc = arun_range(h, b0, b1, h->s_D1, h->s_D2, h->d_sel, h->d_nsel, nullptr, nullptr, sel != nullptr, ks))) return rc;
   }
   if (nch > 1) {  // join the second compute stream before reading results back
     RB_CUDA(h, cudaEventRecord(h->join_ev, cst[1]));
@@ -834,13 +903,49 @@ int rb_align_batch_host(rb_handle* h, const double* D1, const double* D2, const 
   h->affinity_done = true;
   h->last_stream = st; h->last_valid = true;
   const size_t B = (size_t)h->B;
-  if (sel) RB_CUDA(h, cudaMemcpyAsync(sel, h->d_sel, 2 * nA * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  // `sel` comes back compactly: K3 packed the first kcap rows of every problem (kcap = max min(n1, n2), an upper bound
+  // on any inlier set that respects the distinctness constraint) into d_selpad; the host scatters n_sel[b] rows into
+  // the caller's layout.  (Copying the whole padded (sum m) x 2 table would be 9.5 MB for 592 pairs of m = 2000.)
+  const size_t kc = (size_t)h->kcap;
+  if (sel) {
+    if (B * kc * 2 > h->cap_hsel) {
+      if (h->h_selpad) cudaFreeHost(h->h_selpad);
+      h->h_selpad = nullptr; h->cap_hsel = 0;
+      RB_CUDA(h, cudaMallocHost((void**)&h->h_selpad, B * kc * 2 * sizeof(int32_t)));
+      h->cap_hsel = B * kc * 2;
+    }
+    if (B > h->cap_hnsel) {
+      if (h->h_nsel) cudaFreeHost(h->h_nsel);
+      h->h_nsel = nullptr; h->cap_hnsel = 0;
+      RB_CUDA(h, cudaMallocHost((void**)&h->h_nsel, B * sizeof(int32_t)));
+      h->cap_hnsel = B;
+    }
+    RB_CUDA(h, cudaMemcpyAsync(h->h_selpad, h->d_selpad, B * kc * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    RB_CUDA(h, cudaMemcpyAsync(h->h_nsel, h->d_nsel, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  }
   if (n_sel) RB_CUDA(h, cudaMemcpyAsync(n_sel, h->d_nsel, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   if (T) RB_CUDA(h, cudaMemcpyAsync(T, h->d_T, B * 16 * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (status) RB_CUDA(h, cudaMemcpyAsync(status, h->d_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   if (score) RB_CUDA(h, cudaMemcpyAsync(score, h->d_score, B * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (n_passes) RB_CUDA(h, cudaMemcpyAsync(n_passes, h->d_npass, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   RB_CUDA(h, cudaStreamSynchronize(st));
+  h->last_d2h = (int64_t)((sel ? B * kc * 2 * sizeof(int32_t) + B * sizeof(int32_t) : 0) + (n_sel ? B * 4 : 0) + (T ? B * 128 : 0) +
+                          (status ? B * 4 : 0) + (score ? B * 8 : 0) + (n_passes ? B * 4 : 0));
+  if (sel) {
+    bool big = false;
+    for (size_t b = 0; b < B; ++b) {
+      const size_t k = (size_t)h->h_nsel[b];
+      const size_t o = (size_t)h->probs[b].off_assoc;
+      if (k > kc) {  // larger than any distinct inlier set: read this problem's rows straight from the full table
+        RB_CUDA(h, cudaMemcpyAsync(sel + 2 * o, h->d_sel + 2 * o, 2 * k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        h->last_d2h += (int64_t)(2 * k * sizeof(int32_t));
+        big = true;
+      } else if (k > 0) {
+        memcpy(sel + 2 * o, h->h_selpad + b * kc * 2, 2 * k * sizeof(int32_t));
+      }
+    }
+    if (big) RB_CUDA(h, cudaStreamSynchronize(st));
+  }
   return RB_OK;
 }
 

@@ -128,13 +128,19 @@ __device__ void rotation_from_H3(const double H[9], double R[9]) {
 __global__ void __launch_bounds__(128) rb_arun_kernel(const RbProblem* __restrict__ probs, int B, int pd,
                                                       const double* __restrict__ D1, const double* __restrict__ D2,
                                                       const int32_t* __restrict__ sel, const int32_t* __restrict__ n_sel,
-                                                      double* __restrict__ T, int32_t* __restrict__ status) {
+                                                      double* __restrict__ T, int32_t* __restrict__ status,
+                                                      int32_t* __restrict__ selpad, int kcap) {
   const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
   const RbProblem pr = probs[b];
   const int k = n_sel[b];
   double* Tb = T + (int64_t)b * 16;
+  if (selpad) {  // compact copy of the inlier rows for the host entry point's read-back (rb_align_batch_host)
+    const int kk = k < kcap ? k : kcap;
+    const int32_t* sfull = sel + 2 * pr.off_assoc;
+    for (int i = lane; i < 2 * kk; i += 32) selpad[(int64_t)b * kcap * 2 + i] = sfull[i];
+  }
   if (pr.n1 == 0 || pr.n2 == 0 || k < pd) {  // object_registration.py:102-108
     if (lane < 16) Tb[lane] = __longlong_as_double(0x7ff8000000000000ll);
     if (lane == 0) status[b] = RB_PAIR_INSUFFICIENT;
@@ -198,8 +204,9 @@ __global__ void __launch_bounds__(128) rb_arun_kernel(const RbProblem* __restric
 }  // namespace
 
 cudaError_t rb_launch_arun(const RbProblem* probs, int B, int point_dim, const double* D1, const double* D2,
-                           const int32_t* sel, const int32_t* n_sel, double* T, int32_t* status, cudaStream_t st) {
+                           const int32_t* sel, const int32_t* n_sel, double* T, int32_t* status, int32_t* selpad,
+                           int kcap, cudaStream_t st) {
   if (B == 0) return cudaSuccess;
-  rb_arun_kernel<<<(B + 3) / 4, 128, 0, st>>>(probs, B, point_dim, D1, D2, sel, n_sel, T, status);
+  rb_arun_kernel<<<(B + 3) / 4, 128, 0, st>>>(probs, B, point_dim, D1, D2, sel, n_sel, T, status, selpad, kcap);
   return cudaGetLastError();
 }

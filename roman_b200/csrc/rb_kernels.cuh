@@ -14,6 +14,7 @@ struct RbSolveArgs {
   const RbProblem* probs;
   int32_t B;
   int32_t* counter;        // dynamic problem queue (zeroed before launch)
+  const int32_t* order;    // queue position -> problem index (longest problem first), or null = identity
   const double* Mp;        // packed tiles
   const uint8_t* flags;    // per stored tile: 1 = holds a non-zero word; null = every tile is streamed (dense mode)
   int32_t nt_max;          // max stored tiles of one problem (sizes the shared-memory copy of the flags)
@@ -74,4 +75,5 @@ cudaError_t rb_launch_similarity(int S0, int S1, int D, const int64_t* off0, con
                                  const double* F1, double* sim, cudaStream_t st);
 cudaError_t rb_launch_arun(const RbProblem* probs, int B, int point_dim, const double* D1, const double* D2,
                            const int32_t* sel, const int32_t* n_sel, double* T, int32_t* status,
-                           cudaStream_t st);
+                           int32_t* selpad, int kcap, cudaStream_t st);
+cudaError_t rb_launch_live_counts(const RbProblem* probs, int B, const uint32_t* masks, int32_t* out, cudaStream_t st);

@@ -643,7 +643,9 @@ __device__ __forceinline__ void cluster_combine(const Smem& S, int mp, int C, in
   const int L = ((mp / RB_TILE + C - 1) / C) * RB_TILE;  // slice length (multiple of 32)
   const int lo = crank * L, hi = (lo + L < mp) ? lo + L : mp;
   cluster.sync();
-  constexpr int SL = 9;  // slice elements per thread: L <= SL * NT (mp <= 4608 at C = 2)
+  // slice elements per thread: L = ceil(nb / C) * 32 <= ceil(EPT_MAX * NT / 32 / 2) * 32 = SL * NT for every C >= 2
+  constexpr int SL = (EPT_MAX + 1) / 2;
+  static_assert(SL * NT * 2 >= EPT_MAX * NT, "cluster_combine: slice registers must cover mp_max / 2");
   double sm[SL], sc[SL];
 #pragma unroll
   for (int k = 0; k < SL; ++k) { sm[k] = 0.0; sc[k] = 0.0; }
@@ -735,9 +737,10 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
       for (int r = 0; r < C; ++r) *cluster.map_shared_rank(S.misc, r) = nxt;
     }
     cluster.sync();
-    const int b = S.misc[0];
+    const int qpos = S.misc[0];
     t_q += clock64() - tq0;
-    if (b >= A.B) break;
+    if (qpos >= A.B) break;
+    const int b = A.order ? A.order[qpos] : qpos;  // longest problems first (rb_plan sorts by m)
     const RbProblem pr = A.probs[b];
     const int m = pr.m, nb = pr.nb, mp = nb * RB_TILE;
     const double* tiles = A.Mp + pr.off_tile * RB_TILE_ELEMS;

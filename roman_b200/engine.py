@@ -135,6 +135,16 @@ class Engine:
         self._check(self._lib.rb_stored_tiles(self._h, _ptr(out), self._stream()))
         return out
 
+    def live_counts(self) -> torch.Tensor:
+        """(B,) int32: associations per problem that can carry an edge (single score not below affinityeps)."""
+        out = torch.zeros(max(self.B, 1), dtype=torch.int32, device=self.device)
+        self._check(self._lib.rb_live_counts(self._h, _ptr(out), self._stream()))
+        return out[:self.B]
+
+    def host_copy_bytes(self):
+        """(h2d, d2h) bytes moved by the last align_batch_host call."""
+        return int(self._lib.rb_host_copy_bytes(self._h, 0)), int(self._lib.rb_host_copy_bytes(self._h, 1))
+
     def edge_counts(self) -> torch.Tensor:
         """(B,) int32: edges K1 listed per problem (tile-skip format)."""
         out = torch.zeros(max(self.B, 1), dtype=torch.int32, device=self.device)

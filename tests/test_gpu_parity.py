@@ -125,6 +125,30 @@ def test_solver_cluster_sizes_agree_with_oracle(engine, coracle, cluster):
         engine.set_solver_cluster(0)
 
 
+@pytest.mark.parametrize("n1,n2,cluster", [(70, 70, 2), (64, 80, 2), (64, 80, 4), (64, 80, 1), (70, 73, 8)])
+def test_largest_problems_every_cluster_size(engine, coracle, n1, n2, cluster):
+    """m = 4900 / 5110 / 5120 (the largest m the solver's shared-memory layout takes): a 2-CTA cluster's slice
+    of the combined (M x, C x) vectors is 2560 entries — more than the 2304 the round-1 cluster_combine summed."""
+    ip_o, ip_g = params_for_method("gravity")
+    sp = cn.SolverParams()
+    p = synth.make_pair(77 + n2, n1, n2, method="gravity")
+    engine.set_solver_cluster(cluster)
+    try:
+        engine.set_invariant_params(ip_g)
+        engine.plan(3, [n1], [n2])
+        assert engine.solver_cluster == cluster
+        engine.affinity(p.D1.reshape(-1), p.D2.reshape(-1))
+        sol = engine.solve(p.u0, want_u=True)
+        Mo, _, A, _ = coracle.score(ip_o, sp.affinityeps, p.D1, p.D2)
+        ref = coracle.solve(sp, Mo, p.u0)
+        k = int(sol["n_nodes"][0])
+        assert sol["nodes"][:k].cpu().numpy().tolist() == ref["nodes"]
+        assert abs(float(sol["score"][0]) - ref["score"]) <= F_TOL
+        assert np.abs(sol["u"].cpu().numpy() - ref["u"]).max() <= 1e-9
+    finally:
+        engine.set_solver_cluster(0)
+
+
 def test_explicit_associations_euclidean(engine, coracle):
     """clipper+prune style: EuclideanDistance invariant on an arbitrary (pruned) association list."""
     rng = np.random.default_rng(5)
