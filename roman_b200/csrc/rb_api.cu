@@ -55,7 +55,7 @@ struct rb_handle {
   int32_t* d_streamed = nullptr;
   // solver queue order (longest problem first): d_order for whole-batch launches, d_order_chunks for the problem
   // ranges of the host entry point (entries are indices relative to the start of their range)
-  int32_t* d_order = nullptr; int32_t* d_order_chunks = nullptr; size_t cap_order = 0;
+  int32_t* d_order = nullptr; int32_t* d_order_chunks = nullptr; size_t cap_order = 0, cap_order_chunks = 0;
   int nch = 1;               // problem ranges of rb_align_batch_host (fixed at plan time)
   int bounds[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   // compact read-back of the inlier associations: the first kcap rows of every problem's `sel`
@@ -544,10 +544,7 @@ static int plan_impl(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, cons
     h->nch = nch;
     // queue orders: descending m (stable), for the whole batch and inside every range
     if ((rc = ensure(h, &h->d_order, &h->cap_order, (size_t)B))) return rc;
-    {
-      size_t dummy = h->d_order_chunks ? h->cap_order : 0;
-      if ((rc = ensure(h, &h->d_order_chunks, &dummy, (size_t)B))) return rc;
-    }
+    if ((rc = ensure(h, &h->d_order_chunks, &h->cap_order_chunks, (size_t)B))) return rc;
     std::vector<int32_t> ord((size_t)B), ordc((size_t)B);
     auto fill = [&](int b0, int b1, int32_t* out) {
       for (int i = b0; i < b1; ++i) out[i] = i - b0;
