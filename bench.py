@@ -481,7 +481,7 @@ def run_b200(args):
     value = world * B * K / (ms * 1e-3)
     passes = bw.res.n_passes.cpu().numpy().astype(np.int64)
     streamed = eng.solver_streamed_passes().cpu().numpy().astype(np.int64)   # passes that read M from HBM
-    promoted = int((eng.solver_resident().cpu().numpy()[:B] == 3).sum())
+    promoted = int((eng.solver_resident().cpu().numpy()[:B] >= 3).sum())
     live = eng.live_counts().cpu().numpy().astype(np.int64)
     cluster_dense = eng.solver_cluster
     packed_bytes = eng.packed_bytes

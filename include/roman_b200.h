@@ -207,16 +207,19 @@ int rb_get_solver_max_clusters(const rb_handle* h); /* co-resident clusters of t
  * Changing the format invalidates the plan: call rb_plan again (the solver's cluster size is chosen per format). */
 int rb_set_tile_skip(rb_handle* h, int32_t on);
 
-/* After rb_solve: device int32[B] — 0: the problem's stored tiles were streamed every pass; 1: resident mode, the
- * shared-memory CSR was built from one pass over the stored tiles; 2: resident mode, the CSR was built from the edge
- * list K1 wrote (no tile read at all). */
+/* After rb_solve: device int32[B] — 0: the problem's stored tiles were streamed every pass; 1: resident from the start
+ * (tile-skip format), the shared-memory CSR was built from one pass over the stored tiles; 2: resident from the start,
+ * the CSR was built from the edge list K1 wrote (no tile read at all); 3: dense format, promoted after
+ * rb_set_solver_promote streamed passes by one more (extraction) pass over the tiles; 4: dense format, promoted from
+ * K1's edge list (no extra pass). */
 int rb_solver_resident(rb_handle* h, int32_t* out, void* stream);
 
-/* Dense format only — late residency.  A problem that is still iterating after `passes` streamed passes of K2 reads its
- * tiles once more to extract the non-zero words into a shared-memory CSR and runs every later pass from there (if
- * they fit; otherwise it keeps streaming).  Slow-converging problems — tens of passes where a batch averages ~5 —
+/* Dense format only — late residency.  A problem that is still iterating after `passes` streamed passes of K2 builds a
+ * shared-memory CSR of its non-zero words — from the edge list K1 wrote beside the tiles (12 bytes per edge), or, for
+ * matrices given by rb_set_dense, by reading its tiles once more — and runs every later pass from there (if
+ * they fit: about 6-7 thousand edges per SM of the cluster at m = 2000; otherwise it keeps streaming).  Slow-converging problems — tens of passes where a batch averages ~5 —
  * would otherwise pin a cluster to tens of full streams of a matrix holding a few hundred edges.  Default 8;
- * 0 = never.  rb_solver_resident reports 3 for promoted problems.  Results agree with the unpromoted solve to
+ * 0 = never.  rb_solver_resident reports 3 / 4 for promoted problems.  Results agree with the unpromoted solve to
  * rounding (summation order), like the two storage formats do. */
 int rb_set_solver_promote(rb_handle* h, int32_t passes);
 
@@ -225,8 +228,8 @@ int rb_set_solver_promote(rb_handle* h, int32_t passes);
  * resident from the start).  n_passes of rb_solve counts ALL (M x, C x) evaluations regardless of where M came from. */
 int rb_solver_streamed_passes(rb_handle* h, int32_t* out, void* stream);
 
-/* Tile-skip format, after rb_affinity: edges (non-zero words of the strict upper triangle) K1 found per problem,
- * device int32[B]; a count above the list capacity (32 * ceil(m/32)) means the list overflowed and is not used. */
+/* After rb_affinity (both formats): edges (non-zero words of the strict upper triangle) K1 found per problem,
+ * device int32[B]; a count above the list capacity (8 * 32 * ceil(m/32)) means the list overflowed and is not used. */
 int rb_edge_counts(rb_handle* h, int32_t* out, void* stream);
 
 /* After rb_affinity: associations per problem that can carry an edge at all (not padding, single score not below

@@ -422,9 +422,9 @@ __global__ void __launch_bounds__(256) rb_block_mask_kernel(const RbProblem* __r
 //     memset); a live tile is written and flagged iff it ends up holding a non-zero word;
 //   dense format (flags == null): every tile of the packed upper triangle is written, dead ones as
 //     zeros with 16-byte stores.
-// Edge list of a problem (tile-skip format): every non-zero word of the strict upper triangle is also appended as a
-// triple (i << 16 | j, value) to the problem's list, capacity nb*32 entries; the count keeps growing past the
-// capacity so that the solver can tell an overflow (it then reads the tiles instead).
+// Edge list of a problem (both formats): every non-zero word of the strict upper triangle is also appended as a
+// triple (i << 16 | j, value) to the problem's list, capacity RB_EDGE_FACTOR * nb * 32 entries; the count keeps growing
+// past the capacity so that the solver can tell an overflow (it then reads the tiles instead).
 struct RbEdgeOut {
   unsigned* ij;
   double* v;
@@ -507,10 +507,10 @@ __global__ void __launch_bounds__(256) rb_affinity_kernel(const RbProblem* __res
   __syncthreads();
   const int nl = s_nl;
   RbEdgeOut eo;
-  eo.ij = edge_ij ? edge_ij + pr.off_pad : nullptr;
-  eo.v = edge_v ? edge_v + pr.off_pad : nullptr;
-  eo.count = (flags && edge_cnt) ? edge_cnt + blockIdx.y : nullptr;
-  eo.cap = nb * RB_TILE;
+  eo.ij = edge_ij ? edge_ij + (size_t)pr.off_pad * RB_EDGE_FACTOR : nullptr;
+  eo.v = edge_v ? edge_v + (size_t)pr.off_pad * RB_EDGE_FACTOR : nullptr;
+  eo.count = edge_cnt ? edge_cnt + blockIdx.y : nullptr;
+  eo.cap = RB_EDGE_FACTOR * nb * RB_TILE;
 
   if (flags) {
     // live x live block pairs only: pair index pi <-> (a <= b) over the live-block list
@@ -679,10 +679,10 @@ cudaError_t rb_launch_affinity(const RbProblem* probs, int B, int64_t tile_base,
   if (flags) {  // tile-skip format: dead tiles are never visited, so their flags are cleared up front
     cudaError_t e = cudaMemsetAsync(flags + tile_base, 0, (size_t)total_tiles, st);
     if (e != cudaSuccess) return e;
-    if (edge_cnt) {
-      e = cudaMemsetAsync(edge_cnt, 0, (size_t)B * sizeof(int), st);
-      if (e != cudaSuccess) return e;
-    }
+  }
+  if (edge_cnt) {
+    cudaError_t e = cudaMemsetAsync(edge_cnt, 0, (size_t)B * sizeof(int), st);
+    if (e != cudaSuccess) return e;
   }
   // CTAs per problem: enough warps to cover the largest problem's tiles a few per warp, and at least
   // ~8 CTAs per SM over the whole launch when there are few problems
@@ -694,8 +694,7 @@ cudaError_t rb_launch_affinity(const RbProblem* probs, int B, int64_t tile_base,
   if (per > cap) per = cap;
   if (per < 1) per = 1;
   dim3 grid((unsigned)per, (unsigned)B);
-  rb_affinity_kernel<<<grid, 256, 0, st>>>(probs, rec, masks, Mp, flags, flags ? edge_ij : nullptr, flags ? edge_v : nullptr,
-                                           flags ? edge_cnt : nullptr, P);
+  rb_affinity_kernel<<<grid, 256, 0, st>>>(probs, rec, masks, Mp, flags, edge_ij, edge_v, edge_cnt, P);
   return cudaGetLastError();
 }
 

@@ -289,7 +289,7 @@ int rb_set_tile_skip(rb_handle* h, int32_t on) {
 int rb_edge_counts(rb_handle* h, int32_t* out, void* stream) {
   if (!h || !out) return RB_ERR_ARG;
   if (!h->planned || !h->affinity_done) return fail(h, RB_ERR_NOPLAN, "rb_edge_counts before rb_affinity");
-  if (!h->tile_skip || !h->edges_valid) return fail(h, RB_ERR_ARG, "rb_edge_counts: no edge lists (dense format or rb_set_dense)");
+  if (!h->edges_valid) return fail(h, RB_ERR_ARG, "rb_edge_counts: no edge lists (matrix given by rb_set_dense)");
   if (h->B > 0)
     RB_CUDA(h, cudaMemcpyAsync(out, h->d_edge_cnt, (size_t)h->B * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return RB_OK;
@@ -468,8 +468,8 @@ static int plan_impl(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, cons
       if (h->d_edge_ij) cudaFree(h->d_edge_ij);
       if (h->d_edge_v) cudaFree(h->d_edge_v);
       h->d_edge_ij = nullptr; h->d_edge_v = nullptr;
-      RB_CUDA(h, cudaMalloc((void**)&h->d_edge_ij, n * sizeof(unsigned)));
-      RB_CUDA(h, cudaMalloc((void**)&h->d_edge_v, n * sizeof(double)));
+      RB_CUDA(h, cudaMalloc((void**)&h->d_edge_ij, (size_t)RB_EDGE_FACTOR * n * sizeof(unsigned)));
+      RB_CUDA(h, cudaMalloc((void**)&h->d_edge_v, (size_t)RB_EDGE_FACTOR * n * sizeof(double)));
       h->cap_pad = n;
     }
   }
@@ -627,7 +627,7 @@ int affinity_range(rb_handle* h, int b0, int b1, const double* D1, const double*
                                 rec, h->d_masks, h->d_M, h->tile_skip ? h->d_flags : nullptr, h->d_edge_ij, h->d_edge_v,
                                 h->d_edge_cnt + b0, P, h->sm_count, st));
   record(h, 2, st);
-  h->edges_valid = h->tile_skip;
+  h->edges_valid = true;  // K1 lists the edges in both formats
   h->masks_valid = true;
   return RB_OK;
 }
@@ -679,9 +679,9 @@ int solve_range(rb_handle* h, int b0, int b1, int queue, const int32_t* order, c
   a.probs = h->d_probs + b0; a.B = b1 - b0; a.counter = h->d_counter + queue; a.Mp = h->d_M;
   a.order = order;
   a.flags = h->tile_skip ? h->d_flags : nullptr;
-  a.edge_ij = (h->tile_skip && h->edges_valid) ? h->d_edge_ij : nullptr;
+  a.edge_ij = h->edges_valid ? h->d_edge_ij : nullptr;
   a.edge_v = h->d_edge_v;
-  a.edge_cnt = (h->tile_skip && h->edges_valid) ? h->d_edge_cnt + b0 : nullptr;
+  a.edge_cnt = h->edges_valid ? h->d_edge_cnt + b0 : nullptr;
   a.nt_max = (h->max_mp / RB_TILE) * (h->max_mp / RB_TILE + 1) / 2;
   a.i1 = h->d_pad_i32; a.i2 = h->d_pad_i32 + (size_t)h->total_pad;
   a.u0 = u0; a.u_work = u_work(h); a.g_work = g_work(h);

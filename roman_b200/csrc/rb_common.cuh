@@ -21,6 +21,8 @@
 #define RB_TILE 32
 #define RB_TILE_ELEMS (RB_TILE * RB_TILE)
 #define RB_TILE_BYTES (RB_TILE_ELEMS * 8)
+// K1's per-problem edge list holds up to RB_EDGE_FACTOR * (padded m) non-zero words of the strict upper triangle
+#define RB_EDGE_FACTOR 8
 
 // One problem of the batch (device-resident array of these, built by rb_plan).
 struct RbProblem {

@@ -18,9 +18,9 @@ struct RbSolveArgs {
   const double* Mp;        // packed tiles
   const uint8_t* flags;    // per stored tile: 1 = holds a non-zero word; null = every tile is streamed (dense mode)
   int32_t nt_max;          // max stored tiles of one problem (sizes the shared-memory copy of the flags)
-  const unsigned* edge_ij; // tile-skip format: K1's edge lists (padded per problem, i << 16 | j) ...
+  const unsigned* edge_ij; // K1's edge lists (RB_EDGE_FACTOR * nb * 32 slots per problem, i << 16 | j) ...
   const double* edge_v;    // ... their values ...
-  const int* edge_cnt;     // ... and counts (may exceed the capacity nb*32: overflow); null in the dense format
+  const int* edge_cnt;     // ... and counts (may exceed the capacity: overflow, list unusable); null = no lists
   const int32_t* i1;       // association object indices (padded arrays), for `sel`
   const int32_t* i2;
   const double* u0;        // user layout (off_assoc)
@@ -45,6 +45,7 @@ struct RbSolveArgs {
   int promote_after;       // dense format: after this many streamed passes try to make the problem resident (0 = never)
   rb_solver_params sp;
   int32_t mp_max;          // max padded m over the batch (sizes the shared-memory vectors)
+  int32_t smem_total;      // dynamic shared memory of the launch (the resident CSR uses everything past the vectors)
 };
 
 cudaError_t rb_launch_prep(const RbProblem* probs, int B, int max_mp, int max_n1, int max_n2, bool all_to_all,

@@ -109,7 +109,8 @@ struct Smem {
   int* c_rowptr;          // [mp+1] CSR row pointers over directed entries (both (i,j) and (j,i))
   uint16_t* c_col;        // [2*nnz] column index
   double* c_val;          // [2*nnz] value
-  int c_cap;              // capacity in undirected entries
+  int c_cap;              // capacity in undirected entries (CSR built from K1's edge list)
+  int c_cap_stage;        // capacity when the triples are staged in accM / accC first (extraction from tiles): <= mp
   double* c_ug;           // room for u and g (2 * mp doubles) next to the CSR, or null
   int slots;     // TMA ring slots per warp (1 or 2)
   int depth;     // tile-rows in flight between the fastest and slowest warp: 8 (decoupled) or 2 (lock-step)
@@ -402,13 +403,105 @@ __device__ __forceinline__ void build_tile_lists(const Smem& S, const uint8_t* _
   if (w == 0 && lane == 0) S.wcnt[NW] = nlive;
 }
 
+// Inclusive scan of rowptr[1..mp] (counts -> row ends), block-wide; rowptr[0] stays 0.
+__device__ __forceinline__ void csr_scan_rowptr(const Smem& S, int mp) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, tid = threadIdx.x;
+  int* rowptr = S.c_rowptr;
+  const int per = (mp + NT - 1) / NT;
+  const int lo = 1 + tid * per, hi = (lo + per <= mp + 1) ? lo + per : mp + 1;
+  int run = 0;
+  for (int i = lo; i < hi; ++i) run += rowptr[i];
+  int v = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int up = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += up;
+  }
+  int* wsum = reinterpret_cast<int*>(S.red + 48);  // 8 ints of scratch; no reduction is in flight here
+  if (lane == 31) wsum[w] = v;
+  __syncthreads();
+  int acc = v - run;  // exclusive prefix inside the warp ...
+#pragma unroll
+  for (int ww = 0; ww < NW; ++ww)
+    if (ww < w) acc += wsum[ww];  // ... plus the warps before
+  for (int i = lo; i < hi; ++i) { acc += rowptr[i]; rowptr[i] = acc; }
+  __syncthreads();
+}
+
+// Insertion sort of every CSR row by column: fixed summation order whatever order the entries arrived in.
+__device__ __forceinline__ void csr_sort_rows(const Smem& S, int mp) {
+  const int* rowptr = S.c_rowptr;
+  for (int i = threadIdx.x; i < mp; i += NT) {
+    const int b = rowptr[i], e = rowptr[i + 1];
+    for (int a = b + 1; a < e; ++a) {
+      const uint16_t c = S.c_col[a];
+      const double v = S.c_val[a];
+      int q = a - 1;
+      while (q >= b && S.c_col[q] > c) { S.c_col[q + 1] = S.c_col[q]; S.c_val[q + 1] = S.c_val[q]; --q; }
+      S.c_col[q + 1] = c; S.c_val[q + 1] = v;
+    }
+  }
+  __syncthreads();
+}
+
+// Resident CSR straight from the edge list K1 wrote (HBM / L2; 12 bytes per edge), without staging: one pass counts the
+// row lengths, a scan turns them into row pointers, a second pass scatters, rows are sorted by column.  With C > 1 a CTA
+// takes the edges of ITS tile-rows only (the split of matvec_pass_dense) — or, with C == 1 passed for a cluster, all of
+// them.  Returns false (all threads agree) if the entries exceed the capacity.
+__device__ __forceinline__ bool build_csr_from_list(const Smem& S, int nb, int mp, const unsigned* __restrict__ e_ij,
+                                                    const double* __restrict__ e_v, int e_n, int C, int crank) {
+  const int tid = threadIdx.x;
+  int* rowptr = S.c_rowptr;             // [mp + 1]
+  int* cursor = S.c_rowptr + (mp + 1);  // [mp]
+  int* n_mine = S.misc + 14;
+  const int npairs = (nb + 1) >> 1;
+  auto mine = [&](unsigned ij) -> bool {
+    if (C == 1) return true;
+    const int I = (int)(ij >> 16) / RB_TILE;
+    const int pr_ = I < npairs ? I : nb - 1 - I;  // tile-row pair index (see the matvec work split)
+    return (pr_ % C) == crank;
+  };
+  for (int i = tid; i <= mp; i += NT) rowptr[i] = 0;
+  for (int i = tid; i < mp; i += NT) cursor[i] = 0;
+  if (tid == 0) *n_mine = 0;
+  __syncthreads();
+  int cnt = 0;
+  for (int e = tid; e < e_n; e += NT) {
+    const unsigned ij = e_ij[e];
+    if (mine(ij)) {
+      atomicAdd(&rowptr[(ij >> 16) + 1], 1);
+      atomicAdd(&rowptr[(ij & 0xffffu) + 1], 1);
+      ++cnt;
+    }
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if ((tid & 31) == 0 && cnt) atomicAdd(n_mine, cnt);
+  __syncthreads();
+  if (*n_mine > S.c_cap) return false;
+  csr_scan_rowptr(S, mp);
+  for (int e = tid; e < e_n; e += NT) {
+    const unsigned ij = e_ij[e];
+    if (!mine(ij)) continue;
+    const int i = ij >> 16, j = ij & 0xffffu;
+    const double v = e_v[e];
+    int p = rowptr[i] + atomicAdd(&cursor[i], 1);
+    S.c_col[p] = (uint16_t)j; S.c_val[p] = v;
+    p = rowptr[j] + atomicAdd(&cursor[j], 1);
+    S.c_col[p] = (uint16_t)i; S.c_val[p] = v;
+  }
+  __syncthreads();
+  csr_sort_rows(S, mp);
+  return true;
+}
+
+
 // Second half of the resident build: the staged triples (accM: values, accC: i << 16 | j; count in misc[14]) become a
 // CSR over both directions in the ring space.  Returns false (all threads agree) if they exceed the capacity.
 __device__ __forceinline__ bool finish_compact(const Smem& S, int mp) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, tid = threadIdx.x;
+  const int tid = threadIdx.x;
   const double* tv = S.accM;
   const unsigned* tij = reinterpret_cast<const unsigned*>(S.accC);
-  const int cap = S.c_cap;
+  const int cap = S.c_cap_stage;
   const int n = S.misc[14];
   if (n > cap) return false;
 
@@ -424,27 +517,7 @@ __device__ __forceinline__ bool finish_compact(const Smem& S, int mp) {
     atomicAdd(&rowptr[(ij & 0xffffu) + 1], 1);
   }
   __syncthreads();
-  {  // inclusive scan of rowptr[1..mp]: each thread owns a contiguous run; warp scan of the run totals; warp offsets
-    const int per = (mp + NT - 1) / NT;
-    const int lo = 1 + tid * per, hi = (lo + per <= mp + 1) ? lo + per : mp + 1;
-    int run = 0;
-    for (int i = lo; i < hi; ++i) run += rowptr[i];
-    int v = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int up = __shfl_up_sync(0xffffffffu, v, o);
-      if (lane >= o) v += up;
-    }
-    int* wsum = reinterpret_cast<int*>(S.red + 48);  // 8 ints of scratch; no reduction is in flight here
-    if (lane == 31) wsum[w] = v;
-    __syncthreads();
-    int acc = v - run;  // exclusive prefix inside the warp ...
-#pragma unroll
-    for (int ww = 0; ww < NW; ++ww)
-      if (ww < w) acc += wsum[ww];  // ... plus the warps before
-    for (int i = lo; i < hi; ++i) { acc += rowptr[i]; rowptr[i] = acc; }
-  }
-  __syncthreads();
+  csr_scan_rowptr(S, mp);
   for (int e = tid; e < n; e += NT) {
     const unsigned ij = tij[e];
     const int i = ij >> 16, j = ij & 0xffffu;
@@ -455,19 +528,10 @@ __device__ __forceinline__ bool finish_compact(const Smem& S, int mp) {
     S.c_col[p] = (uint16_t)i; S.c_val[p] = v;
   }
   __syncthreads();
-  for (int i = tid; i < mp; i += NT) {  // insertion sort of each row by column: fixed summation order
-    const int b = rowptr[i], e = rowptr[i + 1];
-    for (int a = b + 1; a < e; ++a) {
-      const uint16_t c = S.c_col[a];
-      const double v = S.c_val[a];
-      int q = a - 1;
-      while (q >= b && S.c_col[q] > c) { S.c_col[q + 1] = S.c_col[q]; S.c_val[q + 1] = S.c_val[q]; --q; }
-      S.c_col[q + 1] = c; S.c_val[q + 1] = v;
-    }
-  }
-  __syncthreads();
+  csr_sort_rows(S, mp);
   return true;
 }
+
 
 // ---- resident (compact) form --------------------------------------------------------------------
 // In the tile-skip format a problem often has only a few hundred edges.  Then this CTA's share of
@@ -488,7 +552,7 @@ __device__ __forceinline__ bool build_compact(const Smem& S, const double* __res
   // staging area for the triples: accM (values) and accC (packed i << 16 | j), both unused until the first pass
   double* tv = S.accM;
   unsigned* tij = reinterpret_cast<unsigned*>(S.accC);
-  const int cap = S.c_cap;
+  const int cap = S.c_cap_stage;
   int* n_coo = S.misc + 14;
   if (tid == 0) *n_coo = 0;
   __syncthreads();
@@ -560,7 +624,7 @@ __device__ __forceinline__ bool build_compact_dense(const Smem& S, const double*
   double* ring = S.ring + (size_t)w * SLOTS * RB_TILE_ELEMS;
   double* tv = S.accM;
   unsigned* tij = reinterpret_cast<unsigned*>(S.accC);
-  const int cap = S.c_cap;
+  const int cap = S.c_cap_stage;
   int* n_coo = S.misc + 14;
   if (tid == 0) *n_coo = 0;
   __syncthreads();
@@ -675,15 +739,16 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem S;
   {
+    // Layout: vectors and small state first, then the TMA rings and the partial ring, then whatever is left of the
+    // SM's shared memory (the launch always asks for the device maximum).  The resident CSR overlays everything from
+    // the rings on: once a problem is resident neither rings nor partials are in use.
     const size_t mp = (size_t)A.mp_max;
     unsigned char* p = smem_raw;
     S.slots = A.slots;
     S.depth = A.depth;
-    S.ring = (double*)p; p += (size_t)NW * A.slots * RB_TILE_BYTES;
     S.x = (double*)p; p += mp * 8;
     S.accM = (double*)p; p += mp * 8;
     S.accC = (double*)p; p += mp * 8;
-    S.part = (double*)p; p += (size_t)A.depth * NW * 2 * RB_TILE * 8;
     S.red = (double*)p; p += (size_t)RED_DOUBLES * 8;
     S.bar = (uint64_t*)p; p += (size_t)NW * MAX_SLOTS * 8;
     S.misc = (int*)p; p += (size_t)MISC_INTS * 4;
@@ -691,26 +756,29 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
     const int nbm = A.mp_max / RB_TILE;
     S.wl_cap = (A.nt_max + NW - 1) / NW + nbm;
     S.wlist = A.flags ? (uint16_t*)p : nullptr; p += (size_t)NW * S.wl_cap * 2;
-    S.live_rows = (uint8_t*)p;
+    S.live_rows = (uint8_t*)p; p += (size_t)((nbm + 15) / 16) * 16;
+    p = smem_raw + (((size_t)(p - smem_raw) + 127) / 128) * 128;
+    S.ring = (double*)p; p += (size_t)NW * A.slots * RB_TILE_BYTES;
+    S.part = (double*)p; p += (size_t)A.depth * NW * 2 * RB_TILE * 8;
     {
-      // resident CSR lives in the TMA ring space (idle once the tiles have been read): row pointers + cursors,
-      // then values, then columns; capacity in undirected entries is also bounded by the triple staging area
-      // (accM/accC: mp entries each)
+      // resident CSR: row pointers + cursors, then (if they fit) u and g, then values, then columns
       unsigned char* q = (unsigned char*)S.ring;
-      const size_t ring_bytes = (size_t)NW * A.slots * RB_TILE_BYTES;
+      const size_t region = (size_t)A.smem_total - (size_t)(q - smem_raw);
       S.c_rowptr = (int*)q;
       const size_t head = (((size_t)(2 * mp + 1) * 4 + 15) / 16) * 16;
       const size_t ug = (size_t)2 * mp * 8;
-      size_t room = ring_bytes > head ? ring_bytes - head : 0;
+      size_t room = region > head ? region - head : 0;
       const bool ug_fits = room >= ug + 512 * 2 * (8 + 2);  // keep u, g in shared memory too if >= 512 edges still fit
       if (ug_fits) room -= ug;
       int cap = (int)(room / (2 * (8 + 2)));       // 2 directed entries of (double + uint16) per edge
-      if (cap > (int)mp) cap = (int)mp;
       if (cap > 32767) cap = 32767;
-      S.c_cap = (A.flags || A.promote_after > 0) ? cap : 0;
-      S.c_val = (double*)(q + head);
-      S.c_col = (uint16_t*)(q + head + (size_t)2 * cap * 8);
-      S.c_ug = ug_fits ? (double*)(q + head + ((((size_t)2 * cap * (8 + 2)) + 15) / 16) * 16) : nullptr;
+      const bool any_resident = (A.flags || A.promote_after > 0);
+      S.c_cap = any_resident ? cap : 0;
+      S.c_cap_stage = any_resident ? (cap < (int)mp ? cap : (int)mp) : 0;  // triples staged in accM / accC: mp entries
+      S.c_ug = ug_fits ? (double*)(q + head) : nullptr;
+      unsigned char* v0 = q + head + (ug_fits ? ug : 0);
+      S.c_val = (double*)v0;
+      S.c_col = (uint16_t*)(v0 + (size_t)2 * cap * 8);
     }
   }
   const int tid = threadIdx.x;
@@ -749,37 +817,56 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
     const double* u0 = A.u0 + pr.off_assoc;
     int passes = 0;
     long long tb0 = clock64();
-    // tile-skip format: problems whose edges K1 has listed (count within capacity) are built straight from that
-    // list and need no tile lists at all; the others walk their stored tiles
-    const int e_n = (A.edge_cnt != nullptr) ? A.edge_cnt[b] : -1;
-    const bool listed = (A.edge_ij != nullptr) && e_n >= 0 && e_n <= mp && e_n <= S.c_cap;
-    if (A.flags && !listed) {
-      build_tile_lists(S, A.flags + pr.off_tile, nb, C, crank);
-      __syncthreads();
-    }
-    bool compact = false;
-
     if (m == 0) {
       if (lead && tid == 0) {
         A.n_nodes[b] = 0; A.score[b] = 0.0; A.ifinal[b] = 0; A.n_passes[b] = 0; A.resident[b] = 0; A.streamed[b] = 0;
       }
       continue;
     }
+    // K1 lists every non-zero word of the strict upper triangle (12 bytes per edge, capacity RB_EDGE_FACTOR * mp per
+    // problem; a count above the capacity means the list overflowed and is not used).
+    const int e_n = (A.edge_cnt != nullptr) ? A.edge_cnt[b] : -1;
+    const bool have_list = (A.edge_ij != nullptr) && e_n >= 0 && e_n <= RB_EDGE_FACTOR * mp;
+    const unsigned* e_ij = have_list ? A.edge_ij + (size_t)pr.off_pad * RB_EDGE_FACTOR : nullptr;
+    const double* e_v = have_list ? A.edge_v + (size_t)pr.off_pad * RB_EDGE_FACTOR : nullptr;
+    bool compact = false;   // passes run from the shared-memory CSR
+    bool solo = false;      // C > 1 and every CTA holds the WHOLE matrix: nothing to combine, no cluster barrier per pass
+    bool from_list = false;
 
-    // tile-skip format: try to make this CTA's share of the matrix resident (read from HBM once)
-    if (A.flags && m > 0) {
-      compact = build_compact(S, tiles, nb, mp, phase, listed ? A.edge_ij + pr.off_pad : nullptr,
-                              listed ? A.edge_v + pr.off_pad : nullptr, listed ? e_n : -1, C, crank);
-      if (C > 1) {  // every CTA of the cluster must run the same kind of pass (they combine their partials)
-        cluster.sync();
-        if (tid == 0) S.misc[15] = compact ? 1 : 0;
-        cluster.sync();
-        bool all = true;
-        for (int r = 0; r < C; ++r) all = all && (*cluster.map_shared_rank(S.misc + 15, r) != 0);
-        cluster.sync();
-        compact = all;
+    // all CTAs of a cluster must run the same kind of pass: unanimous vote over distributed shared memory
+    auto cluster_all = [&](bool mine_ok) -> bool {
+      if (C == 1) return mine_ok;
+      cluster.sync();
+      if (tid == 0) S.misc[15] = mine_ok ? 1 : 0;
+      cluster.sync();
+      bool all = true;
+      for (int r = 0; r < C; ++r) all = all && (*cluster.map_shared_rank(S.misc + 15, r) != 0);
+      cluster.sync();
+      return all;
+    };
+    // resident CSR from K1's edge list: the whole matrix in every CTA if it fits (then the CTAs of a cluster run the
+    // problem redundantly without exchanging anything), else each CTA's share of the tile-rows
+    auto try_list = [&]() -> bool {
+      if (!have_list || S.c_cap == 0) return false;
+      if (e_n <= S.c_cap) {
+        build_csr_from_list(S, nb, mp, e_ij, e_v, e_n, 1, 0);
+        solo = (C > 1);
+        return true;
       }
-      if (compact && S.c_ug) {  // resident mode leaves room in the ring space for the iterate and its gradient
+      if (C == 1) return false;
+      return cluster_all(build_csr_from_list(S, nb, mp, e_ij, e_v, e_n, C, crank));
+    };
+
+    // tile-skip format: make the matrix resident up front (read from HBM once) — from the edge list, else from one
+    // pass over this CTA's stored tiles; problems that fit neither way stream their stored tiles every pass
+    if (A.flags) {
+      compact = from_list = try_list();
+      if (!compact) {
+        build_tile_lists(S, A.flags + pr.off_tile, nb, C, crank);
+        __syncthreads();
+        compact = cluster_all(build_compact(S, tiles, nb, mp, phase, nullptr, nullptr, -1, C, crank));
+      }
+      if (compact && S.c_ug) {  // resident mode leaves room for the iterate and its gradient
         u = S.c_ug;
         g = S.c_ug + mp;
       }
@@ -792,20 +879,21 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
     int streamed = 0;      // passes that read the packed matrix from HBM
     bool promoted = false;
     auto run_pass = [&]() {
-      // dense format: a problem still iterating after `promote_after` streamed passes becomes resident (see
-      // build_compact_dense).  accM / accC were cleared for this pass, so they are free to stage the triples.
+      // dense format, late residency: a problem still iterating after `promote_after` streamed passes finishes from the
+      // shared-memory CSR — built from K1's edge list, else by one more pass over the tiles (build_compact_dense; accM /
+      // accC were cleared for this pass, so they are free to stage the triples).
       if (!compact && !A.flags && A.promote_after > 0 && passes == A.promote_after) {
         const long long tb = clock64();
-        bool ok = build_compact_dense(S, tiles, nb, mp, phase, C, crank);
-        ++streamed;
-        if (C > 1) {  // all CTAs of the cluster must run the same kind of pass
-          cluster.sync();
-          if (tid == 0) S.misc[15] = ok ? 1 : 0;
-          cluster.sync();
-          bool all = true;
-          for (int r = 0; r < C; ++r) all = all && (*cluster.map_shared_rank(S.misc + 15, r) != 0);
-          cluster.sync();
-          ok = all;
+        bool ok = try_list();
+        from_list = ok;
+        if (!ok && S.c_cap_stage > 0) {
+          ok = cluster_all(build_compact_dense(S, tiles, nb, mp, phase, C, crank));
+          ++streamed;
+        }
+        if (ok && S.c_ug) {  // iterate and gradient move into shared memory with the matrix
+          for (int i = tid; i < mp; i += NT) { S.c_ug[i] = (i < m) ? u[i] : 0.0; S.c_ug[mp + i] = (i < m) ? g[i] : 0.0; }
+          u = S.c_ug;
+          g = S.c_ug + mp;
         }
         for (int i = tid; i < mp; i += NT) { S.accM[i] = 0.0; S.accC[i] = 0.0; }
         __syncthreads();
@@ -817,7 +905,8 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
       const long long t1 = clock64();
       ++passes;
       if (!compact) ++streamed;
-      cluster_combine(S, mp, C, crank);
+      if (solo) __syncthreads();
+      else cluster_combine(S, mp, C, crank);
       t_mv += t1 - t0;
       t_cb += clock64() - t1;
     };
@@ -1049,8 +1138,8 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
       A.score[b] = F;
       A.ifinal[b] = i_ol;
       A.n_passes[b] = passes;
-      A.resident[b] = promoted ? 3 : (compact ? (listed ? 2 : 1) : 0);
-      A.streamed[b] = streamed + ((compact && !promoted && !listed) ? 1 : 0);  // + the one tile pass of build_compact
+      A.resident[b] = promoted ? (from_list ? 4 : 3) : (compact ? (from_list ? 2 : 1) : 0);
+      A.streamed[b] = streamed + ((compact && !promoted && !from_list) ? 1 : 0);  // + the one tile pass of build_compact
     }
     t_round += clock64() - tr0;
   }
@@ -1067,9 +1156,10 @@ size_t rb_solver_smem_bytes(int mp_max, int slots, int depth) {
   const int nb = mp_max / RB_TILE;
   const size_t nt = (size_t)nb * (nb + 1) / 2;
   const size_t wl_cap = (nt + NW - 1) / NW + nb;  // tile-skip format: per-warp tile lists + live tile-rows
+  // minimum: vectors, small state, tile lists, (alignment), rings, partial ring — see the carve-up in the kernel
   return (size_t)NW * slots * RB_TILE_BYTES + (size_t)3 * mp_max * 8 + (size_t)depth * NW * 2 * RB_TILE * 8 +
          (size_t)RED_DOUBLES * 8 + (size_t)NW * MAX_SLOTS * 8 + (size_t)MISC_INTS * 4 + (size_t)NW * wl_cap * 2 +
-         (size_t)((nb + 15) / 16) * 16 + 16;
+         (size_t)((nb + 15) / 16) * 16 + 128;
 }
 
 // Largest shared-memory configuration that fits: (2 slots, depth 8) > (2, 2) > (1, 2).
@@ -1112,14 +1202,19 @@ cudaError_t rb_solver_max_clusters(int mp_max, int cluster, int* out) {
   cudaLaunchAttribute attr[1];
   int slots = 1, depth = 2;
   if (!rb_solver_config(mp_max, g_max_optin, &slots, &depth)) return cudaErrorInvalidValue;
-  fill_config(cfg, attr, cluster, cluster, rb_solver_smem_bytes(mp_max, slots, depth), nullptr);
+  // the launch always takes the device's whole opt-in shared memory (one CTA per SM either way): what the vectors
+  // and rings leave over extends the resident CSR
+  fill_config(cfg, attr, cluster, cluster, g_max_optin, nullptr);
   return cudaOccupancyMaxActiveClusters(out, rb_solver_kernel, &cfg);
 }
 
-cudaError_t rb_launch_solver(const RbSolveArgs& a, int max_clusters, cudaStream_t st) {
-  if (a.B == 0) return cudaSuccess;
-  const size_t smem = rb_solver_smem_bytes(a.mp_max, a.slots, a.depth);
+cudaError_t rb_launch_solver(const RbSolveArgs& a_in, int max_clusters, cudaStream_t st) {
+  if (a_in.B == 0) return cudaSuccess;
+  RbSolveArgs a = a_in;
+  size_t smem = rb_solver_smem_bytes(a.mp_max, a.slots, a.depth);
   if (g_max_optin && smem > g_max_optin) return cudaErrorInvalidValue;
+  if (g_max_optin > smem) smem = g_max_optin;
+  a.smem_total = (int32_t)smem;
   if (a.mp_max > EPT_MAX * NT) return cudaErrorInvalidValue;
   int nclusters = a.B < max_clusters ? a.B : max_clusters;
   if (nclusters < 1) nclusters = 1;

@@ -149,6 +149,38 @@ def test_largest_problems_every_cluster_size(engine, coracle, n1, n2, cluster):
         engine.set_solver_cluster(0)
 
 
+@pytest.mark.parametrize("cluster", [1, 2, 4])
+def test_resident_csr_split_over_a_cluster(engine, coracle, cluster):
+    """~9 thousand edges at m = 2000 (method 'gravity'): more than one SM's shared-memory CSR holds, so with a cluster
+    every CTA builds the CSR of ITS tile-rows from K1's edge list and the partial products are combined each pass;
+    with one CTA per problem the matrix keeps streaming.  Either way: the oracle's answer."""
+    ip_o, ip_g = params_for_method("gravity")
+    sp = cn.SolverParams()
+    pairs = [synth.make_pair(11 + i, 40, 50, method="gravity") for i in range(3)]
+    engine.set_solver_cluster(cluster)
+    engine.set_solver_promote(2)
+    try:
+        engine.set_invariant_params(ip_g)
+        engine.plan(3, [40] * 3, [50] * 3)
+        engine.affinity(np.concatenate([p.D1.reshape(-1) for p in pairs]), np.concatenate([p.D2.reshape(-1) for p in pairs]))
+        sol = engine.solve(np.concatenate([p.u0 for p in pairs]), want_u=True)
+        kinds = engine.solver_resident().cpu().numpy()[:3]
+        edges = engine.edge_counts().cpu().numpy()[:3]
+        for b, p in enumerate(pairs):
+            Mo, _, A, nnz = coracle.score(ip_o, sp.affinityeps, p.D1, p.D2)
+            assert nnz == edges[b] and 7000 < nnz < 8 * 2016
+            ref = coracle.solve(sp, Mo, p.u0)
+            o, k = int(engine.offsets[b]), int(sol["n_nodes"][b])
+            assert sol["nodes"][o:o + k].cpu().numpy().tolist() == ref["nodes"]
+            assert abs(float(sol["score"][b]) - ref["score"]) <= F_TOL
+            assert np.abs(sol["u"][o:o + 2000].cpu().numpy() - ref["u"]).max() <= 1e-9
+        if cluster > 1:
+            assert (kinds == (2 if engine.default_tile_skip else 4)).all(), kinds
+    finally:
+        engine.set_solver_cluster(0)
+        engine.set_solver_promote(8)
+
+
 def test_explicit_associations_euclidean(engine, coracle):
     """clipper+prune style: EuclideanDistance invariant on an arbitrary (pruned) association list."""
     rng = np.random.default_rng(5)
@@ -478,9 +510,9 @@ def test_exact_dsd_rounding_on_a_broad_support(engine):
 
 @pytest.mark.parametrize("cluster", [1, 2, 4])
 def test_late_residency_promotion_in_the_dense_format(engine, coracle, cluster):
-    """rb_set_solver_promote: after N streamed passes a still-iterating problem is extracted into the shared-memory CSR.
-    Same answers as the oracle; the resident / streamed-pass reports say what happened; problems whose edges do not fit
-    keep streaming."""
+    """rb_set_solver_promote: after N streamed passes a still-iterating problem finishes from the shared-memory CSR (built
+    from K1's edge list, or extracted from the tiles when there is none).  Same answers as the oracle; the resident /
+    streamed-pass reports say what happened; problems whose edges do not fit keep streaming."""
     if engine.default_tile_skip:
         pytest.skip("promotion belongs to the dense format (the tile-skip format is resident from the start)")
     ip_o, ip_g = params_for_method("roman", semantics_dim=40)
@@ -504,7 +536,8 @@ def test_late_residency_promotion_in_the_dense_format(engine, coracle, cluster):
         assert (res0 == 0).all() and np.array_equal(str0, s0["n_passes"])
         assert np.array_equal(s2["n_passes"], s0["n_passes"]) and np.array_equal(s2["n_nodes"], s0["n_nodes"])
         long_running = s0["n_passes"] > 2
-        assert long_running.any() and (res2[long_running] == 3).all() and (str2[long_running] == 3).all()
+        # promoted from K1's edge list (code 4): exactly the 2 streamed passes before the promotion, no extraction pass
+        assert long_running.any() and (res2[long_running] == 4).all() and (str2[long_running] == 2).all()
         assert np.abs(s2["u"] - s0["u"]).max() <= 1e-9 and np.abs(s2["score"] - s0["score"]).max() <= F_TOL
         for b, p in enumerate(pairs):
             Mo, _, _, _ = coracle.score(ip_o, sp.affinityeps, p.D1, p.D2)
@@ -512,18 +545,33 @@ def test_late_residency_promotion_in_the_dense_format(engine, coracle, cluster):
             o, n = int(engine.offsets[b]), int(s2["n_nodes"][b])
             assert s2["nodes"][o:o + n].tolist() == ref["nodes"]
             assert np.abs(s2["u"][o:o + len(p.u0)] - ref["u"]).max() <= 1e-9
-        # a geometry-only graph is far too dense for the shared-memory CSR: the extraction fails, streaming goes on
+        # a matrix handed in by set_matrix_data has no edge list: the promotion extracts the non-zero words from the
+        # tiles with one more streamed pass (code 3)
+        b = int(np.argmax(s0["n_passes"]))
+        p = pairs[b]
+        Mo, _, _, _ = coracle.score(ip_o, sp.affinityeps, p.D1, p.D2)
+        ref = coracle.solve(sp, Mo, p.u0)
+        engine.set_solver_promote(2)
+        engine.plan(p.D1.shape[1], [shapes[b][0]], [shapes[b][1]])
+        engine.set_dense(0, Mo + Mo.T + np.eye(len(p.u0)))
+        sol = engine.solve(p.u0, want_u=True)
+        k = int(sol["n_nodes"][0])
+        assert sol["nodes"][:k].cpu().numpy().tolist() == ref["nodes"]
+        assert np.abs(sol["u"].cpu().numpy() - ref["u"]).max() <= 1e-9
+        assert int(engine.solver_resident()[0]) == 3 and int(engine.solver_streamed_passes()[0]) == 3
+        # a geometry-only graph at m = 2000 overflows the edge list and is far too dense for the shared-memory CSR:
+        # the extraction fails, streaming goes on
         ip_o2, ip_g2 = params_for_method("clipper")
-        p = synth.make_pair(3, 30, 30, method="clipper")
+        p = synth.make_pair(3, 40, 50, method="clipper")
         engine.set_invariant_params(ip_g2)
         engine.set_solver_promote(3)
-        engine.plan(3, [30], [30])
+        engine.plan(3, [40], [50])
         engine.affinity(p.D1.reshape(-1), p.D2.reshape(-1))
         sol = engine.solve(p.u0)
         Mo, _, _, nnz = coracle.score(ip_o2, sp.affinityeps, p.D1, p.D2)
         ref = coracle.solve(sp, Mo, p.u0)
         k = int(sol["n_nodes"][0])
-        assert nnz > 2000 and sol["nodes"][:k].cpu().numpy().tolist() == ref["nodes"]
+        assert nnz > 8 * 2016 and sol["nodes"][:k].cpu().numpy().tolist() == ref["nodes"]
         assert int(engine.solver_resident()[0]) == 0
         assert int(engine.solver_streamed_passes()[0]) == int(sol["n_passes"][0]) + 1      # + the failed extraction pass
     finally:

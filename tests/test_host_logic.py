@@ -279,7 +279,7 @@ def test_shim_covers_every_clipperpy_use_of_the_reference():
 
 
 def test_bench_reference_arm_contract():
-    """`bench.py --impl reference` (the CPU restatement timed on the host cores) needs no GPU, prints exactly one JSON
+    """`bench.py --impl reference` (the reference algorithm timed on the host cores) needs no GPU, prints exactly one JSON
     line on stdout and carries the keys the driver reads."""
     import json
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -291,7 +291,8 @@ def test_bench_reference_arm_contract():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "alignments/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    from oracle import ref as oref      # "reference" when oracle/_ref (the reference's own sources) was built, else the port
+    assert d["cpu_baseline"]["kind"] == ("reference" if oref.available() else "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"]
 
