@@ -54,6 +54,9 @@ typedef enum {
 /* Which invariant scores the pairs. */
 #define RB_INVARIANT_ROMAN 0     /* clipper::invariants::ROMAN      (pairwise + single) */
 #define RB_INVARIANT_EUCLIDEAN 1 /* clipper::invariants::EuclideanDistance (pairwise)   */
+#define RB_INVARIANT_ROMAN_PAIRWISE 2 /* the ROMAN invariant scored through CLIPPER::scorePairwiseConsistency
+                                         (clipper/src/clipper.cpp:29-73): ROMAN::operator() is pairwise_similarity alone —
+                                         no single-association scores, no single-score gate, no fusion (abstract.h:99-102) */
 
 /* POD mirror of clipper::invariants::ROMAN::Params (clipper/include/clipper/invariants/roman.h:27-53)
  * and EuclideanDistance::Params (euclidean_distance.h:24-29; uses sigma, epsilon, mindist only). */

@@ -40,7 +40,7 @@ SQRT_ONE_THIRD = 0.57735026919   # roman.cpp:12
 @dataclass
 class InvariantParams:
     """clipper/include/clipper/invariants/roman.h:27-53 (+ kind selector)."""
-    kind: int = 0  # 0 ROMAN, 1 EuclideanDistance
+    kind: int = 0  # 0 ROMAN (pairwise + single), 1 EuclideanDistance, 2 ROMAN through scorePairwiseConsistency (pairwise only)
     point_dim: int = 3
     ratio_feature_dim: int = 0
     cos_feature_dim: int = 0
@@ -197,6 +197,9 @@ def score(p: InvariantParams, affinityeps: float, D1: np.ndarray, D2: np.ndarray
                 pw = _pairwise_roman(p, ai, aj, bi, bj)
                 sc = _fusion(p, pw, single[r0:r1, None], single[None, :])
                 gate = ~((single[r0:r1, None] < affinityeps) | (single[None, :] < affinityeps))
+            elif p.kind == 2:  # ROMAN::operator() = pairwise_similarity (abstract.h:99-102), clipper.cpp:59
+                sc = _pairwise_roman(p, ai, aj, bi, bj)
+                gate = np.ones(sc.shape, dtype=bool)
             else:
                 sc = _pairwise_euclid(p, ai, aj, bi, bj)
                 gate = np.ones(sc.shape, dtype=bool)

@@ -56,7 +56,7 @@
 #define SQRT_ONE_THIRD 0.57735026919
 
 typedef struct {
-  int32_t kind;              /* 0 = ROMAN (pairwise + single), 1 = EuclideanDistance */
+  int32_t kind;              /* 0 = ROMAN (pairwise + single), 1 = EuclideanDistance, 2 = ROMAN via scorePairwiseConsistency */
   int32_t point_dim;         /* roman.h:29 */
   int32_t ratio_feature_dim; /* roman.h:30 */
   int32_t cos_feature_dim;   /* roman.h:31 */
@@ -281,6 +281,8 @@ int orc_score(const orc_invariant_params *ip, double affinityeps, int d, int n1,
       if (single_sim[i] < affinityeps || single_sim[j] < affinityeps) continue;
       const double pw = orc_pairwise_similarity(ip, cos_unc, sin_unc, d1i, d1j, d2i, d2j);
       scr = orc_pairwise_single_fusion(ip, pw, single_sim[i], single_sim[j]);
+    } else if (ip->kind == 2) { /* the ROMAN invariant through scorePairwiseConsistency: operator() = pairwise_similarity */
+      scr = orc_pairwise_similarity(ip, cos_unc, sin_unc, d1i, d1j, d2i, d2j);
     } else {
       scr = orc_euclidean(ip, d, d1i, d1j, d2i, d2j);
     }

@@ -13,6 +13,7 @@ RB_MAX_RATIO_FEATURES = 8
 
 RB_INVARIANT_ROMAN = 0
 RB_INVARIANT_EUCLIDEAN = 1
+RB_INVARIANT_ROMAN_PAIRWISE = 2
 RB_PAIR_OK = 0
 RB_PAIR_INSUFFICIENT = 1
 

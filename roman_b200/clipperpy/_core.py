@@ -105,7 +105,7 @@ class CLIPPER:
         sp.rescale_u0, sp.rounding = int(bool(p.rescale_u0)), int(p.rounding)
         return sp
 
-    def _score(self, D1, D2, A):
+    def _score(self, D1, D2, A, pairwise_only=False):
         inv = self._invariant
         if not hasattr(inv, "_rb_params"):
             raise NotImplementedError(
@@ -119,7 +119,12 @@ class CLIPPER:
         assert D2.shape[1] == d
         A = np.asarray(A) if A is not None else np.zeros((0, 2), dtype=np.int32)
         e = self._eng()
-        e.set_invariant_params(inv._rb_params())
+        ip = inv._rb_params()
+        if pairwise_only and ip.kind == 0:
+            # CLIPPER::scorePairwiseConsistency calls invariant->operator(), which for a PairwiseAndSingleInvariant is
+            # pairwise_similarity alone (abstract.h:99-102): no single scores, no single-score gate, no fusion
+            ip.kind = 2
+        e.set_invariant_params(ip)
         e.set_solver_params(self._solver_params())
         if A.size == 0:  # clipper.cpp:32,81: empty A => all-to-all
             self._A = create_all_to_all(n1, n2)
@@ -135,7 +140,7 @@ class CLIPPER:
     # ------------------------------------------------------------------ reference API
     def score_pairwise_consistency(self, D1, D2, A=None):
         """CLIPPER::scorePairwiseConsistency (clipper.cpp:29-73)."""
-        self._score(D1, D2, A)
+        self._score(D1, D2, A, pairwise_only=True)
 
     def solve(self, u0=None):
         """CLIPPER::solve (clipper.cpp:140-149): u0 empty => U[0,1) random start (utils.cpp:22-29)."""

@@ -114,6 +114,8 @@ __device__ __forceinline__ double pair_score(const RbDevParams& P, const Rec& i,
     if (i.s < P.affinityeps || j.s < P.affinityeps) return 0.0;
     const double pw = pairwise_roman(P, i, j);
     scr = fusion(P, pw, i.s, j.s);
+  } else if (P.inv.kind == RB_INVARIANT_ROMAN_PAIRWISE) {  // scorePairwiseConsistency: ROMAN::operator() (abstract.h:99-102)
+    scr = pairwise_roman(P, i, j);
   } else {
     scr = pairwise_euclid(P, i, j);
   }
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(256) rb_prep_kernel(const RbProblem* __restric
                      1.0 / (p.ratio_weight + p.cosine_weight));
     }
     if (lane == 0) {
-      const int pd = (p.kind == RB_INVARIANT_ROMAN) ? p.point_dim : (pr.d < 3 ? pr.d : 3);
+      const int pd = (p.kind != RB_INVARIANT_EUCLIDEAN) ? p.point_dim : (pr.d < 3 ? pr.d : 3);
       rec.ax[o] = a[0];
       rec.ay[o] = pd > 1 ? a[1] : 0.0;
       rec.az[o] = pd > 2 ? a[2] : 0.0;
@@ -211,33 +213,52 @@ __global__ void __launch_bounds__(256) rb_prep_kernel(const RbProblem* __restric
 
 
 // ---------------------------------------------------------------------------------------------
-// K1a for all-to-all plans: the n1 x n2 cosine table is a small dense contraction
-// (descriptors^T * descriptors), so it is tiled through shared memory instead of re-reading two
-// D-vectors per association.  One CTA per (<=64) x (<=64) block of (object of map 1, object of map
-// 2); the thread grid is TY x TX with 4x4 outputs per thread, sized to the batch's largest maps
-// (40 x 50 objects -> 10 x 13 threads), descriptors streamed once in chunks of 32 columns and kept
-// k-major in shared memory so that a thread's four operands are one 32-byte load.  Each dot product
-// and squared norm is accumulated sequentially over the descriptor index (the order of the scalar
-// loop of the reference's restatement) with fused multiply-adds: one rounding per term instead of
-// two, i.e. at least as accurate as the reference's own (compiler-contracted, vectorised) sums.
-constexpr int PT = 64;        // max objects per tile edge
-constexpr int PK = 32;        // descriptor columns per chunk
-constexpr int PLD = PT + 2;   // shared-memory row length (doubles): rows stay 16-byte aligned
+// K1a for all-to-all plans: the n1 x n2 cosine table is a small dense contraction (descriptors^T * descriptors) and
+// is evaluated as one, instead of re-reading two D-vectors per association.
+//
+// One CTA per (<= 64) x (<= 64) block of (object of map 1, object of map 2).  The thread grid is TY x TX with 4 x 4
+// outputs per thread (rows ty + r*TY of map 1, columns tx + c*TX of map 2), sized to the batch's largest maps
+// (40 x 50 objects -> 10 x 13 threads = 5 warps; three such CTAs share an SM).
+//
+// Staging: descriptor columns [k0, k0 + 32) of all rows of the block form one stage ([row][k], 34 doubles per row); a
+// ring of PREP_STAGES stages is filled with asynchronous global->shared copies (cp.async, 8 bytes each — SASS LDGSTS)
+// issued two stages ahead, so HBM latency is hidden behind the fp64 work of the stages in between and the main loop
+// has ONE block barrier per 32 columns.  Why not the bulk / TMA form the solver uses for its 8 KB tiles: object rows
+// are d = 3 + r + D doubles long (775 for the `roman` method, odd), so every other row starts 8 bytes off a 16-byte
+// boundary; cp.async.bulk and tensor maps both need 16-byte aligned sources and strides.
+//
+// Arithmetic: each dot product and squared norm is accumulated sequentially over the descriptor index (the order of
+// the scalar loop) with fused multiply-adds, exactly as in round 1 — one thread owns an output from k = 0 to D - 1,
+// nothing is split or tree-reduced, so the cosine gate `<= cosine_min` sees bit-identical inputs.  Operands come from
+// shared memory as 16-byte pairs (k, k+1): 8 loads per 32 FMAs.
+constexpr int PT = 64;            // max objects per block edge
+constexpr int PREP_KC = 32;       // descriptor columns per stage
+constexpr int PREP_LD = PREP_KC + 2;  // shared-memory row length (doubles): rows 16-byte aligned, consecutive rows hit different bank groups
+constexpr int PREP_STAGES = 3;
+
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __global__ void __launch_bounds__(256) rb_prep_table_kernel(const RbProblem* __restrict__ probs, RbAssocSoA rec,
                                                             const double* __restrict__ D1,
                                                             const double* __restrict__ D2, RbDevParams P,
                                                             int tiles2_max, int TY, int TX) {
-  __shared__ __align__(16) double As[PK][PLD];
-  __shared__ __align__(16) double Bs[PK][PLD];
-  __shared__ double s_na[PT], s_nb[PT];
+  extern __shared__ __align__(16) unsigned char prep_smem[];
   const RbProblem pr = probs[blockIdx.y];
   const rb_invariant_params& p = P.inv;
-  const int PT1 = 4 * TY, PT2 = 4 * TX;
+  const int PT1 = 4 * TY, PT2 = 4 * TX, R = PT1 + PT2;
+  double* stage0 = reinterpret_cast<double*>(prep_smem);                // [PREP_STAGES][R][PREP_LD]
+  double* s_na = stage0 + (size_t)PREP_STAGES * R * PREP_LD;            // [PT1]
+  double* s_nb = s_na + PT1;                                            // [PT2]
+  const int NTH = blockDim.x;
   const int t1 = blockIdx.x / tiles2_max, t2 = blockIdx.x % tiles2_max;
   const int i1_0 = t1 * PT1, i2_0 = t2 * PT2;
-  const int tid = threadIdx.x;  // always 256 threads: TY*TX of them compute, all of them stage data
+  const int tid = threadIdx.x;
   if (blockIdx.x == 0) {  // padding records of this problem
-    for (int k = pr.m + tid; k < pr.nb * RB_TILE; k += 256) {
+    for (int k = pr.m + tid; k < pr.nb * RB_TILE; k += NTH) {
       const int64_t o = pr.off_pad + k;
       rec.ax[o] = rec.ay[o] = rec.az[o] = rec.bx[o] = rec.by[o] = rec.bz[o] = 0.0;
       rec.single[o] = 0.0;
@@ -252,9 +273,25 @@ __global__ void __launch_bounds__(256) rb_prep_table_kernel(const RbProblem* __r
   const double* B0 = D2 + pr.off_obj2 * (int64_t)pr.d;
   const int foff = p.point_dim + p.ratio_feature_dim;
   const int Dc = (p.kind == RB_INVARIANT_ROMAN) ? p.cos_feature_dim : 0;
-  // the squared norms of the 4*TX map-2 objects are accumulated by the threads of thread-row 0
-  // only, those of the map-1 objects by thread-column 0 only
+  const int nchunks = (Dc + PREP_KC - 1) / PREP_KC;
+  // the squared norms of the map-2 objects are accumulated by the threads of thread-row 0 only, those of the map-1
+  // objects by thread-column 0 only
   const bool do_nb = active && ty == 0, do_na = active && tx == 0;
+
+  // rows of the block that exist: stage row q < PT1 is object i1_0 + q of map 1, q >= PT1 object i2_0 + q - PT1 of map 2
+  auto issue = [&](int c) {  // asynchronous copies of chunk c into stage c % PREP_STAGES (rows / columns that do not exist: zeros)
+    double* st = stage0 + (size_t)(c % PREP_STAGES) * R * PREP_LD;
+    const int k0 = c * PREP_KC;
+    for (int e = tid; e < R * PREP_KC; e += NTH) {  // consecutive threads -> consecutive columns of one row: coalesced
+      const int q = e / PREP_KC, k = e % PREP_KC;
+      const bool is1 = q < PT1;
+      const int o = is1 ? i1_0 + q : i2_0 + q - PT1;
+      const bool ok = (k0 + k) < Dc && (is1 ? o < pr.n1 : o < pr.n2);
+      double* dst = st + q * PREP_LD + k;
+      if (ok) cp_async_8(dst, (is1 ? A0 : B0) + (int64_t)o * pr.d + foff + k0 + k);
+      else *dst = 0.0;
+    }
+  };
 
   double acc[4][4];
   double na[4] = {0, 0, 0, 0}, nb[4] = {0, 0, 0, 0};
@@ -263,115 +300,111 @@ __global__ void __launch_bounds__(256) rb_prep_table_kernel(const RbProblem* __r
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
 
-  // Software pipeline: while chunk c is consumed from shared memory, chunk c+1 is already in flight
-  // from HBM into registers (each of the 256 threads carries at most 8 + 8 elements of a chunk).
-  constexpr int NLD = PT * PK / 256;
-  double ra_[NLD], rb_[NLD];
-  auto fetch = [&](int k0) {
-#pragma unroll
-    for (int j = 0; j < NLD; ++j) {
-      const int e = tid + j * 256;  // coalesced along the descriptor index
-      const int o = e / PK, k = e % PK;
-      const bool kin = (k0 + k) < Dc;
-      ra_[j] = (e < PT1 * PK && kin && i1_0 + o < pr.n1) ? A0[(int64_t)(i1_0 + o) * pr.d + foff + k0 + k] : 0.0;
-      rb_[j] = (e < PT2 * PK && kin && i2_0 + o < pr.n2) ? B0[(int64_t)(i2_0 + o) * pr.d + foff + k0 + k] : 0.0;
-    }
-  };
-  auto stage = [&]() {
-#pragma unroll
-    for (int j = 0; j < NLD; ++j) {
-      const int e = tid + j * 256;
-      const int o = e / PK, k = e % PK;
-      if (e < PT1 * PK) As[k][o] = ra_[j];
-      if (e < PT2 * PK) Bs[k][o] = rb_[j];
-    }
-  };
-  if (Dc > 0) fetch(0);
-  for (int k0 = 0; k0 < Dc; k0 += PK) {
-    __syncthreads();  // everybody is done reading the previous chunk
-    stage();
-    __syncthreads();
-    if (k0 + PK < Dc) fetch(k0 + PK);
+  for (int c = 0; c < PREP_STAGES - 1; ++c) {
+    if (c < nchunks) issue(c);
+    cp_async_commit();
+  }
+#pragma unroll 1
+  for (int c = 0; c < nchunks; ++c) {
+    cp_async_wait<PREP_STAGES - 2>();  // this thread's copies of chunk c have landed ...
+    __syncthreads();                   // ... and everybody's; also: everybody is done with the stage refilled next
+    if (c + PREP_STAGES - 1 < nchunks) issue(c + PREP_STAGES - 1);
+    cp_async_commit();
     if (active) {
-      const int kend = (Dc - k0) < PK ? (Dc - k0) : PK;
-      for (int k = 0; k < kend; ++k) {
-        const double2 a01 = *reinterpret_cast<const double2*>(&As[k][ty * 4]);
-        const double2 a23 = *reinterpret_cast<const double2*>(&As[k][ty * 4 + 2]);
-        const double2 b01 = *reinterpret_cast<const double2*>(&Bs[k][tx * 4]);
-        const double2 b23 = *reinterpret_cast<const double2*>(&Bs[k][tx * 4 + 2]);
-        const double a[4] = {a01.x, a01.y, a23.x, a23.y};
-        const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+      const double* st = stage0 + (size_t)(c % PREP_STAGES) * R * PREP_LD;
+      const double* pa = st + ty * PREP_LD;
+      const double* pb = st + (PT1 + tx) * PREP_LD;
+#pragma unroll 4
+      for (int k = 0; k < PREP_KC; k += 2) {
+        double2 a[4], b[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a[r] = *reinterpret_cast<const double2*>(pa + r * TY * PREP_LD + k);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) b[q] = *reinterpret_cast<const double2*>(pb + q * TX * PREP_LD + k);
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) acc[r][c] = fma(a[r], b[c], acc[r][c]);
+          for (int q = 0; q < 4; ++q) acc[r][q] = fma(a[r].x, b[q].x, acc[r][q]);
         if (do_na)
 #pragma unroll
-          for (int r = 0; r < 4; ++r) na[r] = fma(a[r], a[r], na[r]);
+          for (int r = 0; r < 4; ++r) na[r] = fma(a[r].x, a[r].x, na[r]);
         if (do_nb)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) nb[c] = fma(b[c], b[c], nb[c]);
+          for (int q = 0; q < 4; ++q) nb[q] = fma(b[q].x, b[q].x, nb[q]);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[r][q] = fma(a[r].y, b[q].y, acc[r][q]);
+        if (do_na)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) na[r] = fma(a[r].y, a[r].y, na[r]);
+        if (do_nb)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) nb[q] = fma(b[q].y, b[q].y, nb[q]);
       }
     }
   }
   __syncthreads();
   if (do_na)
 #pragma unroll
-    for (int r = 0; r < 4; ++r) s_na[ty * 4 + r] = na[r];
+    for (int r = 0; r < 4; ++r) s_na[ty + r * TY] = na[r];
   if (do_nb)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) s_nb[tx * 4 + c] = nb[c];
+    for (int q = 0; q < 4; ++q) s_nb[tx + q * TX] = nb[q];
   __syncthreads();
   if (!active) return;
 
-  const int pd = (p.kind == RB_INVARIANT_ROMAN) ? p.point_dim : (pr.d < 3 ? pr.d : 3);
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int i1 = i1_0 + ty * 4 + r;
-    if (i1 >= pr.n1) continue;
+  const int pd = (p.kind != RB_INVARIANT_EUCLIDEAN) ? p.point_dim : (pr.d < 3 ? pr.d : 3);
+  // 16 outputs per thread, one instance of the scoring code (pow is long)
+#pragma unroll 1
+  for (int rq = 0; rq < 16; ++rq) {
+    const int r = rq >> 2, q = rq & 3;
+    const int l1 = ty + r * TY, l2 = tx + q * TX;
+    const int i1 = i1_0 + l1, i2 = i2_0 + l2;
+    if (i1 >= pr.n1 || i2 >= pr.n2) continue;
     const double* a = A0 + (int64_t)i1 * pr.d;
-    const double a0 = a[0], a1 = pd > 1 ? a[1] : 0.0, a2 = pd > 2 ? a[2] : 0.0;
+    const double* b = B0 + (int64_t)i2 * pr.d;
+    double dotv = 0.0;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int i2 = i2_0 + tx * 4 + c;
-      if (i2 >= pr.n2) continue;
-      const double* b = B0 + (int64_t)i2 * pr.d;
-      double single = 1.0;
-      if (p.kind == RB_INVARIANT_ROMAN && (p.cos_feature_dim > 0 || p.ratio_feature_dim > 0)) {  // roman.cpp:116-164
-        bool zero = false;
-        double cos_scaled = 0.0, ratio_score = 0.0;
-        if (p.cos_feature_dim > 0) {
-          const double cs = acc[r][c] / (sqrt(s_na[ty * 4 + r]) * sqrt(s_nb[tx * 4 + c]));
-          if (cs >= p.cosine_max) cos_scaled = 1.0;
-          else if (cs <= p.cosine_min) zero = true;
-          else cos_scaled = (cs - p.cosine_min) / (p.cosine_max - p.cosine_min);
-        }
-        if (!zero && p.ratio_feature_dim > 0) {
-          double prod = 1.0;
-          bool below = false;
-          for (int t = 0; t < p.ratio_feature_dim; ++t) {
-            const double x = a[p.point_dim + t], y = b[p.point_dim + t];
-            const double q = x < y ? x / y : y / x;
-            if (q < p.ratio_epsilon[t]) below = true;
-            prod *= q;
-          }
-          if (below) zero = true;
-          else ratio_score = pow(prod, 1.0 / p.ratio_feature_dim);
-        }
-        if (zero) single = 0.0;
-        else if (p.ratio_feature_dim == 0) single = cos_scaled;
-        else if (p.cos_feature_dim == 0) single = ratio_score;
-        else
-          single = pow(pow(ratio_score, p.ratio_weight) * pow(cos_scaled, p.cosine_weight),
-                       1.0 / (p.ratio_weight + p.cosine_weight));
+    for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq)
+        if (rr == r && qq == q) dotv = acc[rr][qq];  // register select: acc[][] must not be indexed dynamically
+    double single = 1.0;
+    if (p.kind == RB_INVARIANT_ROMAN && (p.cos_feature_dim > 0 || p.ratio_feature_dim > 0)) {  // roman.cpp:116-164
+      bool zero = false;
+      double cos_scaled = 0.0, ratio_score = 0.0;
+      if (p.cos_feature_dim > 0) {
+        const double cs = dotv / (sqrt(s_na[l1]) * sqrt(s_nb[l2]));
+        if (cs >= p.cosine_max) cos_scaled = 1.0;
+        else if (cs <= p.cosine_min) zero = true;
+        else cos_scaled = (cs - p.cosine_min) / (p.cosine_max - p.cosine_min);
       }
-      const int64_t o = pr.off_pad + (int64_t)i1 * pr.n2 + i2;  // utils::createAllToAll order
-      rec.ax[o] = a0; rec.ay[o] = a1; rec.az[o] = a2;
-      rec.bx[o] = b[0]; rec.by[o] = pd > 1 ? b[1] : 0.0; rec.bz[o] = pd > 2 ? b[2] : 0.0;
-      rec.single[o] = single;
-      rec.i1[o] = i1;
-      rec.i2[o] = i2;
+      if (!zero && p.ratio_feature_dim > 0) {
+        double prod = 1.0;
+        bool below = false;
+        for (int t = 0; t < p.ratio_feature_dim; ++t) {
+          const double x = a[p.point_dim + t], y = b[p.point_dim + t];
+          const double qv = x < y ? x / y : y / x;
+          if (qv < p.ratio_epsilon[t]) below = true;
+          prod *= qv;
+        }
+        if (below) zero = true;
+        else ratio_score = pow(prod, 1.0 / p.ratio_feature_dim);
+      }
+      if (zero) single = 0.0;
+      else if (p.ratio_feature_dim == 0) single = cos_scaled;
+      else if (p.cos_feature_dim == 0) single = ratio_score;
+      else
+        single = pow(pow(ratio_score, p.ratio_weight) * pow(cos_scaled, p.cosine_weight),
+                     1.0 / (p.ratio_weight + p.cosine_weight));
     }
+    const int64_t o = pr.off_pad + (int64_t)i1 * pr.n2 + i2;  // utils::createAllToAll order
+    rec.ax[o] = a[0]; rec.ay[o] = pd > 1 ? a[1] : 0.0; rec.az[o] = pd > 2 ? a[2] : 0.0;
+    rec.bx[o] = b[0]; rec.by[o] = pd > 1 ? b[1] : 0.0; rec.bz[o] = pd > 2 ? b[2] : 0.0;
+    rec.single[o] = single;
+    rec.i1[o] = i1;
+    rec.i2[o] = i2;
   }
 }
 
@@ -445,14 +478,24 @@ __device__ __forceinline__ void affinity_tile(const RbProblem& pr, int I, int J,
   __syncwarp();
   const bool diag = (I == J);
   bool any_nz = false;
-#pragma unroll 4
+  // One instance of the scoring code, no unrolling: the transcendental paths (exp, pow) are long, and several copies
+  // of them made the kernel's instruction footprint (~250 KB of SASS) thrash the instruction cache — 76 % of the
+  // warp stalls of the round-1 kernel on dense graphs were "no instruction".
+#pragma unroll 1
   for (int r = 0; r < RB_TILE; ++r) {
     double v = 0.0;
-    if (((row_live >> r) & 1u) && ((col_live >> lane) & 1u)) {
+    if (((row_live >> r) & 1u) && ((col_live >> lane) & 1u) && !(diag && r == lane)) {  // r == lane: implicit identity (clipper.cpp:129-130)
       const Rec row = s_row[r];
-      if (!diag || r < lane) v = pair_score(P, row, col);       // i = row index < j = column index
-      else if (r > lane) v = pair_score(P, col, row);           // mirrored entry of the diagonal tile
-      // r == lane: identity is implicit (clipper.cpp:129-130)
+      // i = the association with the smaller index: the row, except for the mirrored half of a diagonal tile
+      const bool mirrored = diag && r > lane;
+      Rec a, b;
+      a.ax = mirrored ? col.ax : row.ax; a.ay = mirrored ? col.ay : row.ay; a.az = mirrored ? col.az : row.az;
+      a.bx = mirrored ? col.bx : row.bx; a.by = mirrored ? col.by : row.by; a.bz = mirrored ? col.bz : row.bz;
+      a.s = mirrored ? col.s : row.s; a.i1 = mirrored ? col.i1 : row.i1; a.i2 = mirrored ? col.i2 : row.i2;
+      b.ax = mirrored ? row.ax : col.ax; b.ay = mirrored ? row.ay : col.ay; b.az = mirrored ? row.az : col.az;
+      b.bx = mirrored ? row.bx : col.bx; b.by = mirrored ? row.by : col.by; b.bz = mirrored ? row.bz : col.bz;
+      b.s = mirrored ? row.s : col.s; b.i1 = mirrored ? row.i1 : col.i1; b.i2 = mirrored ? row.i2 : col.i2;
+      v = pair_score(P, a, b);
     }
     any_nz |= (v != 0.0);
     out[rb_tile_elem(r, lane)] = v;
@@ -512,34 +555,33 @@ __global__ void __launch_bounds__(256) rb_affinity_kernel(const RbProblem* __res
   eo.count = edge_cnt ? edge_cnt + blockIdx.y : nullptr;
   eo.cap = RB_EDGE_FACTOR * nb * RB_TILE;
 
-  if (flags) {
-    // live x live block pairs only: pair index pi <-> (a <= b) over the live-block list
-    const int npairs = nl * (nl + 1) / 2;
-    for (int pi = blockIdx.x * 8 + warp; pi < npairs; pi += gridDim.x * 8) {
-      // invert pi = a*nl - a(a-1)/2 + (b - a)
-      int a = (int)floor(((2.0 * nl + 1.0) - sqrt((2.0 * nl + 1.0) * (2.0 * nl + 1.0) - 8.0 * (double)pi)) * 0.5);
+  // Work items: tile-skip format — live x live block pairs only (pair index <-> (a <= b) over the live-block list; dead
+  // tiles are never touched); dense format — every tile of the packed upper triangle, dead ones written as zeros.
+  const int nwork = flags ? nl * (nl + 1) / 2 : (int)pr.n_tiles;
+#pragma unroll 1
+  for (int wi = blockIdx.x * 8 + warp; wi < nwork; wi += gridDim.x * 8) {
+    int I, J;
+    if (flags) {
+      // invert wi = a*nl - a(a-1)/2 + (b - a)
+      int a = (int)floor(((2.0 * nl + 1.0) - sqrt((2.0 * nl + 1.0) * (2.0 * nl + 1.0) - 8.0 * (double)wi)) * 0.5);
       if (a < 0) a = 0;
       if (a > nl - 1) a = nl - 1;
-      while (a > 0 && a * nl - a * (a - 1) / 2 > pi) --a;
-      while (a + 1 < nl && (a + 1) * nl - (a + 1) * a / 2 <= pi) ++a;
-      const int bcol = a + (pi - (a * nl - a * (a - 1) / 2));
-      const int I = s_live[a], J = s_live[bcol];
-      affinity_tile(pr, I, J, s_mask[I], s_mask[J], rec, s_row[warp], Mp, flags, eo, P, lane);
+      while (a > 0 && a * nl - a * (a - 1) / 2 > wi) --a;
+      while (a + 1 < nl && (a + 1) * nl - (a + 1) * a / 2 <= wi) ++a;
+      const int bcol = a + (wi - (a * nl - a * (a - 1) / 2));
+      I = s_live[a];
+      J = s_live[bcol];
+    } else {
+      tile_coords(wi, nb, I, J);
     }
-  } else {
-    const int nt = (int)pr.n_tiles;
-    for (int q = blockIdx.x * 8 + warp; q < nt; q += gridDim.x * 8) {
-      int I, J;
-      tile_coords(q, nb, I, J);
-      const unsigned row_live = s_mask[I], col_live = s_mask[J];
-      if (row_live == 0u || col_live == 0u) {
-        double2* o2 = reinterpret_cast<double2*>(Mp + (pr.off_tile + q) * RB_TILE_ELEMS);
+    const unsigned row_live = s_mask[I], col_live = s_mask[J];
+    if (row_live == 0u || col_live == 0u) {  // dense format only: a dead tile is all zeros
+      double2* o2 = reinterpret_cast<double2*>(Mp + (pr.off_tile + wi) * RB_TILE_ELEMS);
 #pragma unroll
-        for (int t = 0; t < RB_TILE_ELEMS / 2 / 32; ++t) o2[t * 32 + lane] = make_double2(0.0, 0.0);
-        continue;
-      }
-      affinity_tile(pr, I, J, row_live, col_live, rec, s_row[warp], Mp, nullptr, eo, P, lane);
+      for (int t = 0; t < RB_TILE_ELEMS / 2 / 32; ++t) o2[t * 32 + lane] = make_double2(0.0, 0.0);
+      continue;
     }
+    affinity_tile(pr, I, J, row_live, col_live, rec, s_row[warp], Mp, flags, eo, P, lane);
   }
 }
 
@@ -654,7 +696,15 @@ cudaError_t rb_launch_prep(const RbProblem* probs, int B, int max_mp, int max_n1
     const int t1 = (max_n1 + 4 * TY - 1) / (4 * TY), t2 = (max_n2 + 4 * TX - 1) / (4 * TX);
     if ((int64_t)t1 * t2 <= 65535 * 32) {
       dim3 grid((unsigned)(t1 * t2 > 0 ? t1 * t2 : 1), B);
-      rb_prep_table_kernel<<<grid, 256, 0, st>>>(probs, rec, D1, D2, P, t2 > 0 ? t2 : 1, TY, TX);
+      const int nth = ((TY * TX + 31) / 32) * 32;
+      const size_t smem = ((size_t)PREP_STAGES * (4 * TY + 4 * TX) * PREP_LD + 4 * TY + 4 * TX) * sizeof(double);
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(rb_prep_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+      }
+      rb_prep_table_kernel<<<grid, nth, smem, st>>>(probs, rec, D1, D2, P, t2 > 0 ? t2 : 1, TY, TX);
       return cudaGetLastError();
     }
   }

@@ -231,8 +231,9 @@ int rb_device_sm_count(const rb_handle* h) { return h ? h->sm_count : 0; }
 
 int rb_set_invariant_params(rb_handle* h, const rb_invariant_params* p) {
   if (!h || !p) return RB_ERR_ARG;
-  if (p->kind != RB_INVARIANT_ROMAN && p->kind != RB_INVARIANT_EUCLIDEAN) return fail(h, RB_ERR_ARG, "unknown invariant kind");
-  if (p->kind == RB_INVARIANT_ROMAN) {
+  if (p->kind != RB_INVARIANT_ROMAN && p->kind != RB_INVARIANT_EUCLIDEAN && p->kind != RB_INVARIANT_ROMAN_PAIRWISE)
+    return fail(h, RB_ERR_ARG, "unknown invariant kind");
+  if (p->kind != RB_INVARIANT_EUCLIDEAN) {
     if (p->point_dim != 2 && p->point_dim != 3) return fail(h, RB_ERR_ARG, "point_dim must be 2 or 3");
     if (p->gravity_guided && p->point_dim != 3) return fail(h, RB_ERR_ARG, "gravity_guided requires point_dim == 3");
     if (p->ratio_feature_dim < 0 || p->ratio_feature_dim > RB_MAX_RATIO_FEATURES)
@@ -529,6 +530,10 @@ static int plan_impl(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, cons
     }
     if (nw >= 1 && B >= 2 * nw) nch = nw;
     else nw = 0;
+    // ranges exist to overlap the upload with the kernels: with little to upload (shared object tables, small maps)
+    // one range — one launch sequence, one solver tail — is faster
+    const double h2d_bytes = 8.0 * ((double)(off1 ? tot1 : o1) + (double)(off2 ? tot2 : o2)) * d + 8.0 * (double)oa + (m ? 8.0 * (double)oa : 0.0);
+    if (!getenv("RB_HOST_SPLIT") && h2d_bytes < 24.0e6) { nch = 1; nw = 0; }
     // ranges are cut by WORK (tiles), not by problem count: ragged batches arrive longest-first
     double tot = 0.0, acc = 0.0;
     for (int c = 0; c < nch; ++c) tot += nw ? wts[c] : 1.0;
@@ -605,7 +610,7 @@ int check_affinity_args(rb_handle* h, const double* D1, const double* D2, const 
   if (!D1 || !D2) return fail(h, RB_ERR_ARG, "rb_affinity: null feature table");
   if (!h->all_to_all && !A) return fail(h, RB_ERR_ARG, "rb_affinity: plan has explicit associations but A is null");
   const rb_invariant_params& p = h->inv;
-  if (p.kind == RB_INVARIANT_ROMAN) {
+  if (p.kind != RB_INVARIANT_EUCLIDEAN) {
     if (h->d < p.point_dim + p.ratio_feature_dim + p.cos_feature_dim)
       return fail(h, RB_ERR_ARG, "rb_affinity: row length d smaller than point_dim + ratio_feature_dim + cos_feature_dim");
   } else if (h->d > 3) {
@@ -715,7 +720,7 @@ int solve_range(rb_handle* h, int b0, int b1, int queue, const int32_t* order, c
 int arun_range(rb_handle* h, int b0, int b1, const double* D1, const double* D2, const int32_t* sel,
                const int32_t* n_sel, double* T, int32_t* status, bool pack_sel, cudaStream_t st) {
   if (b1 <= b0) return RB_OK;
-  const int pd = h->inv.kind == RB_INVARIANT_ROMAN ? h->inv.point_dim : (h->d < 3 ? h->d : 3);
+  const int pd = h->inv.kind != RB_INVARIANT_EUCLIDEAN ? h->inv.point_dim : (h->d < 3 ? h->d : 3);
   if (pd < 2) return fail(h, RB_ERR_ARG, "rb_arun: point dimension must be 2 or 3");
   record(h, 5, st);
   RB_CUDA(h, rb_launch_arun(h->d_probs + b0, b1 - b0, pd, D1, D2, sel, n_sel + b0, (T ? T : h->d_T) + (size_t)b0 * 16,

@@ -49,6 +49,33 @@ def test_reference_kat_through_clipperpy(engine):
     assert all(M[a, b] == 1 for a in c.get_solution().nodes for b in c.get_solution().nodes)
 
 
+def test_roman_invariant_through_score_pairwise_consistency(engine, coracle):
+    """clipperpy.CLIPPER.score_pairwise_consistency with a ROMAN invariant: pairwise_similarity alone, no single scores
+    and no fusion (clipper.cpp:59 calls invariant->operator(); abstract.h:99-102) — what the base
+    ObjectRegistration.get_MCA computes with a ROMAN invariant."""
+    import copy
+    from roman_b200 import clipperpy
+    ip_o, _ = params_for_method("roman", semantics_dim=16)
+    ip_o = copy.copy(ip_o)
+    ip_o.kind = 2
+    p = synth.make_pair(91, 11, 13, method="roman", semantics_dim=16, desc_common=1.0)
+    rp = clipperpy.invariants.ROMANParams()
+    rp.point_dim, rp.ratio_feature_dim, rp.cos_feature_dim = 3, 4, 16
+    rp.sigma, rp.epsilon, rp.mindist = ip_o.sigma, ip_o.epsilon, ip_o.mindist
+    rp.ratio_epsilon = np.zeros(4)
+    rp.cosine_min, rp.cosine_max = ip_o.cosine_min, ip_o.cosine_max
+    rp.gravity_guided, rp.gravity_unc_ang_rad = True, ip_o.gravity_unc_ang_rad
+    c = clipperpy.CLIPPER(clipperpy.invariants.ROMAN(rp), clipperpy.Params())
+    c.score_pairwise_consistency(p.D1.T, p.D2.T, clipperpy.utils.create_all_to_all(11, 13))
+    Mo, _, A, _ = coracle.score(ip_o, 1e-4, p.D1, p.D2)
+    Mfull = Mo + Mo.T + np.eye(len(A))
+    Mg = c.get_affinity_matrix()
+    assert np.array_equal(Mg != 0, Mfull != 0) and np.abs(Mg - Mfull).max() <= 1e-12
+    c.solve(p.u0)
+    ref = coracle.solve(cn.SolverParams(), Mo, p.u0)
+    assert c.get_solution().nodes == ref["nodes"]
+
+
 def test_oracle_vectors_through_registration_classes(engine):
     """Committed fixtures (tests/golden/oracle_vectors.json): ObjectRegistration.register / T_align."""
     from roman_b200.align import SubmapAlignParams

@@ -207,3 +207,23 @@ def test_set_matrix_data_path_equals_the_restatement(R, coracle):
         o = coracle.solve(sp, Mu, u0, Cupper=Cu)
         assert r["nodes"] == o["nodes"] and abs(r["score"] - o["score"]) <= 1e-12
         assert np.abs(r["u"] - o["u"]).max() <= 1e-12
+
+
+def test_roman_invariant_through_score_pairwise_consistency(R, coracle):
+    """CLIPPER::scorePairwiseConsistency with a ROMAN invariant evaluates pairwise_similarity alone (abstract.h:99-102):
+    no single scores, no fusion — the base ObjectRegistration._clipper_score_all_to_all / get_MCA path.  kind = 2 of
+    the restatements against the reference's own code."""
+    import copy
+    ip, _ = params_for_method("roman", semantics_dim=16)
+    sp = cn.SolverParams()
+    for seed in range(3):
+        p = synth.make_pair(90 + seed, 11, 13, method="roman", semantics_dim=16, desc_common=1.0)
+        Mr, Cr = R.score(ip, sp, p.D1, p.D2, pairwise_only=True)
+        ip2 = copy.copy(ip)
+        ip2.kind = 2
+        Mo, _, A, _ = coracle.score(ip2, sp.affinityeps, p.D1, p.D2)
+        Mn, _, _ = cn.score(ip2, sp.affinityeps, p.D1, p.D2)
+        assert np.array_equal(Mr, Mo + Mo.T + np.eye(len(A)))
+        assert np.abs(Mo - Mn).max() < 1e-14
+        Mfull, _ = R.score(ip, sp, p.D1, p.D2)          # and it is NOT what the pairwise-and-single entry computes
+        assert not np.array_equal(Mr, Mfull)
