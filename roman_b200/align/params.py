@@ -5,8 +5,11 @@ SubmapAlignParams with the field names and defaults of the reference dataclass
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, fields
-from typing import Optional
+import os
+from dataclasses import dataclass, field, fields
+from typing import Any, List, Optional
+
+import numpy as np
 
 import yaml
 
@@ -86,3 +89,57 @@ class SubmapAlignParams:
                          cos_max=self.cosine_max, epsilon_shape=self.epsilon_shape)
         rp.fusion_method = _FUSION[self.fusion_method]
         return ROMANRegistration(rp)
+
+
+@dataclass
+class SubmapAlignInputOutput:
+    """Input / output specification of `submap_align` — the field names, defaults and derived file names of the
+    reference dataclass (reference roman/params/submap_align_params.py:153-198)."""
+    inputs: List[Any]
+    output_dir: str
+    run_name: str
+    input_type_pkl: bool = True
+    input_type_json: bool = False
+    input_gt_pose_yaml: List[Optional[str]] = field(default_factory=lambda: [None, None])
+    robot_names: List[str] = field(default_factory=lambda: ["0", "1"])
+    robot_env: Optional[str] = None
+    lc_association_thresh: int = 4
+    g2o_t_std: float = 0.5
+    g2o_r_std: float = np.deg2rad(0.5)
+    debug_show_maps: bool = False
+    skip_distance: float = np.inf
+
+    def _out(self, suffix: str) -> str:
+        return os.path.join(self.output_dir, f"{self.run_name}{suffix}")
+
+    @property
+    def output_img(self):
+        return self._out(".png")
+
+    @property
+    def output_matrix(self):
+        return self._out(".matrix.pkl")
+
+    @property
+    def output_pkl(self):
+        return self._out(".pkl")
+
+    @property
+    def output_timing(self):
+        return self._out(".timing.txt")
+
+    @property
+    def output_params(self):
+        return self._out(".params.txt")
+
+    @property
+    def output_g2o(self):
+        return self._out(".g2o")
+
+    @property
+    def output_lc_json(self):
+        return self._out(".json")
+
+    @property
+    def output_submaps(self):
+        return [os.path.join(self.output_dir, f"{rn}.sm.json") for rn in self.robot_names]

@@ -216,25 +216,31 @@ __global__ void __launch_bounds__(256) rb_prep_kernel(const RbProblem* __restric
 // K1a for all-to-all plans: the n1 x n2 cosine table is a small dense contraction (descriptors^T * descriptors) and
 // is evaluated as one, instead of re-reading two D-vectors per association.
 //
-// One CTA per (<= 64) x (<= 64) block of (object of map 1, object of map 2).  The thread grid is TY x TX with 4 x 4
-// outputs per thread (rows ty + r*TY of map 1, columns tx + c*TX of map 2), sized to the batch's largest maps
-// (40 x 50 objects -> 10 x 13 threads = 5 warps; three such CTAs share an SM).
+// One CTA per (<= 64) x (<= 64) block of (object of map 1, object of map 2).  The compute threads form a TY x TX grid
+// with MR x 4 outputs each (rows ty + r*TY of map 1, columns tx + c*TX of map 2); MR is 4 or 5, whichever fills whole
+// warps better for the batch's largest maps (40 x 50 objects: 5 x 4 outputs on 8 x 13 threads = 4 warps, one per
+// scheduler; 4 x 4 would need a fifth warp with two live lanes that costs a full warp's issue slots).  One more warp
+// accumulates the squared norms of all rows of the block.  Four such CTAs share an SM.
 //
-// Staging: descriptor columns [k0, k0 + 32) of all rows of the block form one stage ([row][k], 34 doubles per row); a
-// ring of PREP_STAGES stages is filled with asynchronous global->shared copies (cp.async, 8 bytes each — SASS LDGSTS)
-// issued two stages ahead, so HBM latency is hidden behind the fp64 work of the stages in between and the main loop
-// has ONE block barrier per 32 columns.  Why not the bulk / TMA form the solver uses for its 8 KB tiles: object rows
-// are d = 3 + r + D doubles long (775 for the `roman` method, odd), so every other row starts 8 bytes off a 16-byte
+// Staging: descriptor columns [k0, k0 + 16) of all rows of the block form one stage ([row][k], 17 doubles per row); a
+// ring of 4 stages is filled with asynchronous global->shared copies (cp.async, 8 bytes each — SASS LDGSTS) issued
+// three stages ahead, so HBM latency hides behind the fp64 work of the stages in between and the main loop has ONE
+// block barrier per 16 columns.  Why not the bulk / TMA form the solver uses for its 8 KB tiles: object rows are
+// d = 3 + r + D doubles long (775 for the `roman` method, odd), so every other row starts 8 bytes off a 16-byte
 // boundary; cp.async.bulk and tensor maps both need 16-byte aligned sources and strides.
 //
+// Shared-memory traffic is what bounds this kernel next to the fp64 pipe (128 B / clock / SM against 64 FMA / clock:
+// a 4 x 4 register tile fed with 16-byte loads needs twice that).  Operands are therefore read as 8-byte words with
+// an ODD row pitch: the lanes of a warp then touch at most 13 distinct words per load, all in different banks, and
+// lanes that share a row are served by broadcast — one wavefront per load, 8-9 loads per 16-20 FMAs.
+//
 // Arithmetic: each dot product and squared norm is accumulated sequentially over the descriptor index (the order of
-// the scalar loop) with fused multiply-adds, exactly as in round 1 — one thread owns an output from k = 0 to D - 1,
-// nothing is split or tree-reduced, so the cosine gate `<= cosine_min` sees bit-identical inputs.  Operands come from
-// shared memory as 16-byte pairs (k, k+1): 8 loads per 32 FMAs.
-constexpr int PT = 64;            // max objects per block edge
-constexpr int PREP_KC = 32;       // descriptor columns per stage
-constexpr int PREP_LD = PREP_KC + 2;  // shared-memory row length (doubles): rows 16-byte aligned, consecutive rows hit different bank groups
-constexpr int PREP_STAGES = 3;
+// the scalar loop) with fused multiply-adds, exactly as in round 1 — one thread owns an output (or a norm) from k = 0
+// to D - 1, nothing is split or tree-reduced, so the cosine gate `<= cosine_min` sees bit-identical inputs.
+constexpr int PREP_KC = 16;           // descriptor columns per stage
+constexpr int PREP_LD = PREP_KC + 1;  // shared-memory row pitch (doubles): odd -> consecutive rows start in different banks
+constexpr int PREP_STAGES = 4;
+constexpr int PREP_HEAD = 8;          // leading (non-descriptor) columns of a row kept for the epilogue: centre + ratio features
 
 __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
@@ -242,18 +248,20 @@ __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(256) rb_prep_table_kernel(const RbProblem* __restrict__ probs, RbAssocSoA rec,
-                                                            const double* __restrict__ D1,
-                                                            const double* __restrict__ D2, RbDevParams P,
-                                                            int tiles2_max, int TY, int TX) {
+template <int MR>
+__global__ void __launch_bounds__(160, 4) rb_prep_table_kernel(const RbProblem* __restrict__ probs, RbAssocSoA rec,
+                                                               const double* __restrict__ D1,
+                                                               const double* __restrict__ D2, RbDevParams P,
+                                                               int tiles2_max, int TY, int TX) {
   extern __shared__ __align__(16) unsigned char prep_smem[];
   const RbProblem pr = probs[blockIdx.y];
   const rb_invariant_params& p = P.inv;
-  const int PT1 = 4 * TY, PT2 = 4 * TX, R = PT1 + PT2;
+  const int PT1 = MR * TY, PT2 = 4 * TX, R = PT1 + PT2;
+  const int NC = ((TY * TX + 31) / 32) * 32;   // compute threads (whole warps); the last warp of the CTA takes the norms
+  const int NTH = blockDim.x;                  // NC + 32
   double* stage0 = reinterpret_cast<double*>(prep_smem);                // [PREP_STAGES][R][PREP_LD]
-  double* s_na = stage0 + (size_t)PREP_STAGES * R * PREP_LD;            // [PT1]
-  double* s_nb = s_na + PT1;                                            // [PT2]
-  const int NTH = blockDim.x;
+  double* s_norm = stage0 + (size_t)PREP_STAGES * R * PREP_LD;          // [R] squared norms
+  double* s_head = s_norm + R;                                          // [R][PREP_HEAD] centres and ratio features
   const int t1 = blockIdx.x / tiles2_max, t2 = blockIdx.x % tiles2_max;
   const int i1_0 = t1 * PT1, i2_0 = t2 * PT2;
   const int tid = threadIdx.x;
@@ -268,37 +276,48 @@ __global__ void __launch_bounds__(256) rb_prep_table_kernel(const RbProblem* __r
   }
   if (i1_0 >= pr.n1 || i2_0 >= pr.n2) return;
   const bool active = tid < TY * TX;
+  const bool norm_warp = tid >= NC;
   const int tx = active ? tid % TX : 0, ty = active ? tid / TX : 0;
   const double* A0 = D1 + pr.off_obj1 * (int64_t)pr.d;
   const double* B0 = D2 + pr.off_obj2 * (int64_t)pr.d;
   const int foff = p.point_dim + p.ratio_feature_dim;
   const int Dc = (p.kind == RB_INVARIANT_ROMAN) ? p.cos_feature_dim : 0;
   const int nchunks = (Dc + PREP_KC - 1) / PREP_KC;
-  // the squared norms of the map-2 objects are accumulated by the threads of thread-row 0 only, those of the map-1
-  // objects by thread-column 0 only
-  const bool do_nb = active && ty == 0, do_na = active && tx == 0;
+  const int nhead = foff < PREP_HEAD ? foff : PREP_HEAD;
 
-  // rows of the block that exist: stage row q < PT1 is object i1_0 + q of map 1, q >= PT1 object i2_0 + q - PT1 of map 2
-  auto issue = [&](int c) {  // asynchronous copies of chunk c into stage c % PREP_STAGES (rows / columns that do not exist: zeros)
+  // stage row q < PT1 is object i1_0 + q of map 1, q >= PT1 object i2_0 + q - PT1 of map 2 (rows / columns that do
+  // not exist are zeros)
+  auto row_ptr = [&](int q) -> const double* {
+    const bool is1 = q < PT1;
+    const int o = is1 ? i1_0 + q : i2_0 + q - PT1;
+    if (is1 ? o >= pr.n1 : o >= pr.n2) return nullptr;
+    return (is1 ? A0 : B0) + (int64_t)o * pr.d;
+  };
+  auto issue = [&](int c) {  // asynchronous copies of chunk c into stage c % PREP_STAGES
     double* st = stage0 + (size_t)(c % PREP_STAGES) * R * PREP_LD;
     const int k0 = c * PREP_KC;
-    for (int e = tid; e < R * PREP_KC; e += NTH) {  // consecutive threads -> consecutive columns of one row: coalesced
+    for (int e = tid; e < R * PREP_KC; e += NTH) {  // 16 consecutive threads -> 16 consecutive columns of one row (128 B)
       const int q = e / PREP_KC, k = e % PREP_KC;
-      const bool is1 = q < PT1;
-      const int o = is1 ? i1_0 + q : i2_0 + q - PT1;
-      const bool ok = (k0 + k) < Dc && (is1 ? o < pr.n1 : o < pr.n2);
+      const double* src = row_ptr(q);
       double* dst = st + q * PREP_LD + k;
-      if (ok) cp_async_8(dst, (is1 ? A0 : B0) + (int64_t)o * pr.d + foff + k0 + k);
+      if (src != nullptr && (k0 + k) < Dc) cp_async_8(dst, src + foff + k0 + k);
       else *dst = 0.0;
     }
   };
+  for (int e = tid; e < R * PREP_HEAD; e += NTH) {  // centres and ratio features for the epilogue
+    const int q = e / PREP_HEAD, k = e % PREP_HEAD;
+    const double* src = row_ptr(q);
+    s_head[e] = (src != nullptr && k < nhead) ? src[k] : 0.0;
+  }
 
-  double acc[4][4];
-  double na[4] = {0, 0, 0, 0}, nb[4] = {0, 0, 0, 0};
+  double acc[MR][4];
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+  for (int r = 0; r < MR; ++r)
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+  constexpr int NJ = 4;              // norm warp: rows lane, lane + 32, ... of the block (R <= 5 * 8 + 4 * 16 = 104)
+  double nrm[NJ] = {0.0, 0.0, 0.0, 0.0};
+  const int lane = tid & 31;
 
   for (int c = 0; c < PREP_STAGES - 1; ++c) {
     if (c < nchunks) issue(c);
@@ -310,63 +329,56 @@ __global__ void __launch_bounds__(256) rb_prep_table_kernel(const RbProblem* __r
     __syncthreads();                   // ... and everybody's; also: everybody is done with the stage refilled next
     if (c + PREP_STAGES - 1 < nchunks) issue(c + PREP_STAGES - 1);
     cp_async_commit();
+    const double* st = stage0 + (size_t)(c % PREP_STAGES) * R * PREP_LD;
     if (active) {
-      const double* st = stage0 + (size_t)(c % PREP_STAGES) * R * PREP_LD;
       const double* pa = st + ty * PREP_LD;
       const double* pb = st + (PT1 + tx) * PREP_LD;
 #pragma unroll 4
-      for (int k = 0; k < PREP_KC; k += 2) {
-        double2 a[4], b[4];
+      for (int k = 0; k < PREP_KC; ++k) {
+        double a[MR], b[4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) a[r] = *reinterpret_cast<const double2*>(pa + r * TY * PREP_LD + k);
+        for (int r = 0; r < MR; ++r) a[r] = pa[r * TY * PREP_LD + k];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) b[q] = *reinterpret_cast<const double2*>(pb + q * TX * PREP_LD + k);
+        for (int q = 0; q < 4; ++q) b[q] = pb[q * TX * PREP_LD + k];
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < MR; ++r)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) acc[r][q] = fma(a[r].x, b[q].x, acc[r][q]);
-        if (do_na)
+          for (int q = 0; q < 4; ++q) acc[r][q] = fma(a[r], b[q], acc[r][q]);
+      }
+    } else if (norm_warp) {
 #pragma unroll
-          for (int r = 0; r < 4; ++r) na[r] = fma(a[r].x, a[r].x, na[r]);
-        if (do_nb)
+      for (int j = 0; j < NJ; ++j) {
+        const int q = lane + 32 * j;
+        if (q < R) {
+          const double* pr_ = st + q * PREP_LD;
+          double s2 = nrm[j];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) nb[q] = fma(b[q].x, b[q].x, nb[q]);
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) acc[r][q] = fma(a[r].y, b[q].y, acc[r][q]);
-        if (do_na)
-#pragma unroll
-          for (int r = 0; r < 4; ++r) na[r] = fma(a[r].y, a[r].y, na[r]);
-        if (do_nb)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) nb[q] = fma(b[q].y, b[q].y, nb[q]);
+          for (int k = 0; k < PREP_KC; ++k) s2 = fma(pr_[k], pr_[k], s2);
+          nrm[j] = s2;
+        }
       }
     }
   }
-  __syncthreads();
-  if (do_na)
+  if (norm_warp)
 #pragma unroll
-    for (int r = 0; r < 4; ++r) s_na[ty + r * TY] = na[r];
-  if (do_nb)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) s_nb[tx + q * TX] = nb[q];
+    for (int j = 0; j < NJ; ++j)
+      if (lane + 32 * j < R) s_norm[lane + 32 * j] = nrm[j];
   __syncthreads();
   if (!active) return;
 
   const int pd = (p.kind != RB_INVARIANT_EUCLIDEAN) ? p.point_dim : (pr.d < 3 ? pr.d : 3);
-  // 16 outputs per thread, one instance of the scoring code (pow is long)
+  // MR x 4 outputs per thread, one instance of the scoring code (pow is long)
 #pragma unroll 1
-  for (int rq = 0; rq < 16; ++rq) {
+  for (int rq = 0; rq < MR * 4; ++rq) {
     const int r = rq >> 2, q = rq & 3;
     const int l1 = ty + r * TY, l2 = tx + q * TX;
     const int i1 = i1_0 + l1, i2 = i2_0 + l2;
     if (i1 >= pr.n1 || i2 >= pr.n2) continue;
-    const double* a = A0 + (int64_t)i1 * pr.d;
-    const double* b = B0 + (int64_t)i2 * pr.d;
+    const double* ha = s_head + l1 * PREP_HEAD;
+    const double* hb = s_head + (PT1 + l2) * PREP_HEAD;
     double dotv = 0.0;
 #pragma unroll
-    for (int rr = 0; rr < 4; ++rr)
+    for (int rr = 0; rr < MR; ++rr)
 #pragma unroll
       for (int qq = 0; qq < 4; ++qq)
         if (rr == r && qq == q) dotv = acc[rr][qq];  // register select: acc[][] must not be indexed dynamically
@@ -375,7 +387,7 @@ __global__ void __launch_bounds__(256) rb_prep_table_kernel(const RbProblem* __r
       bool zero = false;
       double cos_scaled = 0.0, ratio_score = 0.0;
       if (p.cos_feature_dim > 0) {
-        const double cs = dotv / (sqrt(s_na[l1]) * sqrt(s_nb[l2]));
+        const double cs = dotv / (sqrt(s_norm[l1]) * sqrt(s_norm[PT1 + l2]));
         if (cs >= p.cosine_max) cos_scaled = 1.0;
         else if (cs <= p.cosine_min) zero = true;
         else cos_scaled = (cs - p.cosine_min) / (p.cosine_max - p.cosine_min);
@@ -384,7 +396,9 @@ __global__ void __launch_bounds__(256) rb_prep_table_kernel(const RbProblem* __r
         double prod = 1.0;
         bool below = false;
         for (int t = 0; t < p.ratio_feature_dim; ++t) {
-          const double x = a[p.point_dim + t], y = b[p.point_dim + t];
+          const int col = p.point_dim + t;
+          const double x = col < PREP_HEAD ? ha[col] : A0[(int64_t)i1 * pr.d + col];
+          const double y = col < PREP_HEAD ? hb[col] : B0[(int64_t)i2 * pr.d + col];
           const double qv = x < y ? x / y : y / x;
           if (qv < p.ratio_epsilon[t]) below = true;
           prod *= qv;
@@ -400,8 +414,8 @@ __global__ void __launch_bounds__(256) rb_prep_table_kernel(const RbProblem* __r
                      1.0 / (p.ratio_weight + p.cosine_weight));
     }
     const int64_t o = pr.off_pad + (int64_t)i1 * pr.n2 + i2;  // utils::createAllToAll order
-    rec.ax[o] = a[0]; rec.ay[o] = pd > 1 ? a[1] : 0.0; rec.az[o] = pd > 2 ? a[2] : 0.0;
-    rec.bx[o] = b[0]; rec.by[o] = pd > 1 ? b[1] : 0.0; rec.bz[o] = pd > 2 ? b[2] : 0.0;
+    rec.ax[o] = ha[0]; rec.ay[o] = pd > 1 ? ha[1] : 0.0; rec.az[o] = pd > 2 ? ha[2] : 0.0;
+    rec.bx[o] = hb[0]; rec.by[o] = pd > 1 ? hb[1] : 0.0; rec.bz[o] = pd > 2 ? hb[2] : 0.0;
     rec.single[o] = single;
     rec.i1[o] = i1;
     rec.i2[o] = i2;
@@ -481,10 +495,17 @@ __device__ __forceinline__ void affinity_tile(const RbProblem& pr, int I, int J,
   // One instance of the scoring code, no unrolling: the transcendental paths (exp, pow) are long, and several copies
   // of them made the kernel's instruction footprint (~250 KB of SASS) thrash the instruction cache — 76 % of the
   // warp stalls of the round-1 kernel on dense graphs were "no instruction".
+  // rows that cannot carry an edge: zeros (a cheap loop, kept apart from the scoring code so that it may be unrolled)
+#pragma unroll 8
+  for (int r = 0; r < RB_TILE; ++r)
+    if (!((row_live >> r) & 1u)) out[rb_tile_elem(r, lane)] = 0.0;
+  unsigned todo = row_live;
 #pragma unroll 1
-  for (int r = 0; r < RB_TILE; ++r) {
+  while (todo) {
+    const int r = __ffs(todo) - 1;
+    todo &= todo - 1;
     double v = 0.0;
-    if (((row_live >> r) & 1u) && ((col_live >> lane) & 1u) && !(diag && r == lane)) {  // r == lane: implicit identity (clipper.cpp:129-130)
+    if (((col_live >> lane) & 1u) && !(diag && r == lane)) {  // r == lane: implicit identity (clipper.cpp:129-130)
       const Rec row = s_row[r];
       // i = the association with the smaller index: the row, except for the mirrored half of a diagonal tile
       const bool mirrored = diag && r > lane;
@@ -686,26 +707,34 @@ cudaError_t rb_launch_prep(const RbProblem* probs, int B, int max_mp, int max_n1
                            const RbAssocSoA& rec, const double* D1, const double* D2, const int32_t* A,
                            const RbDevParams& P, cudaStream_t st) {
   if (B == 0 || max_mp == 0) return cudaSuccess;
-  if (all_to_all) {
-    // thread grid TY x TX (4x4 outputs per thread) sized to the largest maps of the batch, at most 16 x 16
-    int TY = (max_n1 + 3) / 4, TX = (max_n2 + 3) / 4;
-    if (TY > 16) TY = 16;
-    if (TX > 16) TX = 16;
-    if (TY < 1) TY = 1;
-    if (TX < 1) TX = 1;
-    const int t1 = (max_n1 + 4 * TY - 1) / (4 * TY), t2 = (max_n2 + 4 * TX - 1) / (4 * TX);
-    if ((int64_t)t1 * t2 <= 65535 * 32) {
-      dim3 grid((unsigned)(t1 * t2 > 0 ? t1 * t2 : 1), B);
-      const int nth = ((TY * TX + 31) / 32) * 32;
-      const size_t smem = ((size_t)PREP_STAGES * (4 * TY + 4 * TX) * PREP_LD + 4 * TY + 4 * TX) * sizeof(double);
-      static bool attr_set = false;
-      if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(rb_prep_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
+  if (all_to_all && max_n1 > 0 && max_n2 > 0) {
+    // thread grid TY x TX with MR x 4 outputs per thread, sized to the largest maps of the batch (blocks of at most
+    // 64 x 64 objects); MR = 4 or 5, whichever needs fewer warps
+    // blocks of at most 40 x 64 objects (larger maps take several blocks): at most 8 x 16 = 128 compute threads
+    const int e1 = max_n1 < 40 ? max_n1 : 40, e2 = max_n2 < 64 ? max_n2 : 64;
+    const int TX = (e2 + 3) / 4;
+    const int ty4 = (e1 + 3) / 4, ty5 = (e1 + 4) / 5;
+    const int w4 = (ty4 * TX + 31) / 32, w5 = (ty5 * TX + 31) / 32;
+    const int MR = (ty4 * TX > 128 || w5 < w4) ? 5 : 4;
+    const int TY = MR == 5 ? ty5 : ty4;
+    if (TY * TX <= 128) {
+      const int t1 = (max_n1 + MR * TY - 1) / (MR * TY), t2 = (max_n2 + 4 * TX - 1) / (4 * TX);
+      if ((int64_t)t1 * t2 <= 65535) {
+        dim3 grid((unsigned)(t1 * t2), B);
+        const int nth = ((TY * TX + 31) / 32) * 32 + 32;   // compute warps + the norm warp
+        const int R = MR * TY + 4 * TX;
+        const size_t smem = ((size_t)PREP_STAGES * R * PREP_LD + R + (size_t)R * PREP_HEAD) * sizeof(double);
+        static bool attr_set = false;
+        if (!attr_set) {
+          cudaError_t e = cudaFuncSetAttribute(rb_prep_table_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+          if (e == cudaSuccess) e = cudaFuncSetAttribute(rb_prep_table_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+          if (e != cudaSuccess) return e;
+          attr_set = true;
+        }
+        if (MR == 5) rb_prep_table_kernel<5><<<grid, nth, smem, st>>>(probs, rec, D1, D2, P, t2, TY, TX);
+        else rb_prep_table_kernel<4><<<grid, nth, smem, st>>>(probs, rec, D1, D2, P, t2, TY, TX);
+        return cudaGetLastError();
       }
-      rb_prep_table_kernel<<<grid, nth, smem, st>>>(probs, rec, D1, D2, P, t2 > 0 ? t2 : 1, TY, TX);
-      return cudaGetLastError();
     }
   }
   dim3 grid((max_mp + 7) / 8, B);
