@@ -13,9 +13,9 @@ One "step" = one pass of the hot path (K1a + K1 + K2 + K3) over one batch of syn
   --config cfg5    the all-pairs loop-closure search (BASELINE.json configs[4]; reference loop
                    roman/align/submap_align.py:93-200): per GPU one robot pair = 20 x 20 submaps of <= 40 objects, every
                    submap pair one problem (400 per GPU, ragged m <= 1600), object tables shared between problems
-                   (rb_plan_indexed).  With N GPUs the N x 400 problems are sorted by m (longest first) and dealt to
-                   the ranks in snake order; each rank's list stays longest-first, which is also the order the
-                   persistent solver queue takes them in.
+                   (rb_plan_indexed).  With N GPUs every GPU searches its own robot pair (a multi-robot session has one
+                   such search per pair of robots); a rank's problems are ordered longest-first, which is also the
+                   order the persistent solver queue takes them in.
 All configs are weak scaling (fixed work per GPU).  The only inter-GPU exchange is one all-gather of fixed-size per-pair
 records per step.
 
@@ -174,25 +174,25 @@ def build_workload(cfg, rank, world, batch=0, desc_common=None, rank_offset=0):
     assert cfg == "cfg5"
     S = 20
     dc = 1.0 if desc_common is None else desc_common
-    worlds = [synth.make_all_pairs_world(5000 + w + rank_offset, S, S, 40, method=METHOD, semantics_dim=SEM_DIM,
-                                         desc_common=dc) for w in range(world)]
+    # one robot pair (world) per GPU: a rank uploads and searches its own pair's tables only.  (Dealing the N x 400
+    # problems of all pairs longest-first over the ranks balances K2 to +-2.5 %, but then every rank needs every pair's
+    # tables: 8 x 12 MB per step through the shared host PCIe cost more than the balance won — measured.)
+    worlds = [synth.make_all_pairs_world(5000 + rank + rank_offset, S, S, 40, method=METHOD, semantics_dim=SEM_DIM, desc_common=dc)]
     t0 = [t for w in worlds for t in w.tables[0]]
     t1 = [t for w in worlds for t in w.tables[1]]
     off0 = np.concatenate([[0], np.cumsum([len(t) for t in t0])]).astype(np.int64)
     off1 = np.concatenate([[0], np.cumsum([len(t) for t in t1])]).astype(np.int64)
-    probs = [(w, i, j) for w in range(world) for i in range(S) for j in range(S)]
-    msz = np.array([len(t0[w * S + i]) * len(t1[w * S + j]) for (w, i, j) in probs])
-    order = np.argsort(-msz, kind="stable")                      # longest problem first
-    # snake deal: round r goes rank 0..W-1, round r+1 goes W-1..0 — per-rank work stays within one problem of equal
-    mine = [int(g) for q, g in enumerate(order) if ((q % world) if (q // world) % 2 == 0 else world - 1 - (q % world)) == rank]
-    sel = [probs[g] for g in mine]
+    probs = [(0, i, j) for i in range(S) for j in range(S)]
+    msz = np.array([len(t0[i]) * len(t1[j]) for (_, i, j) in probs])
+    order = np.argsort(-msz, kind="stable")                      # longest problem first: the order the solver queue takes them in
+    sel = [probs[int(g)] for g in order]
     if batch:
         sel = sel[:batch]
     a = np.array([w * S + i for (w, i, j) in sel])
     b = np.array([w * S + j for (w, i, j) in sel])
     n1 = np.array([len(t0[x]) for x in a], dtype=np.int32)
     n2 = np.array([len(t1[x]) for x in b], dtype=np.int32)
-    u0 = np.concatenate([np.random.default_rng(7_000_000 + 1000 * (w + rank_offset) + 20 * i + j).uniform(0, 1, int(x) * int(y))
+    u0 = np.concatenate([np.random.default_rng(7_000_000 + 1000 * (rank + rank_offset) + 20 * i + j).uniform(0, 1, int(x) * int(y))
                          for (w, i, j), x, y in zip(sel, n1, n2)])
     text = (f"all-pairs loop-closure search: per GPU one robot pair of {S} x {S} synthetic submaps (<= 40 objects, ragged "
             f"m <= 1600), every submap pair one problem, shared object tables, method roman, D=768, descriptors in a cone "
@@ -533,7 +533,7 @@ def run_b200(args):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl.text, "name": wl.name, "pairs_per_gpu_per_step": B,
-                       "parallelism": (f"longest-first snake deal of {world} x {B} problems over {world} GPU(s)" if wl.name == "cfg5"
+                       "parallelism": (f"one robot pair (20 x 20 submaps = {B} problems, longest first) per GPU, {world} GPU(s)" if wl.name == "cfg5"
                                        else f"round-robin pairs over {world} GPU(s)"),
                        "l2": f"inputs larger than L2: packed affinity working set {packed_bytes / 1e9:.2f} GB per GPU per step",
                        "layout": "packed upper triangle, 32x32 fp64 tiles, dense format (every tile written by K1 and streamed by K2 each pass)",

@@ -24,3 +24,36 @@ def install_as_clipperpy():
     sys.modules["clipperpy.invariants"] = _cp.invariants
     sys.modules["clipperpy.utils"] = _cp.utils
     return _cp
+
+
+def install_as_roman():
+    """Register this package's mirrors under the reference's module paths (`roman.align.submap_align`,
+    `roman.params.submap_align_params`, `roman.align.results`, `roman.align.object_registration`, ...), together with
+    `clipperpy`, so that a caller written against the reference — demo/loop_closures.py:3-4,19-28 — runs unchanged:
+
+        from roman.params.submap_align_params import SubmapAlignInputOutput, SubmapAlignParams
+        from roman.align.submap_align import submap_align
+    """
+    import importlib
+    import sys
+    import types
+    from . import align
+    mods = {n: importlib.import_module(f"{__name__}.align.{n}") for n in
+            ("dist_reg_with_pruning", "object_registration", "params", "results", "roman_registration", "submap_align")}
+    install_as_clipperpy()
+    for name in ("roman", "roman.align", "roman.params"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            sys.modules[name] = m
+    table = {"roman.align.submap_align": mods["submap_align"], "roman.align.results": mods["results"],
+             "roman.align.object_registration": mods["object_registration"],
+             "roman.align.roman_registration": mods["roman_registration"],
+             "roman.align.dist_reg_with_pruning": mods["dist_reg_with_pruning"],
+             "roman.params.submap_align_params": mods["params"]}
+    for name, mod in table.items():
+        sys.modules[name] = mod
+        setattr(sys.modules[name.rsplit(".", 1)[0]], name.rsplit(".", 1)[1], mod)
+    sys.modules["roman"].align = sys.modules["roman.align"]
+    sys.modules["roman"].params = sys.modules["roman.params"]
+    return align

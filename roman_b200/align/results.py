@@ -11,8 +11,9 @@ dependency outside numpy/scipy.  Quaternions are scipy's `Rotation.from_matrix(R
 from __future__ import annotations
 
 import json
+import pickle
 from dataclasses import dataclass
-from typing import List, Sequence
+from typing import Any, List, Optional, Sequence
 
 import numpy as np
 from scipy.spatial.transform import Rotation as Rot
@@ -129,3 +130,131 @@ def write_submaps_json(path: str, robot_name: str, segments: Sequence[dict], sub
         })
     with open(path, "w") as f:
         json.dump(doc, f, indent=4)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The result object of `submap_align` and its writer (reference roman/align/results.py:18-44, 122-246)
+@dataclass
+class SubmapAlignResults:
+    """Field names, order and meaning of the reference dataclass (roman/align/results.py:18-44)."""
+    robots_nearby_mat: np.ndarray
+    clipper_angle_mat: np.ndarray
+    clipper_dist_mat: np.ndarray
+    clipper_num_associations: np.ndarray
+    similarity_mat: Optional[np.ndarray]
+    submap_yaw_diff_mat: np.ndarray
+    associated_objs_mat: Any
+    T_ij_mat: np.ndarray
+    T_ij_hat_mat: np.ndarray
+    timing_list: List[float]
+    submap_align_params: Any
+    submap_io: Any
+    total_time: float = -np.inf
+
+    def save(self):
+        with open(self.submap_io.output_pkl, "wb") as f:
+            pickle.dump(self, f)
+
+    @classmethod
+    def load(cls, file_path) -> "SubmapAlignResults":
+        with open(file_path, "rb") as f:
+            return pickle.load(f)
+
+
+def plot_align_results(results: SubmapAlignResults, dpi=500) -> bool:
+    """The heat-map figure of reference results.py:55-120 — drawn only where matplotlib exists (it is not part of
+    this image); returns whether a figure was made."""
+    try:
+        import matplotlib.pyplot as plt
+    except ImportError:
+        return False
+    show_sim = results.similarity_mat is not None
+    names = results.submap_io.robot_names
+    if None in results.submap_io.input_gt_pose_yaml:   # no ground truth: only the association counts (and similarity)
+        fig, ax = plt.subplots(2 if show_sim else 1, 1, figsize=(8 if show_sim else 4, 4), dpi=dpi)
+        ax = np.array(ax).reshape(-1, 1)
+        mp = ax[0, 0].imshow(results.clipper_num_associations, cmap="viridis", vmin=0)
+        fig.colorbar(mp, fraction=0.04, pad=0.04)
+        ax[0, 0].set_title("Number of Associations")
+        if show_sim:
+            mp = ax[1, 0].imshow(results.similarity_mat, cmap="viridis", vmin=0.0, vmax=1.0)
+            fig.colorbar(mp, fraction=0.04, pad=0.04)
+            ax[1, 0].set_title("Similarity Score")
+        fig.suptitle(f"{results.submap_io.run_name}: {names[0]}, {names[1]}")
+        return True
+    fig, ax = plt.subplots(3, 2, figsize=(8, 12), dpi=dpi)
+    fig.subplots_adjust(wspace=.3)
+    fig.suptitle(f"{results.submap_io.run_name}: {names[0]}, {names[1]}")
+    angle_thresh, dist_thresh = 10.0, 5.0
+    ang, dst = results.clipper_angle_mat.copy(), results.clipper_dist_mat.copy()
+    ang[(dst > dist_thresh) & ~np.isnan(ang)] = angle_thresh
+    dst[(ang > angle_thresh) & ~np.isnan(dst)] = dist_thresh
+    panels = [(0, 0, results.robots_nearby_mat, "magma", dict(vmin=0), "Submaps Center Distance (m)"),
+              (0, 1, results.submap_yaw_diff_mat, "magma", dict(vmin=0), "Submap Center Yaw Diff. (deg)"),
+              (1, 0, dst, "viridis_r", dict(vmax=dist_thresh, vmin=0.0), "Registration Translation Error (m)"),
+              (1, 1, ang, "viridis_r", dict(vmax=angle_thresh, vmin=0.0), "Registration Angle Error (deg)"),
+              (2, 0, results.clipper_num_associations, "viridis", dict(vmin=0), "Number of Associations")]
+    if show_sim:
+        panels.append((2, 1, results.similarity_mat, "viridis", dict(vmin=0.0, vmax=1.0), "Similarity Score"))
+    for i, j, mat, cmap, kw, title in panels:
+        mp = ax[i, j].imshow(mat, cmap=cmap, **kw)
+        fig.colorbar(mp, fraction=0.04, pad=0.04)
+        ax[i, j].set_title(title)
+    for a in ax.reshape(-1):
+        a.set_xlabel("submap index (robot 2)")
+        a.set_ylabel("submap index (robot 1)")
+        a.grid(False)
+    if not show_sim:
+        fig.delaxes(ax[2, 1])
+    return True
+
+
+def save_submap_align_results(results: SubmapAlignResults, submaps, roman_maps):
+    """
+    Everything the reference's writer leaves in `submap_io.output_dir` (roman/align/results.py:122-246): the figure
+    (where matplotlib exists), `<run>.matrix.pkl`, `<run>.pkl`, `<run>.timing.txt`, `<run>.params.txt`, `<run>.g2o`,
+    `<run>.json` and one `<robot>.sm.json` per robot.  `submaps[r]`: the robot's submaps (time, pose_gravity_aligned,
+    pose_flu, segments with .id); `roman_maps[r]`: its map (times, trajectory, segments).
+    """
+    io, sp = results.submap_io, results.submap_align_params
+    if plot_align_results(results):
+        import matplotlib.pyplot as plt
+        plt.savefig(io.output_img)
+    with open(io.output_matrix, "wb") as f:
+        pickle.dump([results.robots_nearby_mat, results.clipper_angle_mat, results.clipper_dist_mat,
+                     results.clipper_num_associations, results.submap_yaw_diff_mat], f)
+    with open(io.output_pkl, "wb") as f:
+        pickle.dump(results, f)
+    sizes = [len(sm) for sm in list(submaps[0]) + list(submaps[1])]
+    with open(io.output_timing, "w") as f:
+        f.write(f"Total number of submaps: {len(submaps[0])} x {len(submaps[1])} = {len(submaps[0])*len(submaps[1])}\n")
+        f.write(f"Average time per registration: {np.mean(results.timing_list):.4f} seconds\n")
+        f.write(f"Total time: {np.sum(results.timing_list):.4f} seconds\n")
+        f.write(f"Total number of objects: {np.sum(sizes)}\n")
+        f.write(f"Average number of obects per map: {np.mean(sizes):.2f}\n")
+    with open(io.output_params, "w") as f:
+        f.write(f"{sp}")
+
+    def pose_index(rm, t):   # robotdatapy PoseData.idx(t, force_single=True): the trajectory pose closest in time
+        return int(np.argmin(np.abs(np.asarray(rm.times, dtype=np.float64) - t)))
+    meta = [[SubmapMeta(sm.time, sm.pose_gravity_aligned, sm.pose_flu, pose_index(rm, sm.time)) for sm in run]
+            for run, rm in zip(submaps, roman_maps)]
+    pair_res = SubmapPairResults(T_ij_hat_mat=results.T_ij_hat_mat, clipper_num_associations=results.clipper_num_associations,
+                                 clipper_percent_associations=None, associated_objs_mat=None, status_mat=None)
+    lcs = loop_closures(pair_res, meta[0], meta[1], lc_association_thresh=io.lc_association_thresh,
+                        single_robot_lc=sp.single_robot_lc, single_robot_lc_time_thresh=sp.single_robot_lc_time_thresh)
+    write_g2o(io.output_g2o, lcs, g2o_t_std=io.g2o_t_std, g2o_r_std=io.g2o_r_std)
+    write_lc_json(io.output_lc_json, lcs, io.robot_names)
+    for r, path in enumerate(io.output_submaps):
+        if path is None:
+            continue
+        segs = []
+        for sg in roman_maps[r].segments:   # the reference skips segments without a point cloud (minimal data), results.py:211-226
+            pts = getattr(sg, "points", None)
+            if pts is None:
+                continue
+            segs.append(dict(id=sg.id, centroid_odom=np.mean(np.asarray(pts), axis=0), volume=sg.volume, linearity=sg.linearity,
+                             planarity=sg.planarity, scattering=sg.scattering, first_seen=sg.first_seen, last_seen=sg.last_seen))
+        write_submaps_json(path, io.robot_names[r], segs,
+                           [dict(time=sm.time, pose_gravity_aligned=sm.pose_gravity_aligned,
+                                 segment_ids=[s.id for s in sm.segments]) for sm in submaps[r]])

