@@ -123,6 +123,17 @@ int rb_plan(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const int32_t
  * rows [obj1_offset[b], obj1_offset[b] + n1[b]) of D1 and [obj2_offset[b], ... + n2[b]) of D2. */
 int rb_plan_indexed(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const int32_t* n2, const int32_t* m,
                     const int64_t* obj1_offset, const int64_t* obj2_offset, int64_t total_obj1, int64_t total_obj2);
+/* Same as rb_plan_indexed, for batches in which several problems are the SAME submap pair solved from different start
+ * vectors (multi-start: CLIPPER is a local method and the reference draws one random start per solve,
+ * clipper/src/utils.cpp:22-29; roman/align/object_registration.py:57-86 re-solves one pair several times).
+ * share[b] == b: problem b owns its affinity matrix; share[b] == a < b (with share[a] == a, identical n1, n2, m and
+ * object ranges): problem b uses a's matrix, association records and edge list — K1 builds and stores the matrix
+ * once, K2 / K3 run for every problem with its own u0 and outputs.  The solver clusters of a group stream the same
+ * tiles at the same time, so each pass reads the matrix from HBM once and from L2 for the other starts; per-start
+ * results are bit-identical to solving the problems separately. */
+int rb_plan_shared(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const int32_t* n2, const int32_t* m,
+                   const int64_t* obj1_offset, const int64_t* obj2_offset, int64_t total_obj1, int64_t total_obj2,
+                   const int32_t* share);
 int64_t rb_assoc_offset(const rb_handle* h, int32_t b); /* b == B gives the total */
 int64_t rb_obj1_offset(const rb_handle* h, int32_t b);  /* in objects (rows of d doubles) */
 int64_t rb_obj2_offset(const rb_handle* h, int32_t b);

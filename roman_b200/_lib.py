@@ -55,6 +55,7 @@ SIGNATURES = {
     "rb_set_solver_params": (C.c_int, [_vp, C.POINTER(RbSolverParams)]),
     "rb_plan": (C.c_int, [_vp, _i32, _i32, _ip, _ip, _ip]),
     "rb_plan_indexed": (C.c_int, [_vp, _i32, _i32, _ip, _ip, _ip, _vp, _vp, _i64, _i64]),
+    "rb_plan_shared": (C.c_int, [_vp, _i32, _i32, _ip, _ip, _ip, _vp, _vp, _i64, _i64, _ip]),
     "rb_assoc_offset": (_i64, [_vp, _i32]),
     "rb_obj1_offset": (_i64, [_vp, _i32]),
     "rb_obj2_offset": (_i64, [_vp, _i32]),

@@ -170,9 +170,10 @@ class ROMANRegistration(ObjectRegistration):
     def register_multistart(self, map1: List, map2: List, u0s: Sequence[np.ndarray]):
         """
         K solver restarts on ONE pair (CLIPPER is a local method and the reference
-        draws a single random start per pair, clipper/src/utils.cpp:22-29).  The K problems reference the
-        same two object tables (rb_plan_indexed) and run as one batch.  Returns a dict with the best-scoring
-        start's `associations` (k, 2), `T`, `status`, its index `best`, and the `scores` of all starts.
+        draws a single random start per pair, clipper/src/utils.cpp:22-29).  The K problems share ONE affinity
+        matrix (rb_plan_shared): K1 scores and stores the pair once, the K solves run side by side on it with their own
+        start vectors.  Returns a dict with the best-scoring start's `associations` (k, 2), `T`, `status`, its index
+        `best`, and the `scores` of all starts.
         """
         from ..engine import Engine, default_solver_params
         K = len(u0s)
@@ -186,7 +187,8 @@ class ROMANRegistration(ObjectRegistration):
         e.set_invariant_params(clipperpy.invariants.ROMAN(self.iparams)._rb_params())
         e.set_solver_params(default_solver_params())
         zeros = np.zeros(K, dtype=np.int64)
-        e.plan(D1.shape[1], [n1] * K, [n2] * K, obj1_offsets=zeros, obj2_offsets=zeros, total_obj1=n1, total_obj2=n2)
+        e.plan(D1.shape[1], [n1] * K, [n2] * K, obj1_offsets=zeros, obj2_offsets=zeros, total_obj1=n1, total_obj2=n2,
+               share=np.zeros(K, dtype=np.int32))
         u0cat = np.concatenate([np.asarray(u, dtype=np.float64).reshape(-1) for u in u0s])
         assert u0cat.size == K * n1 * n2
         out = e.align_batch_host(np.ascontiguousarray(D1), np.ascontiguousarray(D2), u0cat)

@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(256) rb_prep_kernel(const RbProblem* __restric
                                                       const double* __restrict__ D1, const double* __restrict__ D2,
                                                       const int32_t* __restrict__ A, RbDevParams P) {
   const RbProblem pr = probs[blockIdx.y];
+  if (pr.is_copy) return;  // shares another problem's matrix and records (rb_plan_shared)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int mp = pr.nb * RB_TILE;
   const rb_invariant_params& p = P.inv;
@@ -255,6 +256,7 @@ __global__ void __launch_bounds__(160, 4) rb_prep_table_kernel(const RbProblem* 
                                                                int tiles2_max, int TY, int TX) {
   extern __shared__ __align__(16) unsigned char prep_smem[];
   const RbProblem pr = probs[blockIdx.y];
+  if (pr.is_copy) return;  // shares another problem's matrix and records (rb_plan_shared)
   const rb_invariant_params& p = P.inv;
   const int PT1 = MR * TY, PT2 = 4 * TX, R = PT1 + PT2;
   const int NC = ((TY * TX + 31) / 32) * 32;   // compute threads (whole warps); the last warp of the CTA takes the norms
@@ -450,6 +452,7 @@ __device__ __forceinline__ void tile_coords(int64_t q, int nb, int& I, int& J) {
 __global__ void __launch_bounds__(256) rb_block_mask_kernel(const RbProblem* __restrict__ probs, RbAssocSoA rec,
                                                             uint32_t* __restrict__ masks, RbDevParams P) {
   const RbProblem pr = probs[blockIdx.y];
+  if (pr.is_copy) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool roman = (P.inv.kind == RB_INVARIANT_ROMAN);
   for (int I = blockIdx.x * 8 + warp; I < pr.nb; I += gridDim.x * 8) {
@@ -551,7 +554,7 @@ __global__ void __launch_bounds__(256) rb_affinity_kernel(const RbProblem* __res
   const RbProblem pr = probs[blockIdx.y];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nb = pr.nb;
-  if (nb == 0) return;
+  if (nb == 0 || pr.is_copy) return;
   // An association whose single score is below affinityeps (clipper.cpp:104-108), or padding, can
   // have no edge at all (NaN scores are "live", exactly as the reference's `<` test);
   // rb_block_mask_kernel has condensed that into one word per 32-association block.
@@ -684,7 +687,7 @@ __global__ void rb_live_counts_kernel(const RbProblem* __restrict__ probs, int B
   if (b >= B) return;
   const RbProblem pr = probs[b];
   int c = 0;
-  for (int I = threadIdx.x & 31; I < pr.nb; I += 32) c += __popc(masks[(pr.off_pad >> 5) + I]);
+  for (int I = threadIdx.x & 31; I < pr.nb; I += 32) c += __popc(masks[(pr.off_rec >> 5) + I]);
   for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
   if ((threadIdx.x & 31) == 0) out[b] = c;
 }

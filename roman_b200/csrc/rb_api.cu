@@ -24,6 +24,7 @@ struct rb_handle {
   int32_t B = 0, d = 0;
   bool all_to_all = true;
   bool indexed = false;      // rb_plan_indexed: problems reference ranges of shared object tables
+  bool shared = false;       // rb_plan_shared: some problems use another problem's matrix (one range only)
   std::vector<RbProblem> probs;
   std::vector<int64_t> tile_prefix;  // B+1
   int64_t total_assoc = 0, total_pad = 0, total_tiles = 0, total_obj1 = 0, total_obj2 = 0;
@@ -360,10 +361,17 @@ int rb_get_stage_ms(rb_handle* h, float ms[4]) {
 }
 
 static int plan_impl(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const int32_t* n2, const int32_t* m,
-                     const int64_t* off1, const int64_t* off2, int64_t tot1, int64_t tot2);
+                     const int64_t* off1, const int64_t* off2, int64_t tot1, int64_t tot2, const int32_t* share = nullptr);
 
 int rb_plan(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const int32_t* n2, const int32_t* m) {
   return plan_impl(h, B, d, n1, n2, m, nullptr, nullptr, 0, 0);
+}
+
+int rb_plan_shared(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const int32_t* n2, const int32_t* m,
+                   const int64_t* obj1_offset, const int64_t* obj2_offset, int64_t total_obj1, int64_t total_obj2,
+                   const int32_t* share) {
+  if (B > 0 && (!obj1_offset || !obj2_offset || !share)) return h ? fail(h, RB_ERR_ARG, "rb_plan_shared: null argument") : RB_ERR_ARG;
+  return plan_impl(h, B, d, n1, n2, m, obj1_offset, obj2_offset, total_obj1, total_obj2, share);
 }
 
 int rb_plan_indexed(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const int32_t* n2, const int32_t* m,
@@ -373,7 +381,7 @@ int rb_plan_indexed(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const
 }
 
 static int plan_impl(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, const int32_t* n2, const int32_t* m,
-                     const int64_t* off1, const int64_t* off2, int64_t tot1, int64_t tot2) {
+                     const int64_t* off1, const int64_t* off2, int64_t tot1, int64_t tot2, const int32_t* share) {
   if (!h) return RB_ERR_ARG;
   if (B < 0 || d < 1 || (B > 0 && (!n1 || !n2))) return fail(h, RB_ERR_ARG, "rb_plan: bad arguments");
   RB_CUDA(h, cudaSetDevice(h->device));
@@ -395,7 +403,21 @@ static int plan_impl(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, cons
       return fail(h, RB_ERR_ARG, "rb_plan_indexed: object range outside the shared tables");
     p.off_assoc = oa; p.off_pad = op; p.off_tile = ot;
     p.n_tiles = (int64_t)p.nb * (p.nb + 1) / 2;
+    p.base = b; p.is_copy = 0; p.off_rec = op;
     h->tile_prefix[(size_t)b] = ot;
+    if (share && share[b] != b) {  // uses the matrix, records and edge list of an earlier problem of the same shape
+      const int sb = share[b];
+      if (sb < 0 || sb > b || share[sb] != sb) return fail(h, RB_ERR_ARG, "rb_plan_shared: share[b] must name an earlier problem that owns its matrix");
+      const RbProblem& q = h->probs[(size_t)sb];
+      if (q.n1 != p.n1 || q.n2 != p.n2 || q.m != p.m || q.off_obj1 != p.off_obj1 || q.off_obj2 != p.off_obj2)
+        return fail(h, RB_ERR_ARG, "rb_plan_shared: problems that share a matrix must have identical shapes and object ranges");
+      p.base = sb; p.is_copy = 1; p.off_rec = q.off_pad; p.off_tile = q.off_tile;
+      o1 += n1[b]; o2 += n2[b]; oa += mm; op += (int64_t)p.nb * RB_TILE;   // private vectors and outputs, no tiles
+      if (p.nb * RB_TILE > max_mp) max_mp = p.nb * RB_TILE;
+      if (n1[b] > mx1) mx1 = n1[b];
+      if (n2[b] > mx2) mx2 = n2[b];
+      continue;
+    }
     o1 += n1[b]; o2 += n2[b]; oa += mm; op += (int64_t)p.nb * RB_TILE; ot += p.n_tiles;
     if (p.nb * RB_TILE > max_mp) max_mp = p.nb * RB_TILE;
     if (n1[b] > mx1) mx1 = n1[b];
@@ -417,6 +439,7 @@ static int plan_impl(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, cons
   h->total_assoc = oa; h->total_pad = op; h->total_tiles = ot;
   h->total_obj1 = off1 ? tot1 : o1; h->total_obj2 = off2 ? tot2 : o2;
   h->indexed = (off1 != nullptr);
+  h->shared = (share != nullptr);
   h->max_mp = max_mp;
   h->max_n1 = mx1;
   h->max_n2 = mx2;
@@ -533,7 +556,7 @@ static int plan_impl(rb_handle* h, int32_t B, int32_t d, const int32_t* n1, cons
     // ranges exist to overlap the upload with the kernels: with little to upload (shared object tables, small maps)
     // one range — one launch sequence, one solver tail — is faster
     const double h2d_bytes = 8.0 * ((double)(off1 ? tot1 : o1) + (double)(off2 ? tot2 : o2)) * d + 8.0 * (double)oa + (m ? 8.0 * (double)oa : 0.0);
-    if (!getenv("RB_HOST_SPLIT") && h2d_bytes < 24.0e6) { nch = 1; nw = 0; }
+    if ((!getenv("RB_HOST_SPLIT") && h2d_bytes < 24.0e6) || share) { nch = 1; nw = 0; }  // sharing groups must not straddle ranges
     // ranges are cut by WORK (tiles), not by problem count: ragged batches arrive longest-first
     double tot = 0.0, acc = 0.0;
     for (int c = 0; c < nch; ++c) tot += nw ? wts[c] : 1.0;
@@ -667,8 +690,8 @@ int dsd_epilogue(rb_handle* h, int b0, int b1, int32_t* nodes, int32_t* sel, int
     hn[q] = n_out;
     if (n_out > 0) {
       RB_CUDA(h, cudaMemcpyAsync(nodes + pr.off_assoc, out.data(), (size_t)n_out * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-      RB_CUDA(h, rb_launch_select(nodes + pr.off_assoc, n_out, h->d_pad_i32 + pr.off_pad,
-                                  h->d_pad_i32 + (size_t)h->total_pad + pr.off_pad, sel + 2 * pr.off_assoc, st));
+      RB_CUDA(h, rb_launch_select(nodes + pr.off_assoc, n_out, h->d_pad_i32 + pr.off_rec,
+                                  h->d_pad_i32 + (size_t)h->total_pad + pr.off_rec, sel + 2 * pr.off_assoc, st));
       RB_CUDA(h, cudaStreamSynchronize(st));  // `out` is reused by the next problem
     }
   }
@@ -681,7 +704,7 @@ int solve_range(rb_handle* h, int b0, int b1, int queue, const int32_t* order, c
                 int32_t* n_nodes, double* u, double* score, int32_t* ifinal, int32_t* n_passes, cudaStream_t st) {
   if (b1 <= b0) return RB_OK;
   RbSolveArgs a;
-  a.probs = h->d_probs + b0; a.B = b1 - b0; a.counter = h->d_counter + queue; a.Mp = h->d_M;
+  a.probs = h->d_probs + b0; a.B = b1 - b0; a.b0 = b0; a.counter = h->d_counter + queue; a.Mp = h->d_M;
   a.order = order;
   a.flags = h->tile_skip ? h->d_flags : nullptr;
   a.edge_ij = h->edges_valid ? h->d_edge_ij : nullptr;
@@ -813,6 +836,7 @@ int rb_set_dense(rb_handle* h, int32_t b, const double* M, const double* C, void
   RB_ENTER(h);
   cudaStream_t st = (cudaStream_t)stream;
   const RbProblem& pr = h->probs[(size_t)b];
+  if (pr.is_copy) return fail(h, RB_ERR_ARG, "rb_set_dense: problem shares another problem's matrix (rb_plan_shared); set the owner");
   RB_CUDA(h, cudaMemsetAsync(h->d_bad, 0, sizeof(int), st));
   // set_matrix_data carries no association table: nodes map to themselves (sel = (node, 0))
   const size_t n = (size_t)pr.nb * RB_TILE;

@@ -33,6 +33,11 @@ struct RbProblem {
   int64_t off_pad;             // offset into internal padded per-association arrays (sum of nb*32)
   int64_t off_tile;            // offset (in tiles) into the packed M buffer
   int64_t n_tiles;
+  // Problems may SHARE an affinity matrix (multi-start: K start vectors on one submap pair, rb_plan_shared): `base` is
+  // the batch index of the problem that owns the matrix, the association records and the edge list (== own index for
+  // ordinary problems), off_rec its off_pad; K1 skips the copies, K2 / K3 run on every problem with private vectors.
+  int32_t base, is_copy;
+  int64_t off_rec;
 };
 
 // Internal SoA association records, padded arrays of length sum(nb*32).

@@ -13,6 +13,7 @@ struct RbDevParams {
 struct RbSolveArgs {
   const RbProblem* probs;
   int32_t B;
+  int32_t b0;              // batch index of probs[0] (problem ranges): RbProblem::base is a batch index
   int32_t* counter;        // dynamic problem queue (zeroed before launch)
   const int32_t* order;    // queue position -> problem index (longest problem first), or null = identity
   const double* Mp;        // packed tiles

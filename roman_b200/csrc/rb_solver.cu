@@ -825,10 +825,10 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
     }
     // K1 lists every non-zero word of the strict upper triangle (12 bytes per edge, capacity RB_EDGE_FACTOR * mp per
     // problem; a count above the capacity means the list overflowed and is not used).
-    const int e_n = (A.edge_cnt != nullptr) ? A.edge_cnt[b] : -1;
+    const int e_n = (A.edge_cnt != nullptr) ? A.edge_cnt[pr.base - A.b0] : -1;  // the list belongs to the matrix's owner
     const bool have_list = (A.edge_ij != nullptr) && e_n >= 0 && e_n <= RB_EDGE_FACTOR * mp;
-    const unsigned* e_ij = have_list ? A.edge_ij + (size_t)pr.off_pad * RB_EDGE_FACTOR : nullptr;
-    const double* e_v = have_list ? A.edge_v + (size_t)pr.off_pad * RB_EDGE_FACTOR : nullptr;
+    const unsigned* e_ij = have_list ? A.edge_ij + (size_t)pr.off_rec * RB_EDGE_FACTOR : nullptr;
+    const double* e_v = have_list ? A.edge_v + (size_t)pr.off_rec * RB_EDGE_FACTOR : nullptr;
     bool compact = false;   // passes run from the shared-memory CSR
     bool solo = false;      // C > 1 and every CTA holds the WHOLE matrix: nothing to combine, no cluster barrier per pass
     bool from_list = false;
@@ -1126,8 +1126,8 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
     int32_t* sel = A.sel + 2 * pr.off_assoc;
     for (int p = tid; p < n_sel; p += NT) {
       const int nd = nodes[p];
-      sel[2 * p] = A.i1[pr.off_pad + nd];
-      sel[2 * p + 1] = A.i2[pr.off_pad + nd];
+      sel[2 * p] = A.i1[pr.off_rec + nd];
+      sel[2 * p + 1] = A.i2[pr.off_rec + nd];
     }
     if (A.u_out) {
       double* uo = A.u_out + pr.off_assoc;

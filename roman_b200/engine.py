@@ -177,9 +177,10 @@ class Engine:
 
     def plan(self, d: int, n1: Sequence[int], n2: Sequence[int], m: Optional[Sequence[int]] = None,
              obj1_offsets: Optional[Sequence[int]] = None, obj2_offsets: Optional[Sequence[int]] = None,
-             total_obj1: Optional[int] = None, total_obj2: Optional[int] = None):
+             total_obj1: Optional[int] = None, total_obj2: Optional[int] = None, share: Optional[Sequence[int]] = None):
         """Describe the batch shapes (host side).  m=None: all-to-all associations.
-        obj*_offsets: problems reference row ranges of shared object tables (rb_plan_indexed)."""
+        obj*_offsets: problems reference row ranges of shared object tables (rb_plan_indexed).
+        share: share[b] = index of the problem whose affinity matrix problem b uses (rb_plan_shared; multi-start)."""
         n1a = np.ascontiguousarray(n1, dtype=np.int32)
         n2a = np.ascontiguousarray(n2, dtype=np.int32)
         B = len(n1a)
@@ -192,9 +193,16 @@ class Engine:
             o1 = np.ascontiguousarray(obj1_offsets, dtype=np.int64)
             o2 = np.ascontiguousarray(obj2_offsets, dtype=np.int64)
             assert len(o1) == B and len(o2) == B
-            self._check(self._lib.rb_plan_indexed(self._h, B, int(d), n1a.ctypes.data, n2a.ctypes.data,
-                                                  None if ma is None else ma.ctypes.data, o1.ctypes.data,
-                                                  o2.ctypes.data, int(total_obj1), int(total_obj2)))
+            if share is None:
+                self._check(self._lib.rb_plan_indexed(self._h, B, int(d), n1a.ctypes.data, n2a.ctypes.data,
+                                                      None if ma is None else ma.ctypes.data, o1.ctypes.data,
+                                                      o2.ctypes.data, int(total_obj1), int(total_obj2)))
+            else:
+                sh = np.ascontiguousarray(share, dtype=np.int32)
+                assert len(sh) == B
+                self._check(self._lib.rb_plan_shared(self._h, B, int(d), n1a.ctypes.data, n2a.ctypes.data,
+                                                     None if ma is None else ma.ctypes.data, o1.ctypes.data,
+                                                     o2.ctypes.data, int(total_obj1), int(total_obj2), sh.ctypes.data))
         self.B, self.d, self.all_to_all = B, int(d), ma is None
         self.offsets = np.array([self._lib.rb_assoc_offset(self._h, b) for b in range(B + 1)], dtype=np.int64)
         self.obj1_offsets = np.array([self._lib.rb_obj1_offset(self._h, b) for b in range(B + 1)], dtype=np.int64)

@@ -181,6 +181,43 @@ def test_resident_csr_split_over_a_cluster(engine, coracle, cluster):
         engine.set_solver_promote(8)
 
 
+def test_shared_matrix_multistart_plan(engine, coracle):
+    """rb_plan_shared: K start vectors per submap pair on ONE stored affinity matrix.  Per start: bit-identical to the
+    same problem planned on its own; storage: one matrix per pair; K1's live / edge counts reported for the copies are
+    the owner's."""
+    ip_o, ip_g = params_for_method("roman", semantics_dim=24)
+    sp = cn.SolverParams()
+    shapes = [(18, 22), (30, 25)]
+    K = 4
+    pairs = [synth.make_pair(40 + i, a, b, method="roman", semantics_dim=24, desc_common=1.0) for i, (a, b) in enumerate(shapes)]
+    rng = np.random.default_rng(8)
+    u0s = [[rng.uniform(0, 1, a * b) for _ in range(K)] for (a, b) in shapes]
+    D1 = np.concatenate([p.D1 for p in pairs]); D2 = np.concatenate([p.D2 for p in pairs])
+    o1 = np.cumsum([0] + [a for a, _ in shapes]); o2 = np.cumsum([0] + [b for _, b in shapes])
+    n1 = [shapes[g][0] for g in range(2) for _ in range(K)]; n2 = [shapes[g][1] for g in range(2) for _ in range(K)]
+    engine.set_invariant_params(ip_g)
+    engine.plan(D1.shape[1], n1, n2, obj1_offsets=[o1[g] for g in range(2) for _ in range(K)],
+                obj2_offsets=[o2[g] for g in range(2) for _ in range(K)], total_obj1=len(D1), total_obj2=len(D2),
+                share=[g * K for g in range(2) for _ in range(K)])
+    nt = lambda m: ((m + 31) // 32) * ((m + 31) // 32 + 1) // 2
+    assert engine.packed_bytes == 8192 * sum(nt(a * b) for a, b in shapes)          # one matrix per pair, not K
+    shared = engine.align_batch_host(np.ascontiguousarray(D1), np.ascontiguousarray(D2), np.concatenate([u for g in u0s for u in g]))
+    Mg, _ = engine.get_dense(K + 1)                                                  # a copy reads its owner's matrix
+    Mo, _, _, _ = coracle.score(ip_o, sp.affinityeps, pairs[1].D1, pairs[1].D2)
+    assert np.abs(Mg.cpu().numpy() - (Mo + Mo.T + np.eye(len(Mo)))).max() <= M_TOL
+    for g, p in enumerate(pairs):
+        for k in range(K):
+            b = g * K + k
+            engine.plan(p.D1.shape[1], [shapes[g][0]], [shapes[g][1]])
+            alone = engine.align_batch_host(np.ascontiguousarray(p.D1), np.ascontiguousarray(p.D2), u0s[g][k])
+            o = sum(shapes[h][0] * shapes[h][1] * K for h in range(g)) + k * shapes[g][0] * shapes[g][1]
+            n = int(shared["n_sel"][b])
+            assert n == int(alone["n_sel"][0]) and np.array_equal(shared["sel"][o:o + n], alone["sel"][:n])
+            assert shared["score"][b] == alone["score"][0] and np.array_equal(shared["T"][b], alone["T"][0], equal_nan=True)
+            ref = coracle.align_pair(ip_o, sp, p.D1, p.D2, u0s[g][k])
+            assert np.array_equal(shared["sel"][o:o + n], ref["sel"])
+
+
 def test_explicit_associations_euclidean(engine, coracle):
     """clipper+prune style: EuclideanDistance invariant on an arbitrary (pruned) association list."""
     rng = np.random.default_rng(5)
