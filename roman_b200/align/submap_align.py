@@ -231,6 +231,7 @@ def align_submap_pairs(sm_params: SubmapAlignParams, submaps0: Sequence[List], s
     if timing is not None:
         timing["registration_seconds"] = _time.perf_counter() - t0
         timing["n_registered"] = len(pairs)
+        timing["n_empty"] = int((res.status_mat == 1).sum())   # pairs with an empty map: never handed to register()'s solver
 
     T = out["T"].copy()
     status = out["status"].astype(np.int32).copy()
@@ -427,8 +428,13 @@ def submap_align(sm_params: SubmapAlignParams, sm_io, u0=None):
                     similarity_mat=z.copy() if sm_params.submap_descriptor is not None else None, submap_yaw_diff_mat=z.copy(),
                     associated_objs_mat=[[[] for _ in range(S1)] for _ in range(S0)],
                     T_ij_mat=np.zeros((S0, S1, 4, 4)) * np.nan, T_ij_hat_mat=np.zeros((S0, S1, 4, 4)) * np.nan)
+    # one entry per register() call — and, as in the reference, a second one for a pair whose T_align / gravity check
+    # raised afterwards (submap_align.py:157 and :180 both append)
     n_reg = int(timing.get("n_registered", 0))
-    timing_list = [timing.get("registration_seconds", 0.0) / n_reg] * n_reg if n_reg else []
+    n_calls = n_reg + int(timing.get("n_empty", 0))          # an empty map still goes through register() (it returns at once)
+    n_failed = int(np.isin(pr.status_mat, (1, 2)).sum()) if (S0 and S1) else 0
+    share_t = timing.get("registration_seconds", 0.0) / n_reg if n_reg else 0.0
+    timing_list = [share_t] * (n_calls + n_failed)
     results = SubmapAlignResults(timing_list=timing_list, submap_align_params=sm_params, submap_io=sm_io,
                                  total_time=_time.time() - total_t0, **mats)
     os.makedirs(sm_io.output_dir, exist_ok=True)
