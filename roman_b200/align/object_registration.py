@@ -92,6 +92,10 @@ class ObjectRegistration:
         correspondences = self.register(map1, map2) if correspondences is None else correspondences
         if len(correspondences) < self.dim:      # Arun's method needs at least `dim` point pairs
             raise InsufficientAssociationsException(n1, n2, len(correspondences))
+        corr = np.asarray(correspondences, dtype=np.int64).reshape(-1, 2)
+        if ((corr[:, 0] < -n1) | (corr[:, 0] >= n1) | (corr[:, 1] < -n2) | (corr[:, 1] >= n2)).any():
+            raise IndexError("list index out of range")       # what map1[corr[i, 0]] raises in the reference (:110-111)
+        correspondences = np.stack([corr[:, 0] % n1, corr[:, 1] % n2], axis=1)   # negative indices count from the end, as Python lists do
         pts1 = np.array([np.asarray(o.center).reshape(-1)[:self.dim] for o in map1], dtype=np.float64)
         pts2 = np.array([np.asarray(o.center).reshape(-1)[:self.dim] for o in map2], dtype=np.float64)
         T = _arun_gpu(pts1, pts2, np.asarray(correspondences), self.dim)

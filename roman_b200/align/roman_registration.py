@@ -158,6 +158,7 @@ class ROMANRegistration(ObjectRegistration):
         sel = res.sel.cpu().numpy()
         T = res.T.cpu().numpy()
         status = res.status.cpu().numpy().copy()
+        self.last_scores = res.score.cpu().numpy().copy()      # objective value F of every pair of the last batch
         assoc = [sel[int(e.offsets[b]):int(e.offsets[b]) + int(n_sel[b])].copy() for b in range(B)]
         if self.dim == 2:
             T3 = np.tile(np.eye(3), (B, 1, 1))

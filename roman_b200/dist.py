@@ -89,11 +89,13 @@ def unshard(g_rec: torch.Tensor, n_items: int, g_inl: Optional[torch.Tensor] = N
 
 
 def register_pairs_distributed(registration, pairs: Sequence[Tuple[List, List]], u0: Optional[Sequence[np.ndarray]] = None,
-                               max_k: int = 64, device=None):
+                               max_k: Optional[int] = None, device=None):
     """
     All-pairs loop-closure search over the ranks: each rank registers the pairs g with
     g mod world == rank through `registration.register_batch`, then one all-gather makes the
     complete result table available on every rank, in the order of `pairs`.
+    `max_k` (rows of the padded inlier lists) defaults to the largest inlier count over all ranks (one tiny
+    all-reduce), so no list is ever truncated; a caller-given max_k smaller than a list raises.
     """
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
@@ -107,7 +109,16 @@ def register_pairs_distributed(registration, pairs: Sequence[Tuple[List, List]],
         k = T.shape[1]
         T4[:, :k - 1, :k - 1] = T[:, :k - 1, :k - 1]
         T4[:, :k - 1, 3] = T[:, :k - 1, k - 1]
-    rec = pack_records(status, n_sel, np.zeros(len(mine)), T4, slots, device=device)
+    k_local = int(n_sel.max(initial=0))
+    if max_k is None:
+        kt = torch.tensor([k_local], dtype=torch.int64, device=device if device is not None else "cpu")
+        if world > 1:
+            dist.all_reduce(kt, op=dist.ReduceOp.MAX)
+        max_k = max(int(kt.item()), 1)
+    elif k_local > max_k:
+        raise ValueError(f"max_k = {max_k} is smaller than an inlier list of this rank ({k_local} associations)")
+    scores = getattr(registration, "last_scores", None)
+    rec = pack_records(status, n_sel, np.zeros(len(mine)) if scores is None or len(scores) != len(mine) else scores, T4, slots, device=device)
     inl = pack_inliers(assoc, slots, max_k, device=device)
     g_rec, g_inl = all_gather_records(rec, inl)
     return unshard(g_rec, len(pairs), g_inl)
