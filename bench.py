@@ -387,6 +387,11 @@ def run_b200(args):
     eng.set_invariant_params(make_invariant_params(**method_invariant_kwargs(METHOD, semantics_dim=SEM_DIM)))
     if args.promote >= 0:
         eng.set_solver_promote(args.promote)
+    if args.cluster > 0:
+        eng.set_solver_cluster(args.cluster)
+    elif args.config == "cfg5":   # the preset roman_b200.align.align_submap_pairs applies to an all-pairs search
+        from roman_b200.align.submap_align import ALL_PAIRS_SOLVER_CLUSTER
+        eng.set_solver_cluster(ALL_PAIRS_SOLVER_CLUSTER)
     eng.set_profiling(True)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a).reshape(-1)).pin_memory()
 
@@ -671,6 +676,7 @@ def main():
     ap.add_argument("--rank-offset", type=int, default=0,
                     help="dev: shift the synthetic seeds by this many ranks (run another rank's batch on this GPU)")
     ap.add_argument("--promote", type=int, default=-1, help="dev: rb_set_solver_promote value (-1 = library default)")
+    ap.add_argument("--cluster", type=int, default=0, help="dev: CTAs per problem in the solver (0 = library default)")
     ap.add_argument("--format", default="both", choices=["both", "dense"],
                     help="both: also time the opt-in sparse fast path (fast_path block, N = 1); dense: default format only")
     args = ap.parse_args()

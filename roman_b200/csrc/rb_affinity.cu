@@ -214,59 +214,67 @@ __global__ void __launch_bounds__(256) rb_prep_kernel(const RbProblem* __restric
 
 
 // ---------------------------------------------------------------------------------------------
-// K1a for all-to-all plans: the n1 x n2 cosine table is a small dense contraction (descriptors^T * descriptors) and
-// is evaluated as one, instead of re-reading two D-vectors per association.
+// K1a for all-to-all plans: the n1 x n2 cosine table is the one dense contraction of this path (descriptors^T *
+// descriptors, n1 x D x n2) and is evaluated as one — on the fp64 tensor-core path (mma.sync.m8n8k4.f64, SASS DMMA) —
+// instead of re-reading two D-vectors per association.
 //
-// One CTA per (<= 64) x (<= 64) block of (object of map 1, object of map 2).  The compute threads form a TY x TX grid
-// with MR x 4 outputs each (rows ty + r*TY of map 1, columns tx + c*TX of map 2); MR is 4 or 5, whichever fills whole
-// warps better for the batch's largest maps (40 x 50 objects: 5 x 4 outputs on 8 x 13 threads = 4 warps, one per
-// scheduler; 4 x 4 would need a fifth warp with two live lanes that costs a full warp's issue slots).  One more warp
-// accumulates the squared norms of all rows of the block.  Four such CTAs share an SM.
+// One CTA per (<= 64) x (<= 64) block of (object of map 1, object of map 2).  Compute warp w owns the 8 map-1 objects
+// 8w .. 8w+7 and all NCB 8-object column blocks of map 2: per 4 descriptor columns it loads one A fragment and NCB B
+// fragments (one double per lane each) and issues NCB DMMAs, accumulating two doubles per lane per column block.  One
+// more warp accumulates the squared norms of all rows of the block.  40 x 50 objects: 5 compute warps x 7 column
+// blocks; four such CTAs share an SM.
 //
-// Staging: descriptor columns [k0, k0 + 16) of all rows of the block form one stage ([row][k], 17 doubles per row); a
-// ring of 4 stages is filled with asynchronous global->shared copies (cp.async, 8 bytes each — SASS LDGSTS) issued
-// three stages ahead, so HBM latency hides behind the fp64 work of the stages in between and the main loop has ONE
-// block barrier per 16 columns.  Why not the bulk / TMA form the solver uses for its 8 KB tiles: object rows are
-// d = 3 + r + D doubles long (775 for the `roman` method, odd), so every other row starts 8 bytes off a 16-byte
-// boundary; cp.async.bulk and tensor maps both need 16-byte aligned sources and strides.
+// Why the tensor pipe although its fp64 rate equals the FMA pipe's: shared-memory bandwidth.  An FMA register tile
+// needs (MR + NR) operand words per MR * NR multiply-adds per lane and every 8-byte shared load costs two wavefronts
+// (measured: a 5 x 4 tile stalls at 54 % of the fp64 peak, tools/micro/fp64_rate.cu); the MMA fragments of a warp
+// hold 32 operands for 256 multiply-adds — a third of the wavefronts.
 //
-// Shared-memory traffic is what bounds this kernel next to the fp64 pipe (128 B / clock / SM against 64 FMA / clock:
-// a 4 x 4 register tile fed with 16-byte loads needs twice that).  Operands are therefore read as 8-byte words with
-// an ODD row pitch: the lanes of a warp then touch at most 13 distinct words per load, all in different banks, and
-// lanes that share a row are served by broadcast — one wavefront per load, 8-9 loads per 16-20 FMAs.
+// Staging: descriptor columns [k0, k0 + 16) of all rows of the block form one stage ([row][k], pitch 20 doubles: a
+// fragment load touches rows g = 0..7 x columns t = 0..3, and 20 = 4 mod 16 puts the 16 words of a half-warp into 16
+// different bank pairs); a ring of 4 stages is filled with asynchronous global->shared copies (cp.async, 8 bytes each
+// — SASS LDGSTS) issued three stages ahead (the loop is latency-bound on HBM otherwise: 12 KB per stage and CTA); ONE
+// block barrier per 16 columns.  Why not the bulk / TMA form the solver
+// uses for its 8 KB tiles: object rows are d = 3 + r + D doubles long (775 for the `roman` method, odd), so every
+// other row starts 8 bytes off a 16-byte boundary; cp.async.bulk and tensor maps need 16-byte aligned sources.
 //
-// Arithmetic: each dot product and squared norm is accumulated sequentially over the descriptor index (the order of
-// the scalar loop) with fused multiply-adds, exactly as in round 1 — one thread owns an output (or a norm) from k = 0
-// to D - 1, nothing is split or tree-reduced, so the cosine gate `<= cosine_min` sees bit-identical inputs.
+// Arithmetic: every dot product is a chain of fp64 fused multiply-adds over the descriptor index in ascending order
+// (the m8n8k4 DMMA accumulates its four products in k order, each with a single rounding), the squared norms likewise
+// in the norm warp: the same values as a scalar loop with fma(), so the cosine gate `<= cosine_min` sees what it saw
+// in round 1.  Nothing is split across threads or tree-reduced; results do not depend on the launch shape.
 constexpr int PREP_KC = 16;           // descriptor columns per stage
-constexpr int PREP_LD = PREP_KC + 1;  // shared-memory row pitch (doubles): odd -> consecutive rows start in different banks
-constexpr int PREP_STAGES = 4;
+constexpr int PREP_LD = 20;           // shared-memory row pitch (doubles): 4 mod 16, see above
+constexpr int PREP_STAGES = 4;         // copies run three stages (48 columns) ahead of the arithmetic
 constexpr int PREP_HEAD = 8;          // leading (non-descriptor) columns of a row kept for the epilogue: centre + ratio features
+constexpr int PREP_MAXCB = 8;         // column blocks per warp (n2 <= 64 per block of the grid)
 
 __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// D(8x8) += A(8x4, row) * B(4x8, col), fp64: lane l holds A[l>>2][l&3], B[l&3][l>>2], D[l>>2][2*(l&3) + {0,1}]
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
 
-template <int MR>
-__global__ void __launch_bounds__(160, 4) rb_prep_table_kernel(const RbProblem* __restrict__ probs, RbAssocSoA rec,
+template <int NCB>
+__global__ void __launch_bounds__(288, 2) rb_prep_table_kernel(const RbProblem* __restrict__ probs, RbAssocSoA rec,
                                                                const double* __restrict__ D1,
                                                                const double* __restrict__ D2, RbDevParams P,
-                                                               int tiles2_max, int TY, int TX) {
+                                                               int tiles2_max, int NRB) {
   extern __shared__ __align__(16) unsigned char prep_smem[];
   const RbProblem pr = probs[blockIdx.y];
   if (pr.is_copy) return;  // shares another problem's matrix and records (rb_plan_shared)
   const rb_invariant_params& p = P.inv;
-  const int PT1 = MR * TY, PT2 = 4 * TX, R = PT1 + PT2;
-  const int NC = ((TY * TX + 31) / 32) * 32;   // compute threads (whole warps); the last warp of the CTA takes the norms
-  const int NTH = blockDim.x;                  // NC + 32
+  const int PT1 = 8 * NRB, PT2 = 8 * NCB, R = PT1 + PT2;
+  const int NTH = blockDim.x;                  // 32 * NRB compute threads + 32 (norm warp)
   double* stage0 = reinterpret_cast<double*>(prep_smem);                // [PREP_STAGES][R][PREP_LD]
   double* s_norm = stage0 + (size_t)PREP_STAGES * R * PREP_LD;          // [R] squared norms
   double* s_head = s_norm + R;                                          // [R][PREP_HEAD] centres and ratio features
+  const double** s_rowp = reinterpret_cast<const double**>(s_head + (size_t)R * PREP_HEAD);   // [R] descriptor row starts (null: no such object)
   const int t1 = blockIdx.x / tiles2_max, t2 = blockIdx.x % tiles2_max;
   const int i1_0 = t1 * PT1, i2_0 = t2 * PT2;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (blockIdx.x == 0) {  // padding records of this problem
     for (int k = pr.m + tid; k < pr.nb * RB_TILE; k += NTH) {
       const int64_t o = pr.off_pad + k;
@@ -277,9 +285,7 @@ __global__ void __launch_bounds__(160, 4) rb_prep_table_kernel(const RbProblem* 
     }
   }
   if (i1_0 >= pr.n1 || i2_0 >= pr.n2) return;
-  const bool active = tid < TY * TX;
-  const bool norm_warp = tid >= NC;
-  const int tx = active ? tid % TX : 0, ty = active ? tid / TX : 0;
+  const bool norm_warp = warp == NRB;
   const double* A0 = D1 + pr.off_obj1 * (int64_t)pr.d;
   const double* B0 = D2 + pr.off_obj2 * (int64_t)pr.d;
   const int foff = p.point_dim + p.ratio_feature_dim;
@@ -295,31 +301,35 @@ __global__ void __launch_bounds__(160, 4) rb_prep_table_kernel(const RbProblem* 
     if (is1 ? o >= pr.n1 : o >= pr.n2) return nullptr;
     return (is1 ? A0 : B0) + (int64_t)o * pr.d;
   };
-  auto issue = [&](int c) {  // asynchronous copies of chunk c into stage c % PREP_STAGES
-    double* st = stage0 + (size_t)(c % PREP_STAGES) * R * PREP_LD;
-    const int k0 = c * PREP_KC;
-    for (int e = tid; e < R * PREP_KC; e += NTH) {  // 16 consecutive threads -> 16 consecutive columns of one row (128 B)
-      const int q = e / PREP_KC, k = e % PREP_KC;
-      const double* src = row_ptr(q);
-      double* dst = st + q * PREP_LD + k;
-      if (src != nullptr && (k0 + k) < Dc) cp_async_8(dst, src + foff + k0 + k);
-      else *dst = 0.0;
-    }
-  };
+  for (int q = tid; q < R; q += NTH) {
+    const double* src = row_ptr(q);
+    s_rowp[q] = src ? src + foff : nullptr;
+  }
   for (int e = tid; e < R * PREP_HEAD; e += NTH) {  // centres and ratio features for the epilogue
     const int q = e / PREP_HEAD, k = e % PREP_HEAD;
     const double* src = row_ptr(q);
     s_head[e] = (src != nullptr && k < nhead) ? src[k] : 0.0;
   }
+  __syncthreads();
+  const int kk = tid % PREP_KC, q0 = tid / PREP_KC, qstep = NTH / PREP_KC;   // NTH is a multiple of 32, PREP_KC = 16
+  auto issue = [&](int c) {  // asynchronous copies of chunk c into stage c % PREP_STAGES
+    double* st = stage0 + (size_t)(c % PREP_STAGES) * R * PREP_LD + kk;
+    const int kcol = c * PREP_KC + kk;
+    const bool kin = kcol < Dc;
+    for (int q = q0; q < R; q += qstep) {  // 16 consecutive threads -> 16 consecutive columns of one row (128 B)
+      const double* src = s_rowp[q];
+      double* dst = st + q * PREP_LD;
+      if (src != nullptr && kin) cp_async_8(dst, src + kcol);
+      else *dst = 0.0;
+    }
+  };
 
-  double acc[MR][4];
+  double acc[NCB][2];
 #pragma unroll
-  for (int r = 0; r < MR; ++r)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
-  constexpr int NJ = 4;              // norm warp: rows lane, lane + 32, ... of the block (R <= 5 * 8 + 4 * 16 = 104)
+  for (int c = 0; c < NCB; ++c) acc[c][0] = acc[c][1] = 0.0;
+  constexpr int NJ = 4;              // norm warp: rows lane, lane + 32, ... of the block (R <= 128)
   double nrm[NJ] = {0.0, 0.0, 0.0, 0.0};
-  const int lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
 
   for (int c = 0; c < PREP_STAGES - 1; ++c) {
     if (c < nchunks) issue(c);
@@ -332,22 +342,19 @@ __global__ void __launch_bounds__(160, 4) rb_prep_table_kernel(const RbProblem* 
     if (c + PREP_STAGES - 1 < nchunks) issue(c + PREP_STAGES - 1);
     cp_async_commit();
     const double* st = stage0 + (size_t)(c % PREP_STAGES) * R * PREP_LD;
-    if (active) {
-      const double* pa = st + ty * PREP_LD;
-      const double* pb = st + (PT1 + tx) * PREP_LD;
-#pragma unroll 4
-      for (int k = 0; k < PREP_KC; ++k) {
-        double a[MR], b[4];
+    if (!norm_warp) {
+      const double* pa = st + (warp * 8 + g) * PREP_LD + t;
+      const double* pb = st + (PT1 + g) * PREP_LD + t;
 #pragma unroll
-        for (int r = 0; r < MR; ++r) a[r] = pa[r * TY * PREP_LD + k];
+      for (int k = 0; k < PREP_KC; k += 4) {
+        const double a = pa[k];
+        double b[NCB];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) b[q] = pb[q * TX * PREP_LD + k];
+        for (int q = 0; q < NCB; ++q) b[q] = pb[q * 8 * PREP_LD + k];
 #pragma unroll
-        for (int r = 0; r < MR; ++r)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) acc[r][q] = fma(a[r], b[q], acc[r][q]);
+        for (int q = 0; q < NCB; ++q) dmma_m8n8k4(acc[q][0], acc[q][1], a, b[q]);
       }
-    } else if (norm_warp) {
+    } else {
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const int q = lane + 32 * j;
@@ -366,24 +373,24 @@ __global__ void __launch_bounds__(160, 4) rb_prep_table_kernel(const RbProblem* 
     for (int j = 0; j < NJ; ++j)
       if (lane + 32 * j < R) s_norm[lane + 32 * j] = nrm[j];
   __syncthreads();
-  if (!active) return;
+  if (norm_warp) return;
 
   const int pd = (p.kind != RB_INVARIANT_EUCLIDEAN) ? p.point_dim : (pr.d < 3 ? pr.d : 3);
-  // MR x 4 outputs per thread, one instance of the scoring code (pow is long)
+  // 2 * NCB outputs per lane: row 8*warp + g of map 1, columns 8*cb + 2*t + {0, 1} of map 2; one instance of the
+  // scoring code (pow is long)
 #pragma unroll 1
-  for (int rq = 0; rq < MR * 4; ++rq) {
-    const int r = rq >> 2, q = rq & 3;
-    const int l1 = ty + r * TY, l2 = tx + q * TX;
+  for (int oq = 0; oq < 2 * NCB; ++oq) {
+    const int cb = oq >> 1, hi = oq & 1;
+    const int l1 = warp * 8 + g, l2 = cb * 8 + 2 * t + hi;
     const int i1 = i1_0 + l1, i2 = i2_0 + l2;
     if (i1 >= pr.n1 || i2 >= pr.n2) continue;
     const double* ha = s_head + l1 * PREP_HEAD;
     const double* hb = s_head + (PT1 + l2) * PREP_HEAD;
     double dotv = 0.0;
 #pragma unroll
-    for (int rr = 0; rr < MR; ++rr)
-#pragma unroll
-      for (int qq = 0; qq < 4; ++qq)
-        if (rr == r && qq == q) dotv = acc[rr][qq];  // register select: acc[][] must not be indexed dynamically
+    for (int q = 0; q < NCB; ++q) {  // register select: acc[][] must not be indexed dynamically
+      if (q == cb) dotv = hi ? acc[q][1] : acc[q][0];
+    }
     double single = 1.0;
     if (p.kind == RB_INVARIANT_ROMAN && (p.cos_feature_dim > 0 || p.ratio_feature_dim > 0)) {  // roman.cpp:116-164
       bool zero = false;
@@ -397,12 +404,12 @@ __global__ void __launch_bounds__(160, 4) rb_prep_table_kernel(const RbProblem* 
       if (!zero && p.ratio_feature_dim > 0) {
         double prod = 1.0;
         bool below = false;
-        for (int t = 0; t < p.ratio_feature_dim; ++t) {
-          const int col = p.point_dim + t;
+        for (int f = 0; f < p.ratio_feature_dim; ++f) {
+          const int col = p.point_dim + f;
           const double x = col < PREP_HEAD ? ha[col] : A0[(int64_t)i1 * pr.d + col];
           const double y = col < PREP_HEAD ? hb[col] : B0[(int64_t)i2 * pr.d + col];
           const double qv = x < y ? x / y : y / x;
-          if (qv < p.ratio_epsilon[t]) below = true;
+          if (qv < p.ratio_epsilon[f]) below = true;
           prod *= qv;
         }
         if (below) zero = true;
@@ -483,48 +490,65 @@ struct RbEdgeOut {
 };
 
 __device__ __forceinline__ void affinity_tile(const RbProblem& pr, int I, int J, unsigned row_live, unsigned col_live,
-                                              const RbAssocSoA& rec, Rec* s_row, double* __restrict__ Mp,
+                                              const RbAssocSoA& rec, Rec* s_row, Rec* s_col, unsigned char* s_idx,
+                                              double* __restrict__ Mp,
                                               uint8_t* __restrict__ flags, const RbEdgeOut& eo, const RbDevParams& P,
                                               int lane) {
   const int64_t q = rb_tile_index(I, J, pr.nb);
   double* out = Mp + (pr.off_tile + q) * RB_TILE_ELEMS;
-  const Rec col = load_rec(rec, pr.off_pad + (int64_t)J * RB_TILE + lane);
-  const Rec myrow = load_rec(rec, pr.off_pad + (int64_t)I * RB_TILE + lane);
   __syncwarp();
-  s_row[lane] = myrow;
-  __syncwarp();
+  s_col[lane] = load_rec(rec, pr.off_pad + (int64_t)J * RB_TILE + lane);
+  s_row[lane] = load_rec(rec, pr.off_pad + (int64_t)I * RB_TILE + lane);
+  // the whole tile as zeros first (coalesced 16-byte stores); the few non-zero words overwrite them below
+  {
+    double2* o2 = reinterpret_cast<double2*>(out);
+#pragma unroll
+    for (int t = 0; t < RB_TILE_ELEMS / 2 / 32; ++t) o2[t * 32 + lane] = make_double2(0.0, 0.0);
+  }
+  __syncwarp();  // orders the zero stores before the value stores of other lanes to the same words
   const bool diag = (I == J);
+  // Only (live row, live column) pairs are evaluated, and they are PACKED onto the lanes: pair p = (rows[p / nc],
+  // cols[p % nc]) over the nr live rows and nc live columns of the tile, 32 pairs per sweep.  With half of the
+  // associations live a lane-per-column sweep leaves half of every warp idle (measured: 17 of 32 threads active).
+  const int nr = __popc(row_live), nc = __popc(col_live);
+  const int npairs = nr * nc;
+  // tables: k-th live row / column of the tile
+  if ((row_live >> lane) & 1u) s_idx[__popc(row_live & ((1u << lane) - 1u))] = (unsigned char)lane;
+  if ((col_live >> lane) & 1u) s_idx[32 + __popc(col_live & ((1u << lane) - 1u))] = (unsigned char)lane;
+  __syncwarp();
   bool any_nz = false;
+  int ri = lane / nc, ci = lane % nc;            // pair index p = lane + 32 * sweep  ->  (ri, ci)
+  const int dr = 32 / nc, dc = 32 % nc;
   // One instance of the scoring code, no unrolling: the transcendental paths (exp, pow) are long, and several copies
-  // of them made the kernel's instruction footprint (~250 KB of SASS) thrash the instruction cache — 76 % of the
-  // warp stalls of the round-1 kernel on dense graphs were "no instruction".
-  // rows that cannot carry an edge: zeros (a cheap loop, kept apart from the scoring code so that it may be unrolled)
-#pragma unroll 8
-  for (int r = 0; r < RB_TILE; ++r)
-    if (!((row_live >> r) & 1u)) out[rb_tile_elem(r, lane)] = 0.0;
-  unsigned todo = row_live;
+  // of them made the kernel's instruction footprint (~250 KB of SASS in round 1) thrash the instruction cache.
 #pragma unroll 1
-  while (todo) {
-    const int r = __ffs(todo) - 1;
-    todo &= todo - 1;
+  for (int p0 = 0; p0 < npairs; p0 += 32) {
+    const bool in_range = ri < nr;
     double v = 0.0;
-    if (((col_live >> lane) & 1u) && !(diag && r == lane)) {  // r == lane: implicit identity (clipper.cpp:129-130)
-      const Rec row = s_row[r];
-      // i = the association with the smaller index: the row, except for the mirrored half of a diagonal tile
-      const bool mirrored = diag && r > lane;
-      Rec a, b;
-      a.ax = mirrored ? col.ax : row.ax; a.ay = mirrored ? col.ay : row.ay; a.az = mirrored ? col.az : row.az;
-      a.bx = mirrored ? col.bx : row.bx; a.by = mirrored ? col.by : row.by; a.bz = mirrored ? col.bz : row.bz;
-      a.s = mirrored ? col.s : row.s; a.i1 = mirrored ? col.i1 : row.i1; a.i2 = mirrored ? col.i2 : row.i2;
-      b.ax = mirrored ? row.ax : col.ax; b.ay = mirrored ? row.ay : col.ay; b.az = mirrored ? row.az : col.az;
-      b.bx = mirrored ? row.bx : col.bx; b.by = mirrored ? row.by : col.by; b.bz = mirrored ? row.bz : col.bz;
-      b.s = mirrored ? row.s : col.s; b.i1 = mirrored ? row.i1 : col.i1; b.i2 = mirrored ? row.i2 : col.i2;
-      v = pair_score(P, a, b);
+    int r = 0, c = 0;
+    if (in_range) {
+      r = s_idx[ri];
+      c = s_idx[32 + ci];
+      if (!(diag && r == c)) {  // r == c on the diagonal: implicit identity (clipper.cpp:129-130)
+        const Rec row = s_row[r];
+        const Rec col = s_col[c];
+        // i = the association with the smaller index: the row, except for the mirrored half of a diagonal tile
+        const bool mirrored = diag && r > c;
+        Rec a, b;
+        a.ax = mirrored ? col.ax : row.ax; a.ay = mirrored ? col.ay : row.ay; a.az = mirrored ? col.az : row.az;
+        a.bx = mirrored ? col.bx : row.bx; a.by = mirrored ? col.by : row.by; a.bz = mirrored ? col.bz : row.bz;
+        a.s = mirrored ? col.s : row.s; a.i1 = mirrored ? col.i1 : row.i1; a.i2 = mirrored ? col.i2 : row.i2;
+        b.ax = mirrored ? row.ax : col.ax; b.ay = mirrored ? row.ay : col.ay; b.az = mirrored ? row.az : col.az;
+        b.bx = mirrored ? row.bx : col.bx; b.by = mirrored ? row.by : col.by; b.bz = mirrored ? row.bz : col.bz;
+        b.s = mirrored ? row.s : col.s; b.i1 = mirrored ? row.i1 : col.i1; b.i2 = mirrored ? row.i2 : col.i2;
+        v = pair_score(P, a, b);
+      }
     }
-    any_nz |= (v != 0.0);
-    out[rb_tile_elem(r, lane)] = v;
+    const bool nz = (__double_as_longlong(v) != 0ll);
+    any_nz |= nz;
+    if (nz) out[rb_tile_elem(r, c)] = v;
     if (eo.count) {
-      const bool edge = (__double_as_longlong(v) != 0ll) && (!diag || r < lane);
+      const bool edge = nz && (!diag || r < c);
       const unsigned em = __ballot_sync(0xffffffffu, edge);
       if (em) {
         int base = 0;
@@ -532,11 +556,14 @@ __device__ __forceinline__ void affinity_tile(const RbProblem& pr, int I, int J,
         base = __shfl_sync(0xffffffffu, base, 0);
         const int pos = base + __popc(em & ((1u << lane) - 1u));
         if (edge && pos < eo.cap) {
-          eo.ij[pos] = ((unsigned)(I * RB_TILE + r) << 16) | (unsigned)(J * RB_TILE + lane);
+          eo.ij[pos] = ((unsigned)(I * RB_TILE + r) << 16) | (unsigned)(J * RB_TILE + c);
           eo.v[pos] = v;
         }
       }
     }
+    ri += dr;
+    ci += dc;
+    if (ci >= nc) { ci -= nc; ++ri; }
   }
   const unsigned nzb = __ballot_sync(0xffffffffu, any_nz);
   if (flags && lane == 0) flags[pr.off_tile + q] = nzb ? 1 : 0;
@@ -548,6 +575,8 @@ __global__ void __launch_bounds__(256) rb_affinity_kernel(const RbProblem* __res
                                                           unsigned* __restrict__ edge_ij, double* __restrict__ edge_v,
                                                           int* __restrict__ edge_cnt, RbDevParams P) {
   __shared__ Rec s_row[8][RB_TILE];
+  __shared__ Rec s_col[8][RB_TILE];
+  __shared__ unsigned char s_idx[8][2 * RB_TILE];
   __shared__ unsigned s_mask[256];   // live mask per block (nb <= 160)
   __shared__ unsigned char s_live[256];  // indices of live blocks, ascending
   __shared__ int s_nl;
@@ -605,7 +634,7 @@ __global__ void __launch_bounds__(256) rb_affinity_kernel(const RbProblem* __res
       for (int t = 0; t < RB_TILE_ELEMS / 2 / 32; ++t) o2[t * 32 + lane] = make_double2(0.0, 0.0);
       continue;
     }
-    affinity_tile(pr, I, J, row_live, col_live, rec, s_row[warp], Mp, flags, eo, P, lane);
+    affinity_tile(pr, I, J, row_live, col_live, rec, s_row[warp], s_col[warp], s_idx[warp], Mp, flags, eo, P, lane);
   }
 }
 
@@ -711,33 +740,30 @@ cudaError_t rb_launch_prep(const RbProblem* probs, int B, int max_mp, int max_n1
                            const RbDevParams& P, cudaStream_t st) {
   if (B == 0 || max_mp == 0) return cudaSuccess;
   if (all_to_all && max_n1 > 0 && max_n2 > 0) {
-    // thread grid TY x TX with MR x 4 outputs per thread, sized to the largest maps of the batch (blocks of at most
-    // 64 x 64 objects); MR = 4 or 5, whichever needs fewer warps
-    // blocks of at most 40 x 64 objects (larger maps take several blocks): at most 8 x 16 = 128 compute threads
-    const int e1 = max_n1 < 40 ? max_n1 : 40, e2 = max_n2 < 64 ? max_n2 : 64;
-    const int TX = (e2 + 3) / 4;
-    const int ty4 = (e1 + 3) / 4, ty5 = (e1 + 4) / 5;
-    const int w4 = (ty4 * TX + 31) / 32, w5 = (ty5 * TX + 31) / 32;
-    const int MR = (ty4 * TX > 128 || w5 < w4) ? 5 : 4;
-    const int TY = MR == 5 ? ty5 : ty4;
-    if (TY * TX <= 128) {
-      const int t1 = (max_n1 + MR * TY - 1) / (MR * TY), t2 = (max_n2 + 4 * TX - 1) / (4 * TX);
-      if ((int64_t)t1 * t2 <= 65535) {
-        dim3 grid((unsigned)(t1 * t2), B);
-        const int nth = ((TY * TX + 31) / 32) * 32 + 32;   // compute warps + the norm warp
-        const int R = MR * TY + 4 * TX;
-        const size_t smem = ((size_t)PREP_STAGES * R * PREP_LD + R + (size_t)R * PREP_HEAD) * sizeof(double);
-        static bool attr_set = false;
-        if (!attr_set) {
-          cudaError_t e = cudaFuncSetAttribute(rb_prep_table_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-          if (e == cudaSuccess) e = cudaFuncSetAttribute(rb_prep_table_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    // blocks of at most 64 x 64 objects (larger maps take several blocks): NRB compute warps (8 map-1 objects each),
+    // NCB 8-object column blocks per warp
+    const int e1 = max_n1 < 64 ? max_n1 : 64, e2 = max_n2 < 64 ? max_n2 : 64;
+    const int NRB = (e1 + 7) / 8, NCB = (e2 + 7) / 8;
+    const int t1 = (max_n1 + 8 * NRB - 1) / (8 * NRB), t2 = (max_n2 + 8 * NCB - 1) / (8 * NCB);
+    if ((int64_t)t1 * t2 <= 65535) {
+      dim3 grid((unsigned)(t1 * t2), B);
+      const int nth = 32 * NRB + 32;   // compute warps + the norm warp
+      const int R = 8 * NRB + 8 * NCB;
+      const size_t smem = ((size_t)PREP_STAGES * R * PREP_LD + R + (size_t)R * PREP_HEAD + R) * sizeof(double);
+      using kern_t = void (*)(const RbProblem*, RbAssocSoA, const double*, const double*, RbDevParams, int, int);
+      static const kern_t kerns[PREP_MAXCB] = {rb_prep_table_kernel<1>, rb_prep_table_kernel<2>, rb_prep_table_kernel<3>,
+                                               rb_prep_table_kernel<4>, rb_prep_table_kernel<5>, rb_prep_table_kernel<6>,
+                                               rb_prep_table_kernel<7>, rb_prep_table_kernel<8>};
+      static bool attr_set = false;
+      if (!attr_set) {
+        for (int i = 0; i < PREP_MAXCB; ++i) {
+          cudaError_t e = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
           if (e != cudaSuccess) return e;
-          attr_set = true;
         }
-        if (MR == 5) rb_prep_table_kernel<5><<<grid, nth, smem, st>>>(probs, rec, D1, D2, P, t2, TY, TX);
-        else rb_prep_table_kernel<4><<<grid, nth, smem, st>>>(probs, rec, D1, D2, P, t2, TY, TX);
-        return cudaGetLastError();
+        attr_set = true;
       }
+      kerns[NCB - 1]<<<grid, nth, smem, st>>>(probs, rec, D1, D2, P, t2, NRB);
+      return cudaGetLastError();
     }
   }
   dim3 grid((max_mp + 7) / 8, B);

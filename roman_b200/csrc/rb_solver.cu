@@ -428,7 +428,9 @@ __device__ __forceinline__ void csr_scan_rowptr(const Smem& S, int mp) {
   __syncthreads();
 }
 
-// Insertion sort of every CSR row by column: fixed summation order whatever order the entries arrived in.
+// Insertion sort of every CSR row by column: fixed summation order whatever order the entries arrived in.  Then the
+// list of non-empty rows (most associations carry no edge at all): the passes walk that list only.  It lives in the
+// cursor array, which the build no longer needs; its length goes to misc[13].
 __device__ __forceinline__ void csr_sort_rows(const Smem& S, int mp) {
   const int* rowptr = S.c_rowptr;
   for (int i = threadIdx.x; i < mp; i += NT) {
@@ -440,6 +442,18 @@ __device__ __forceinline__ void csr_sort_rows(const Smem& S, int mp) {
       while (q >= b && S.c_col[q] > c) { S.c_col[q + 1] = S.c_col[q]; S.c_val[q + 1] = S.c_val[q]; --q; }
       S.c_col[q + 1] = c; S.c_val[q + 1] = v;
     }
+  }
+  if (threadIdx.x == 0) S.misc[13] = 0;
+  __syncthreads();
+  int* live = S.c_rowptr + (mp + 1);   // the cursor array
+  for (int i0 = 0; i0 < mp; i0 += NT) {  // ascending row order inside a warp, warps in arrival order: any order is fine
+    const int i = i0 + (int)threadIdx.x;
+    const bool nz = (i < mp) && rowptr[i + 1] > rowptr[i];
+    const unsigned mk = __ballot_sync(0xffffffffu, nz);
+    int base = 0;
+    if ((threadIdx.x & 31) == 0 && mk) base = atomicAdd(&S.misc[13], __popc(mk));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (nz) live[base + __popc(mk & ((1u << (threadIdx.x & 31)) - 1u))] = i;
   }
   __syncthreads();
 }
@@ -674,14 +688,33 @@ __device__ __forceinline__ bool build_compact_dense(const Smem& S, const double*
   return finish_compact(S, mp);
 }
 
-// One pass out of the resident CSR: accM = M x, accC = C x (this CTA's share).
+// One pass out of the resident CSR: accM = M x, accC = C x (this CTA's share).  accM / accC were zeroed by the caller;
+// only rows that hold an entry are visited.  The four loads of an unrolled step are independent (the summation itself
+// stays sequential over the sorted columns).
 __device__ __forceinline__ void matvec_pass_compact(const Smem& S, int mp) {
-  for (int i = threadIdx.x; i < mp; i += NT) {
+  const int* __restrict__ rowptr = S.c_rowptr;
+  const int* __restrict__ live = S.c_rowptr + (mp + 1);
+  const uint16_t* __restrict__ col = S.c_col;
+  const double* __restrict__ val = S.c_val;
+  const double* __restrict__ x = S.x;
+  const int n_live = S.misc[13];
+  for (int t = threadIdx.x; t < n_live; t += NT) {
+    const int i = live[t];
     double sM = 0.0, sC = 0.0;
-    const int b = S.c_rowptr[i], e = S.c_rowptr[i + 1];
-    for (int q = b; q < e; ++q) {
-      const double xj = S.x[S.c_col[q]];
-      sM = fma(S.c_val[q], xj, sM);
+    int q = rowptr[i];
+    const int e = rowptr[i + 1];
+    for (; q + 4 <= e; q += 4) {
+      const int c0 = col[q], c1 = col[q + 1], c2 = col[q + 2], c3 = col[q + 3];
+      const double v0 = val[q], v1 = val[q + 1], v2 = val[q + 2], v3 = val[q + 3];
+      const double x0 = x[c0], x1 = x[c1], x2 = x[c2], x3 = x[c3];
+      sM = fma(v0, x0, sM); sC += x0;
+      sM = fma(v1, x1, sM); sC += x1;
+      sM = fma(v2, x2, sM); sC += x2;
+      sM = fma(v3, x3, sM); sC += x3;
+    }
+    for (; q < e; ++q) {
+      const double xj = x[col[q]];
+      sM = fma(val[q], xj, sM);
       sC += xj;
     }
     S.accM[i] = sM;
