@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libroman_b200.so")
+LIB_PATH = os.environ.get("RB_LIB_PATH") or os.path.join(_HERE, "csrc", "libroman_b200.so")   # RB_LIB_PATH: dev builds of the same library
 RB_MAX_RATIO_FEATURES = 8
 
 RB_INVARIANT_ROMAN = 0

@@ -229,11 +229,10 @@ __global__ void __launch_bounds__(256) rb_prep_kernel(const RbProblem* __restric
 // (measured: a 5 x 4 tile stalls at 54 % of the fp64 peak, tools/micro/fp64_rate.cu); the MMA fragments of a warp
 // hold 32 operands for 256 multiply-adds — a third of the wavefronts.
 //
-// Staging: descriptor columns [k0, k0 + 16) of all rows of the block form one stage ([row][k], pitch 20 doubles: a
-// fragment load touches rows g = 0..7 x columns t = 0..3, and 20 = 4 mod 16 puts the 16 words of a half-warp into 16
-// different bank pairs); a ring of 4 stages is filled with asynchronous global->shared copies (cp.async, 8 bytes each
-// — SASS LDGSTS) issued three stages ahead (the loop is latency-bound on HBM otherwise: 12 KB per stage and CTA); ONE
-// block barrier per 16 columns.  Why not the bulk / TMA form the solver
+// Staging: descriptor columns [k0, k0 + 32) of all rows of the block form one stage ([row][k], pitch 36 doubles: a
+// fragment load touches rows g = 0..7 x columns t = 0..3, and 36 = 4 mod 16 puts the 16 words of a half-warp into 16
+// different bank pairs); a ring of 3 stages is filled with asynchronous global->shared copies (cp.async, 8 bytes each
+// — SASS LDGSTS) issued two stages ahead; ONE block barrier per 32 columns.  Why not the bulk / TMA form the solver
 // uses for its 8 KB tiles: object rows are d = 3 + r + D doubles long (775 for the `roman` method, odd), so every
 // other row starts 8 bytes off a 16-byte boundary; cp.async.bulk and tensor maps need 16-byte aligned sources.
 //
@@ -241,9 +240,18 @@ __global__ void __launch_bounds__(256) rb_prep_kernel(const RbProblem* __restric
 // (the m8n8k4 DMMA accumulates its four products in k order, each with a single rounding), the squared norms likewise
 // in the norm warp: the same values as a scalar loop with fma(), so the cosine gate `<= cosine_min` sees what it saw
 // in round 1.  Nothing is split across threads or tree-reduced; results do not depend on the launch shape.
-constexpr int PREP_KC = 16;           // descriptor columns per stage
-constexpr int PREP_LD = 20;           // shared-memory row pitch (doubles): 4 mod 16, see above
-constexpr int PREP_STAGES = 4;         // copies run three stages (48 columns) ahead of the arithmetic
+// measured on B200 (592 problems of 40 x 50 objects, D = 768; tools/micro/variants): columns per stage / stages / CTAs
+// per SM -> 16/3/4: 0.182 ms, 32/2/3: 0.188, 32/3/2: 0.175, 64/2/2: 0.186, 16/4/3: 0.233 (1.33 waves), 128/2/1: 0.240
+#ifndef RB_PREP_KC
+#define RB_PREP_KC 32
+#define RB_PREP_STAGES 3
+#endif
+#ifndef RB_PREP_MINB
+#define RB_PREP_MINB 2
+#endif
+constexpr int PREP_KC = RB_PREP_KC;   // descriptor columns per stage: 512 contiguous bytes per row and request (HBM pages are 1 KB)
+constexpr int PREP_LD = PREP_KC + 4;  // shared-memory row pitch (doubles): 4 mod 16, see above
+constexpr int PREP_STAGES = RB_PREP_STAGES;  // copies run one stage ahead of the arithmetic
 constexpr int PREP_HEAD = 8;          // leading (non-descriptor) columns of a row kept for the epilogue: centre + ratio features
 constexpr int PREP_MAXCB = 8;         // column blocks per warp (n2 <= 64 per block of the grid)
 
@@ -257,8 +265,8 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-template <int NCB>
-__global__ void __launch_bounds__(288, 2) rb_prep_table_kernel(const RbProblem* __restrict__ probs, RbAssocSoA rec,
+template <int NCB, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) rb_prep_table_kernel(const RbProblem* __restrict__ probs, RbAssocSoA rec,
                                                                const double* __restrict__ D1,
                                                                const double* __restrict__ D2, RbDevParams P,
                                                                int tiles2_max, int NRB) {
@@ -311,15 +319,14 @@ __global__ void __launch_bounds__(288, 2) rb_prep_table_kernel(const RbProblem* 
     s_head[e] = (src != nullptr && k < nhead) ? src[k] : 0.0;
   }
   __syncthreads();
-  const int kk = tid % PREP_KC, q0 = tid / PREP_KC, qstep = NTH / PREP_KC;   // NTH is a multiple of 32, PREP_KC = 16
   auto issue = [&](int c) {  // asynchronous copies of chunk c into stage c % PREP_STAGES
-    double* st = stage0 + (size_t)(c % PREP_STAGES) * R * PREP_LD + kk;
-    const int kcol = c * PREP_KC + kk;
-    const bool kin = kcol < Dc;
-    for (int q = q0; q < R; q += qstep) {  // 16 consecutive threads -> 16 consecutive columns of one row (128 B)
+    double* st = stage0 + (size_t)(c % PREP_STAGES) * R * PREP_LD;
+    const int k0 = c * PREP_KC;
+    for (int e = tid; e < R * PREP_KC; e += NTH) {  // consecutive threads -> consecutive columns of one row: coalesced
+      const int q = e / PREP_KC, k = e % PREP_KC;   // PREP_KC is a power of two
       const double* src = s_rowp[q];
-      double* dst = st + q * PREP_LD;
-      if (src != nullptr && kin) cp_async_8(dst, src + kcol);
+      double* dst = st + q * PREP_LD + k;
+      if (src != nullptr && (k0 + k) < Dc) cp_async_8(dst, src + k0 + k);
       else *dst = 0.0;
     }
   };
@@ -751,18 +758,21 @@ cudaError_t rb_launch_prep(const RbProblem* probs, int B, int max_mp, int max_n1
       const int R = 8 * NRB + 8 * NCB;
       const size_t smem = ((size_t)PREP_STAGES * R * PREP_LD + R + (size_t)R * PREP_HEAD + R) * sizeof(double);
       using kern_t = void (*)(const RbProblem*, RbAssocSoA, const double*, const double*, RbDevParams, int, int);
-      static const kern_t kerns[PREP_MAXCB] = {rb_prep_table_kernel<1>, rb_prep_table_kernel<2>, rb_prep_table_kernel<3>,
-                                               rb_prep_table_kernel<4>, rb_prep_table_kernel<5>, rb_prep_table_kernel<6>,
-                                               rb_prep_table_kernel<7>, rb_prep_table_kernel<8>};
+      // up to 5 compute warps (maps of <= 40 objects, the reference's submap_max_size): 192 threads, four CTAs per SM
+#define RB_PREP_K(n) rb_prep_table_kernel<n, 192, RB_PREP_MINB>, rb_prep_table_kernel<n, 288, 2>
+      static const kern_t kerns[PREP_MAXCB][2] = {{RB_PREP_K(1)}, {RB_PREP_K(2)}, {RB_PREP_K(3)}, {RB_PREP_K(4)},
+                                                  {RB_PREP_K(5)}, {RB_PREP_K(6)}, {RB_PREP_K(7)}, {RB_PREP_K(8)}};
+#undef RB_PREP_K
       static bool attr_set = false;
       if (!attr_set) {
-        for (int i = 0; i < PREP_MAXCB; ++i) {
-          cudaError_t e = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-          if (e != cudaSuccess) return e;
-        }
+        for (int i = 0; i < PREP_MAXCB; ++i)
+          for (int j = 0; j < 2; ++j) {
+            cudaError_t e = cudaFuncSetAttribute(kerns[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+            if (e != cudaSuccess) return e;
+          }
         attr_set = true;
       }
-      kerns[NCB - 1]<<<grid, nth, smem, st>>>(probs, rec, D1, D2, P, t2, NRB);
+      kerns[NCB - 1][nth <= 192 ? 0 : 1]<<<grid, nth, smem, st>>>(probs, rec, D1, D2, P, t2, NRB);
       return cudaGetLastError();
     }
   }
