@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(256) rb_prep_kernel(const RbProblem* __restric
 // 8w .. 8w+7 and all NCB 8-object column blocks of map 2: per 4 descriptor columns it loads one A fragment and NCB B
 // fragments (one double per lane each) and issues NCB DMMAs, accumulating two doubles per lane per column block.  One
 // more warp accumulates the squared norms of all rows of the block.  40 x 50 objects: 5 compute warps x 7 column
-// blocks; four such CTAs share an SM.
+// blocks; two such CTAs share an SM.
 //
 // Why the tensor pipe although its fp64 rate equals the FMA pipe's: shared-memory bandwidth.  An FMA register tile
 // needs (MR + NR) operand words per MR * NR multiply-adds per lane and every 8-byte shared load costs two wavefronts
