@@ -372,3 +372,24 @@ def test_example_script_dry_run():
                        capture_output=True, text=True, timeout=300, cwd=root)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "submap pairs" in r.stdout and "dry run" in r.stdout
+
+
+def test_bench_workloads_are_consistent():
+    """bench.py's three configurations (BASELINE.json configs[1..4] stand-ins): shapes, shared tables, longest-first
+    order of the all-pairs search, per-rank worlds, and the per-problem views the CPU arm and the parity check use."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    wl = bench.build_workload("metric", 0, 1, batch=6)
+    assert wl.B == 6 and not wl.indexed and (wl.m == 2000).all() and wl.D1.shape == (6 * 40, bench.D_ROW)
+    D1, D2, u0 = wl.pair(3)
+    assert D1.shape == (40, bench.D_ROW) and D2.shape == (50, bench.D_ROW) and u0.shape == (2000,)
+    w5 = bench.build_workload("cfg5", 0, 4)
+    assert w5.B == 400 and w5.indexed and w5.m.max() <= 1600 and (np.diff(w5.m) <= 0).all()      # longest problem first
+    assert (w5.obj1 + w5.n1 <= len(w5.D1)).all() and (w5.obj2 + w5.n2 <= len(w5.D2)).all()
+    D1, D2, u0 = w5.pair(17)
+    assert len(u0) == len(D1) * len(D2) == w5.m[17]
+    other = bench.build_workload("cfg5", 1, 4)                 # another rank searches another robot pair
+    assert other.B == 400 and not np.array_equal(other.m, w5.m)
+    t, why = bench.traffic_for("no-such-key")
+    assert t is None and "no committed ncu capture" in why
