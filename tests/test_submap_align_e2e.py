@@ -123,3 +123,23 @@ def test_submap_align_equals_the_reference_end_to_end(engine, case, tmp_path):
                 assert np.isnan(res.T_ij_hat_mat[i, j]).all(), (i, j)
             else:
                 assert np.linalg.norm(res.T_ij_hat_mat[i, j] - np.asarray(Tw)) / np.linalg.norm(Tw) < 1e-9, (i, j)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/demo/loop_closures.py"), reason="reference tree not present (GPU box)")
+def test_reference_demo_script_runs_unchanged_on_the_mirrors(monkeypatch, tmp_path):
+    """The reference's demo/loop_closures.py, executed unmodified after install_as_roman(): its imports resolve, it
+    builds SubmapAlignParams / SubmapAlignInputOutput and calls submap_align(sm_params=..., sm_io=...) — recorded here
+    (the registration itself needs the GPU; test_submap_align_equals_the_reference_end_to_end covers it)."""
+    import runpy
+    import sys
+    import roman_b200
+    roman_b200.install_as_roman()
+    import roman.align.submap_align as mirror
+    calls = []
+    monkeypatch.setattr(mirror, "submap_align", lambda sm_params, sm_io: calls.append((sm_params, sm_io)))
+    monkeypatch.setattr(sys, "argv", ["loop_closures.py", "-i", MAPS[0], MAPS[1], "-o", str(tmp_path), "-n", "lc", "-s"])
+    runpy.run_path("/root/reference/demo/loop_closures.py", run_name="__main__")
+    (sp, io), = calls
+    assert sp.single_robot_lc is True and sp.method == "roman" and sp.submap_max_size == 40
+    assert io.inputs == MAPS and io.output_dir == str(tmp_path) and io.run_name == "lc"
+    assert io.output_g2o == os.path.join(str(tmp_path), "lc.g2o") and io.input_gt_pose_yaml == [None, None]
