@@ -123,6 +123,37 @@ __device__ __forceinline__ double pair_score(const RbDevParams& P, const Rec& i,
 }
 
 // ---------------------------------------------------------------------------------------------
+// The z gate ahead of everything else.  K1 screens all (live row, live column) pairs of a tile with the two tests of
+// pair_score() that need no square root — distinctness, and (gravity-guided, not drift-aware ROMAN) the reference's own
+// z test on the same fp64 expressions (roman.cpp:54-77: c_z > sqrt(1/3) * eps_z returns 0) — and evaluates pair_score(),
+// the reference's expressions untouched, on the survivors only, compacted onto full warps.  At realistic densities nine
+// pairs in ten fail the z test, and with the gates inside the scoring code nearly every 32-pair sweep still walked the
+// whole square-root / exp / pow path for its one or two survivors.  `false` <=> pair_score() returns exactly 0.0 through
+// one of these two exits (no other effect); the operands' order does not matter (differences are negated exactly).
+// (fp32 screens of the length / xy gates were tried as well: conversions and square roots on every z survivor cost more
+// than the few extra pairs they drop.)
+struct ZGate {
+  bool on;
+  double eps, sin_unc;
+  bool unc;
+};
+__device__ __forceinline__ ZGate make_zgate(const RbDevParams& P) {
+  ZGate g;
+  const rb_invariant_params& p = P.inv;
+  g.on = (p.kind == RB_INVARIANT_ROMAN || p.kind == RB_INVARIANT_ROMAN_PAIRWISE) && p.gravity_guided && !p.drift_aware;
+  g.eps = p.epsilon;
+  g.sin_unc = P.sin_unc;
+  g.unc = p.gravity_unc_ang_rad > 0.0;
+  return g;
+}
+__device__ __forceinline__ bool zgate_pass(const ZGate& g, double az_i, double bz_i, double az_j, double bz_j) {
+  const double daz = az_i - az_j, dbz = bz_i - bz_j;
+  double eps_z = g.eps;
+  if (g.unc) eps_z += fabs(0.5 * (fabs(daz) + fabs(dbz)) * g.sin_unc);
+  return !(fabs(daz - dbz) > kSqrtOneThird * eps_z);
+}
+
+// ---------------------------------------------------------------------------------------------
 // K1a: one warp per association — gathers the two object centres and evaluates
 // ROMAN::single_similarity (roman.cpp:116-164); descriptor dot products are warp-strided
 // fp64 sums reduced with a fixed xor tree.
@@ -496,16 +527,37 @@ struct RbEdgeOut {
   int cap;
 };
 
+// The live associations of a tile's row block (or column block), compacted: slot k = the k-th live association.  One
+// array per field, so that lanes holding consecutive slots read consecutive words (no bank conflicts) and lanes holding
+// the same slot share one word (broadcast) — the array-of-records layout this replaces cost up to eight shared-memory
+// wavefronts per load and made the kernel LSU-bound at realistic densities (ncu: 76 % of the LSU peak, fp64 pipe 33 %).
+struct TileSide {
+  double ax[RB_TILE], ay[RB_TILE], az[RB_TILE], bx[RB_TILE], by[RB_TILE], bz[RB_TILE], s[RB_TILE];
+  int32_t i1[RB_TILE], i2[RB_TILE];
+  unsigned char idx[RB_TILE];  // slot -> position in the block
+};
+
+__device__ __forceinline__ void fill_side(TileSide& S, const RbAssocSoA& rec, int64_t o, unsigned live, int lane) {
+  const Rec r = load_rec(rec, o + lane);  // coalesced
+  if ((live >> lane) & 1u) {
+    const int k = __popc(live & ((1u << lane) - 1u));
+    S.ax[k] = r.ax; S.ay[k] = r.ay; S.az[k] = r.az;
+    S.bx[k] = r.bx; S.by[k] = r.by; S.bz[k] = r.bz;
+    S.s[k] = r.s; S.i1[k] = r.i1; S.i2[k] = r.i2;
+    S.idx[k] = (unsigned char)lane;
+  }
+}
+
 __device__ __forceinline__ void affinity_tile(const RbProblem& pr, int I, int J, unsigned row_live, unsigned col_live,
-                                              const RbAssocSoA& rec, Rec* s_row, Rec* s_col, unsigned char* s_idx,
+                                              const RbAssocSoA& rec, TileSide& R, TileSide& C, unsigned short* surv,
                                               double* __restrict__ Mp,
                                               uint8_t* __restrict__ flags, const RbEdgeOut& eo, const RbDevParams& P,
                                               int lane) {
   const int64_t q = rb_tile_index(I, J, pr.nb);
   double* out = Mp + (pr.off_tile + q) * RB_TILE_ELEMS;
   __syncwarp();
-  s_col[lane] = load_rec(rec, pr.off_pad + (int64_t)J * RB_TILE + lane);
-  s_row[lane] = load_rec(rec, pr.off_pad + (int64_t)I * RB_TILE + lane);
+  fill_side(C, rec, pr.off_pad + (int64_t)J * RB_TILE, col_live, lane);
+  fill_side(R, rec, pr.off_pad + (int64_t)I * RB_TILE, row_live, lane);
   // the whole tile as zeros first (coalesced 16-byte stores); the few non-zero words overwrite them below
   {
     double2* o2 = reinterpret_cast<double2*>(out);
@@ -514,42 +566,33 @@ __device__ __forceinline__ void affinity_tile(const RbProblem& pr, int I, int J,
   }
   __syncwarp();  // orders the zero stores before the value stores of other lanes to the same words
   const bool diag = (I == J);
-  // Only (live row, live column) pairs are evaluated, and they are PACKED onto the lanes: pair p = (rows[p / nc],
-  // cols[p % nc]) over the nr live rows and nc live columns of the tile, 32 pairs per sweep.  With half of the
+  // Only (live row, live column) pairs are evaluated, and they are PACKED onto the lanes: pair p = (row slot p / nc,
+  // column slot p % nc) over the nr live rows and nc live columns of the tile, 32 pairs per sweep.  With half of the
   // associations live a lane-per-column sweep leaves half of every warp idle (measured: 17 of 32 threads active).
   const int nr = __popc(row_live), nc = __popc(col_live);
   const int npairs = nr * nc;
-  // tables: k-th live row / column of the tile
-  if ((row_live >> lane) & 1u) s_idx[__popc(row_live & ((1u << lane) - 1u))] = (unsigned char)lane;
-  if ((col_live >> lane) & 1u) s_idx[32 + __popc(col_live & ((1u << lane) - 1u))] = (unsigned char)lane;
-  __syncwarp();
   bool any_nz = false;
-  int ri = lane / nc, ci = lane % nc;            // pair index p = lane + 32 * sweep  ->  (ri, ci)
-  const int dr = 32 / nc, dc = 32 % nc;
-  // One instance of the scoring code, no unrolling: the transcendental paths (exp, pow) are long, and several copies
-  // of them made the kernel's instruction footprint (~250 KB of SASS in round 1) thrash the instruction cache.
-#pragma unroll 1
-  for (int p0 = 0; p0 < npairs; p0 += 32) {
-    const bool in_range = ri < nr;
+  // Survivors of the screens, (row slot << 5 | column slot), scored 32 at a time on full warps.
+  auto score_batch = [&](int first, int count) {
     double v = 0.0;
     int r = 0, c = 0;
-    if (in_range) {
-      r = s_idx[ri];
-      c = s_idx[32 + ci];
-      if (!(diag && r == c)) {  // r == c on the diagonal: implicit identity (clipper.cpp:129-130)
-        const Rec row = s_row[r];
-        const Rec col = s_col[c];
-        // i = the association with the smaller index: the row, except for the mirrored half of a diagonal tile
-        const bool mirrored = diag && r > c;
-        Rec a, b;
-        a.ax = mirrored ? col.ax : row.ax; a.ay = mirrored ? col.ay : row.ay; a.az = mirrored ? col.az : row.az;
-        a.bx = mirrored ? col.bx : row.bx; a.by = mirrored ? col.by : row.by; a.bz = mirrored ? col.bz : row.bz;
-        a.s = mirrored ? col.s : row.s; a.i1 = mirrored ? col.i1 : row.i1; a.i2 = mirrored ? col.i2 : row.i2;
-        b.ax = mirrored ? row.ax : col.ax; b.ay = mirrored ? row.ay : col.ay; b.az = mirrored ? row.az : col.az;
-        b.bx = mirrored ? row.bx : col.bx; b.by = mirrored ? row.by : col.by; b.bz = mirrored ? row.bz : col.bz;
-        b.s = mirrored ? row.s : col.s; b.i1 = mirrored ? row.i1 : col.i1; b.i2 = mirrored ? row.i2 : col.i2;
-        v = pair_score(P, a, b);
-      }
+    if (lane < count) {
+      const int e = surv[first + lane];
+      const int ri = e >> 5, ci = e & 31;
+      r = R.idx[ri];
+      c = C.idx[ci];
+      // i = the association with the smaller index: the row, except for the mirrored half of a diagonal tile.  The
+      // pairwise score is bitwise symmetric in (i, j) (differences are negated exactly, then squared or fabs'ed); the
+      // fusion is not ((d * si) * sj), so the single scores are the one thing that has to swap.
+      const bool mirrored = diag && r > c;
+      Rec a, b;
+      a.ax = R.ax[ri]; a.ay = R.ay[ri]; a.az = R.az[ri]; a.bx = R.bx[ri]; a.by = R.by[ri]; a.bz = R.bz[ri];
+      b.ax = C.ax[ci]; b.ay = C.ay[ci]; b.az = C.az[ci]; b.bx = C.bx[ci]; b.by = C.by[ci]; b.bz = C.bz[ci];
+      a.i1 = R.i1[ri]; a.i2 = R.i2[ri]; b.i1 = C.i1[ci]; b.i2 = C.i2[ci];
+      const double sr = R.s[ri], sc = C.s[ci];
+      a.s = mirrored ? sc : sr;
+      b.s = mirrored ? sr : sc;
+      v = pair_score(P, a, b);
     }
     const bool nz = (__double_as_longlong(v) != 0ll);
     any_nz |= nz;
@@ -568,9 +611,39 @@ __device__ __forceinline__ void affinity_tile(const RbProblem& pr, int I, int J,
         }
       }
     }
-    ri += dr;
-    ci += dc;
-    if (ci >= nc) { ci -= nc; ++ri; }
+  };
+  const ZGate zg = make_zgate(P);
+  int ns = 0;                                    // survivors waiting in surv[0 .. ns)
+  int ri = lane / nc, ci = lane % nc;            // pair index p = lane + 32 * sweep  ->  (ri, ci)
+  const int dr = 32 / nc, dc = 32 % nc;
+  // one call site for the scoring code (its exp / pow paths are long: a second inlined copy costs instruction cache)
+#pragma unroll 1
+  for (int p0 = 0;; p0 += 32) {
+    const bool done = p0 >= npairs;
+    if (!done) {
+      bool keep = false;
+      if (ri < nr) {
+        const int r = R.idx[ri], c = C.idx[ci];
+        if (!(diag && r == c)) {  // r == c on the diagonal: implicit identity (clipper.cpp:129-130)
+          keep = R.i1[ri] != C.i1[ci] && R.i2[ri] != C.i2[ci];   // distinctness (padding is never live)
+          if (keep && zg.on) keep = zgate_pass(zg, R.az[ri], R.bz[ri], C.az[ci], C.bz[ci]);
+        }
+      }
+      const unsigned km = __ballot_sync(0xffffffffu, keep);
+      if (keep) surv[ns + __popc(km & ((1u << lane) - 1u))] = (unsigned short)((ri << 5) | ci);
+      ns += __popc(km);
+      ri += dr;
+      ci += dc;
+      if (ci >= nc) { ci -= nc; ++ri; }
+    }
+    if (ns >= 32 || (done && ns > 0)) {
+      __syncwarp();
+      const int cnt = ns < 32 ? ns : 32;
+      ns -= cnt;
+      score_batch(ns, cnt);  // the newest entries: nothing has to move
+      __syncwarp();
+    }
+    if (done) break;
   }
   const unsigned nzb = __ballot_sync(0xffffffffu, any_nz);
   if (flags && lane == 0) flags[pr.off_tile + q] = nzb ? 1 : 0;
@@ -581,9 +654,8 @@ __global__ void __launch_bounds__(256) rb_affinity_kernel(const RbProblem* __res
                                                           double* __restrict__ Mp, uint8_t* __restrict__ flags,
                                                           unsigned* __restrict__ edge_ij, double* __restrict__ edge_v,
                                                           int* __restrict__ edge_cnt, RbDevParams P) {
-  __shared__ Rec s_row[8][RB_TILE];
-  __shared__ Rec s_col[8][RB_TILE];
-  __shared__ unsigned char s_idx[8][2 * RB_TILE];
+  __shared__ TileSide s_row[8], s_col[8];
+  __shared__ unsigned short s_surv[8][64];
   __shared__ unsigned s_mask[256];   // live mask per block (nb <= 160)
   __shared__ unsigned char s_live[256];  // indices of live blocks, ascending
   __shared__ int s_nl;
@@ -641,7 +713,7 @@ __global__ void __launch_bounds__(256) rb_affinity_kernel(const RbProblem* __res
       for (int t = 0; t < RB_TILE_ELEMS / 2 / 32; ++t) o2[t * 32 + lane] = make_double2(0.0, 0.0);
       continue;
     }
-    affinity_tile(pr, I, J, row_live, col_live, rec, s_row[warp], s_col[warp], s_idx[warp], Mp, flags, eo, P, lane);
+    affinity_tile(pr, I, J, row_live, col_live, rec, s_row[warp], s_col[warp], s_surv[warp], Mp, flags, eo, P, lane);
   }
 }
 
