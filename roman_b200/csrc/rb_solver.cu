@@ -162,6 +162,23 @@ __device__ __forceinline__ void elems4(int n, F&& f, G&& g) {
 }
 struct V2 { double a, b; };
 
+// The same over an index list (the ACTIVE associations of a resident problem, see build_active); act == nullptr: all of
+// 0 .. n-1 as above.
+template <typename V, typename F, typename G>
+__device__ __forceinline__ void elems_act(const uint16_t* __restrict__ act, int n, F&& f, G&& g) {
+  if (act == nullptr) {
+    elems4<V>(n, f, g);
+    return;
+  }
+  int k = threadIdx.x;
+  for (; k + 3 * NT < n; k += 4 * NT) {
+    const int i0 = act[k], i1 = act[k + NT], i2 = act[k + 2 * NT], i3 = act[k + 3 * NT];
+    const V a = f(i0), b = f(i1), c = f(i2), d = f(i3);
+    g(a); g(b); g(c); g(d);
+  }
+  for (; k < n; k += NT) g(f((int)act[k]));
+}
+
 // One fused pass: accM += M x, accC += C x over the packed upper triangle of one problem.
 // Preconditions: x complete, accM/accC zeroed, all threads past a __syncthreads.
 //
@@ -445,8 +462,8 @@ __device__ __forceinline__ void csr_scan_rowptr(const Smem& S, int mp) {
 }
 
 // Insertion sort of every CSR row by column: fixed summation order whatever order the entries arrived in.  Then the
-// list of non-empty rows (most associations carry no edge at all): the passes walk that list only.  It lives in the
-// cursor array, which the build no longer needs; its length goes to misc[13].
+// list of non-empty rows (most associations carry no edge at all): the passes walk that list only.  It lives (16-bit
+// entries) in the first half of the cursor array, which the build no longer needs; its length goes to misc[13].
 __device__ __forceinline__ void csr_sort_rows(const Smem& S, int mp) {
   const int* rowptr = S.c_rowptr;
   for (int i = threadIdx.x; i < mp; i += NT) {
@@ -464,7 +481,8 @@ __device__ __forceinline__ void csr_sort_rows(const Smem& S, int mp) {
   // one row length of each other (row lengths run from 1 to ~50; a plain row -> thread map had the slowest thread set
   // the pace of every pass).  The order inside a length class is arbitrary: which thread sums a row does not change
   // the sum.
-  int* live = S.c_rowptr + (mp + 1);   // the cursor array
+  uint16_t* live = reinterpret_cast<uint16_t*>(S.c_rowptr + (mp + 1));   // first half of the cursor array (the second
+                                                                            // half takes the active list, see build_active)
   int* hist = reinterpret_cast<int*>(S.red);   // 64 counters + 64 cursors; no reduction is in flight here
   for (int t = threadIdx.x; t < 128; t += NT) hist[t] = 0;
   __syncthreads();
@@ -481,7 +499,7 @@ __device__ __forceinline__ void csr_sort_rows(const Smem& S, int mp) {
   __syncthreads();
   for (int i = threadIdx.x; i < mp; i += NT) {
     const int len = rowptr[i + 1] - rowptr[i];
-    if (len > 0) live[atomicAdd(&hist[64 + (len < 63 ? len : 63)], 1)] = i;
+    if (len > 0) live[atomicAdd(&hist[64 + (len < 63 ? len : 63)], 1)] = (uint16_t)i;
   }
   __syncthreads();
 }
@@ -716,21 +734,60 @@ __device__ __forceinline__ bool build_compact_dense(const Smem& S, const double*
   return finish_compact(S, mp);
 }
 
+// ACTIVE associations of a resident problem: those that carry an edge or whose u is not (yet) exactly zero, in index
+// order, as 16-bit indices in the second half of the cursor array; returns their number.  An association without any
+// edge has (M u)_i = (C u)_i = 0, so its gradient is (1 + d) u_i - d sum(u): once u_i has been clipped to zero it stays
+// zero for good (max(0 + alpha * (-d sum u), 0) = 0 for d, sum u >= 0) and adds exactly 0 to every sum of the algorithm
+// (u.g, ||unew||^2, sum unew, ||unew - u||^2, the d update's index set needs u_i > eps).  The all-pairs search is full of
+// them — half of the candidate associations of two non-matching submaps fail the single-score gate — and the vector
+// phases between two passes, not the passes, are what a resident problem spends its time in.  Whole matrix in this CTA
+// only (C == 1 or solo).  Uses S.wcnt (idle while resident) as scratch; two barriers.
+__device__ __forceinline__ int build_active(const Smem& S, int m, int mp) {
+  const int* __restrict__ rowptr = S.c_rowptr;
+  uint16_t* act = reinterpret_cast<uint16_t*>(S.c_rowptr + (mp + 1)) + mp;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int seg = ((m + NW * 32 - 1) / (NW * 32)) * 32;  // indices per warp
+  const int lo = w * seg, hi = (lo + seg < m) ? lo + seg : m;
+  int c = 0;
+  for (int i0 = lo; i0 < hi; i0 += 32) {
+    const int i = i0 + lane;
+    const bool keep = i < hi && (rowptr[i + 1] > rowptr[i] || S.x[i] != 0.0);
+    c += __popc(__ballot_sync(0xffffffffu, keep));
+  }
+  if (lane == 0) S.wcnt[w] = c;
+  __syncthreads();
+  int off = 0, tot = 0;
+#pragma unroll
+  for (int v = 0; v < NW; ++v) {
+    const int cv = S.wcnt[v];
+    off += (v < w) ? cv : 0;
+    tot += cv;
+  }
+  for (int i0 = lo; i0 < hi; i0 += 32) {
+    const int i = i0 + lane;
+    const bool keep = i < hi && (rowptr[i + 1] > rowptr[i] || S.x[i] != 0.0);
+    const unsigned mk = __ballot_sync(0xffffffffu, keep);
+    if (keep) act[off + __popc(mk & ((1u << lane) - 1u))] = (uint16_t)i;
+    off += __popc(mk);
+  }
+  __syncthreads();
+  return tot;
+}
+
 // One pass out of the resident CSR: accM = M x, accC = C x (this CTA's share).  accM / accC were zeroed by the caller;
 // only rows that hold an entry are visited.  The four loads of an unrolled step are independent (the summation itself
-// stays sequential over the sorted columns).
+// stays sequential over the sorted columns).  (Summing the long rows with eight lanes each and a shuffle tree was tried:
+// 1.95 -> 2.67 us per pass on the all-pairs workload; the rows are not long enough to pay for the tree.)
 __device__ __forceinline__ void matvec_pass_compact(const Smem& S, int mp) {
   const int* __restrict__ rowptr = S.c_rowptr;
-  const int* __restrict__ live = S.c_rowptr + (mp + 1);
+  const uint16_t* __restrict__ live = reinterpret_cast<const uint16_t*>(S.c_rowptr + (mp + 1));
   const uint16_t* __restrict__ col = S.c_col;
   const double* __restrict__ val = S.c_val;
   const double* __restrict__ x = S.x;
   const int n_live = S.misc[13];
-  for (int t = threadIdx.x; t < n_live; t += NT) {
-    const int i = live[t];
-    double sM = 0.0, sC = 0.0;
-    int q = rowptr[i];
-    const int e = rowptr[i + 1];
+  // one row: sequential sum over its sorted columns, four independent loads per step
+  // (two rows of a thread at a time, interleaved, was tried: no gain — the pace is set by the thread with most entries)
+  auto row_tail = [&](int q, int e, double& sM, double& sC) {
     for (; q + 4 <= e; q += 4) {
       const int c0 = col[q], c1 = col[q + 1], c2 = col[q + 2], c3 = col[q + 3];
       const double v0 = val[q], v1 = val[q + 1], v2 = val[q + 2], v3 = val[q + 3];
@@ -745,8 +802,20 @@ __device__ __forceinline__ void matvec_pass_compact(const Smem& S, int mp) {
       sM = fma(val[q], xj, sM);
       sC += xj;
     }
-    S.accM[i] = sM;
-    S.accC[i] = sC;
+  };
+  // The list is sorted longest first and dealt to the threads in rounds of NT rows, alternately forwards and backwards
+  // (thread 0 gets the longest row of round 0 and the shortest of round 1): with a plain round-robin the first threads
+  // got the longest row of EVERY round and set the pace of the pass.
+  int r = 0;
+  for (int base = 0; base < n_live; base += NT, ++r) {
+    const int t = base + ((r & 1) ? (NT - 1 - (int)threadIdx.x) : (int)threadIdx.x);
+    if (t < n_live) {
+      const int i = live[t];
+      double sM = 0.0, sC = 0.0;
+      row_tail(rowptr[i], rowptr[i + 1], sM, sC);
+      S.accM[i] = sM;
+      S.accC[i] = sC;
+    }
   }
 }
 
@@ -1023,12 +1092,21 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
     // (the __restrict__ views below live only inside one vector phase, between two barriers: the passes in between
     // write the same arrays through S)
 #define RB_VIEWS double* __restrict__ const xs = S.x; double* __restrict__ const aM = S.accM; double* __restrict__ const aC = S.accC; (void)xs; (void)aM; (void)aC
+    const uint16_t* act = nullptr;  // resident problems: the active associations (build_active), else all of 0 .. m-1
+    int n_el = m;
     for (i_ol = 0; i_ol < sp.maxoliters; ++i_ol) {
+      // (re)built once per outer iteration.  The conditions of build_active's argument: d >= 0 (it only grows from here),
+      // sum(u) >= 0 (true for every later iterate: they are clipped at zero), eps >= 0 (so that u_i = 0 is never in the
+      // d update's index set); a NaN fails the tests and keeps the full range.
+      if (compact && (C == 1 || solo) && sp.eps >= 0.0 && d >= 0.0 && sum_u >= 0.0) {
+        n_el = build_active(S, m, mp);
+        act = reinterpret_cast<const uint16_t*>(S.c_rowptr + (mp + 1)) + mp;
+      }
       {  // gradF and F at (u, d) from the kept M u, C u  (clipper.cpp:290-291)
         double f = 0.0;
         RB_VIEWS;
         double* __restrict__ const gp = g;
-        elems4<V2>(m, [&](int i) {
+        elems_act<V2>(act, n_el, [&](int i) {
           const double ui = xs[i];
           const double gi = (((1.0 + d) * ui - d * sum_u) + aM[i]) + aC[i] * d;
           gp[i] = gi;
@@ -1036,17 +1114,25 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
         }, [&](const V2& v) { f += v.a; });
         F = R.sum1(f);
       }
+      // (the accept step of an inner iteration that goes on already takes the next iteration's first trial step — same
+      // thread, same elements, alpha = 1 — and hands over its partial sums)
+      bool have_trial = false;
+      double z_next = 0.0, sraw_next = 0.0;
       for (int j_il = 0; j_il < sp.maxiniters; ++j_il) {
         double alpha = 1.0, Fnew = 0.0, deltaF = 0.0, du2 = 0.0, sum_un = 0.0;
         for (int k_ls = 0; k_ls < sp.maxlsiters; ++k_ls) {
           // unew = normalize(max(u + alpha*gradF, 0))   (clipper.cpp:306-308)
           // (sum of the normalised vector = sum of the raw one / norm: one reduction for both)
           double z = 0.0, sraw = 0.0;
-          {
+          if (have_trial) {
+            z = z_next;
+            sraw = sraw_next;
+            have_trial = false;
+          } else {
             RB_VIEWS;
             const double* __restrict__ const up = u;
             const double* __restrict__ const gp = g;
-            elems4<double>(m, [&](int i) {
+            elems_act<double>(act, n_el, [&](int i) {
               const double t = up[i] + alpha * gp[i];
               const double r = t > 0.0 ? t : 0.0;
               xs[i] = r;
@@ -1056,7 +1142,11 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
           R.sum2(z, sraw);
           const double nrm = sqrt(z);
           sum_un = (z > 0.0) ? sraw / nrm : sraw;
-          {
+          if (act) {
+            // resident pass: it overwrites (M x)_i, (C x)_i of the rows that hold entries; the others stay zero
+            RB_VIEWS;
+            if (z > 0.0) elems_act<int>(act, n_el, [&](int i) { xs[i] = xs[i] / nrm; return 0; }, [](int) {});
+          } else {
             RB_VIEWS;
             elems4<int>(mp, [&](int i) {
               if (z > 0.0 && i < m) xs[i] = xs[i] / nrm;
@@ -1072,7 +1162,7 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
           {
             RB_VIEWS;
             const double* __restrict__ const up = u;
-            elems4<V2>(m, [&](int i) {
+            elems_act<V2>(act, n_el, [&](int i) {
               const double xi = xs[i];
               const double gi = (((1.0 + d) * xi - d * sum_un) + aM[i]) + aC[i] * d;
               const double t = xi - up[i];
@@ -1090,24 +1180,43 @@ __global__ void __launch_bounds__(NT, 1) rb_solver_kernel(const RbSolveArgs A) {
         const double deltau = sqrt(du2);
         F = Fnew;
         sum_u = sum_un;
-        {
+        const bool converged = (deltau < sp.tol_u || fabs(deltaF) < sp.tol_F);
+        if (converged || j_il + 1 >= sp.maxiniters) {
           RB_VIEWS;
           double* __restrict__ const up = u;
           double* __restrict__ const gp = g;
-          elems4<int>(m, [&](int i) {
+          elems_act<int>(act, n_el, [&](int i) {
             const double xi = xs[i];
             up[i] = xi;
             gp[i] = (((1.0 + d) * xi - d * sum_un) + aM[i]) + aC[i] * d;
             return 0;
           }, [](int) {});
+        } else {
+          RB_VIEWS;
+          double* __restrict__ const up = u;
+          double* __restrict__ const gp = g;
+          const double alpha1 = 1.0;
+          z_next = 0.0;
+          sraw_next = 0.0;
+          elems_act<double>(act, n_el, [&](int i) {
+            const double xi = xs[i];
+            const double gi = (((1.0 + d) * xi - d * sum_un) + aM[i]) + aC[i] * d;
+            up[i] = xi;
+            gp[i] = gi;
+            const double t = xi + alpha1 * gi;
+            const double r = t > 0.0 ? t : 0.0;
+            xs[i] = r;
+            return r;
+          }, [&](double r) { z_next += r * r; sraw_next += r; });
+          have_trial = true;
         }
-        if (deltau < sp.tol_u || fabs(deltaF) < sp.tol_F) break;
+        if (converged) break;
       }
       // ---- increase d (clipper.cpp:339-351), from the kept M u, C u
       double cnt = 0.0, s = 0.0;
       {
         RB_VIEWS;
-        elems4<V2>(m, [&](int i) {
+        elems_act<V2>(act, n_el, [&](int i) {
           const double ui = xs[i];
           const double cbu = (sum_u - aC[i]) - ui;
           const bool in = cbu > sp.eps && ui > sp.eps;
