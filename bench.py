@@ -46,6 +46,8 @@ if ROOT not in sys.path:
 
 SEM_DIM, METHOD = 768, "roman"
 D_ROW = 3 + 3 + 1 + SEM_DIM
+CFG5_POOL = 4   # robot pairs a cfg5 run rotates through (see run_b200)
+GATHER_RING = 4 # N > 1: all-gathers of per-pair records that may be in flight behind the next steps' kernels
 METRIC = "submap-pair alignments/sec at N=2000 correspondences"
 UNIT = "alignments/s"
 T_TOL = 1e-4
@@ -383,16 +385,20 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     K, W = args.steps, args.warmup
 
-    eng = Engine(local)
-    eng.set_invariant_params(make_invariant_params(**method_invariant_kwargs(METHOD, semantics_dim=SEM_DIM)))
-    if args.promote >= 0:
-        eng.set_solver_promote(args.promote)
-    if args.cluster > 0:
-        eng.set_solver_cluster(args.cluster)
-    elif args.config == "cfg5":   # the preset roman_b200.align.align_submap_pairs applies to an all-pairs search
-        from roman_b200.align.submap_align import ALL_PAIRS_SOLVER_CLUSTER
-        eng.set_solver_cluster(ALL_PAIRS_SOLVER_CLUSTER)
-    eng.set_profiling(True)
+    def make_engine():
+        e = Engine(local)
+        e.set_invariant_params(make_invariant_params(**method_invariant_kwargs(METHOD, semantics_dim=SEM_DIM)))
+        if args.promote >= 0:
+            e.set_solver_promote(args.promote)
+        if args.cluster > 0:
+            e.set_solver_cluster(args.cluster)
+        elif args.config == "cfg5":   # the preset roman_b200.align.align_submap_pairs applies to an all-pairs search
+            from roman_b200.align.submap_align import ALL_PAIRS_SOLVER_CLUSTER
+            e.set_solver_cluster(ALL_PAIRS_SOLVER_CLUSTER)
+        e.set_profiling(True)
+        return e
+
+    eng = make_engine()
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a).reshape(-1)).pin_memory()
 
     def sync():
@@ -401,122 +407,185 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     class Bound:
-        """A workload planned on the engine with its device / pinned buffers."""
+        """A workload planned on an engine with its device / pinned buffers."""
 
-        def __init__(self, wl):
+        def __init__(self, wl, engine=None):
             self.wl = wl
+            self.eng = engine if engine is not None else eng
             self.D1p, self.D2p, self.u0p = pin(wl.D1), pin(wl.D2), pin(wl.u0)
             self.D1d, self.D2d, self.u0d = self.D1p.to(dev), self.D2p.to(dev), self.u0p.to(dev)
             B = wl.B
-            self.rec = torch.zeros((B, 20), dtype=torch.float64, device=dev)   # status, n_inliers, F, pad, T[16]
-            self.gathered = torch.zeros((world * B, 20), dtype=torch.float64, device=dev) if world > 1 else None
+            # N > 1: per-pair records (status, n_inliers, F, pad, T[16]) and their all-gather, a ring of GATHER_RING in flight
+            self.rec = [torch.zeros((B, 20), dtype=torch.float64, device=dev) for _ in range(GATHER_RING)] if world > 1 else None
+            self.gathered = [torch.zeros((world * B, 20), dtype=torch.float64, device=dev) for _ in range(GATHER_RING)] if world > 1 else None
+            self.work = [None] * GATHER_RING
+            self.nstep = 0
             self.res = None
+            self.out_h = None
 
         def plan(self, tile_skip):
-            eng.set_tile_skip(tile_skip)
-            self.wl.plan(eng)          # the format decides the solver's cluster size; planning is untimed
-            self.res = eng.alloc_result()
+            self.eng.set_tile_skip(tile_skip)
+            self.wl.plan(self.eng)     # the format decides the solver's cluster size; planning is untimed
+            self.res = self.eng.alloc_result()
 
         def step(self):
             res = self.res
-            eng.align_batch(self.D1d, self.D2d, self.u0d, out=res)
-            if world > 1:  # the path's only exchange: all-gather of fixed-size per-pair records
-                rec = self.rec
+            self.eng.align_batch(self.D1d, self.D2d, self.u0d, out=res)
+            if world > 1:
+                # The path's only exchange: all-gather of fixed-size per-pair records.  It is ASYNCHRONOUS: NCCL runs it on
+                # its own stream behind this step's kernels, and the launch stream goes straight on with the next step; a
+                # slot of the ring is waited for only when it comes round again (and all of them before the timed region
+                # ends).  A blocking all-gather makes every step as long as the slowest rank's — with data-dependent work
+                # per search that cost the all-pairs config 15 % at N = 8.
+                k = self.nstep % GATHER_RING
+                self.nstep += 1
+                if self.work[k] is not None:
+                    self.work[k].wait()
+                rec = self.rec[k]
                 rec[:, 0] = res.status.to(torch.float64)
                 rec[:, 1] = res.n_sel.to(torch.float64)
                 rec[:, 2] = res.score
                 rec[:, 4:] = res.T.reshape(-1, 16)
-                dist.all_gather_into_tensor(self.gathered, rec)
+                self.work[k] = dist.all_gather_into_tensor(self.gathered[k], rec, async_op=True)
+
+        def drain(self):
+            """The launch stream waits for every all-gather still in flight."""
+            for k, w in enumerate(self.work):
+                if w is not None:
+                    w.wait()
+                    self.work[k] = None
+
+        def host_step(self):
+            self.out_h = self.eng.align_batch_host(self.D1p, self.D2p, self.u0p, out=self.out_h)
 
         def timed(self, tile_skip, K, W, sampler=None):
-            """W warm-ups, then exactly K steps between device events; max over ranks."""
-            self.plan(tile_skip)
-            for _ in range(W):
-                self.step()
-            sync()
-            if sampler is not None:
-                sampler.mark()  # only samples taken from here on (the timed region) are reported
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            stage = {"prep": 0.0, "affinity": 0.0, "solve": 0.0, "arun": 0.0}
-            sync()
-            ev0.record()
-            for _ in range(K):
-                self.step()
-                for k, v in eng.stage_ms().items():  # CUDA events on the launch stream (syncs on the step's last event)
-                    stage[k] += v / K
-            ev1.record()
-            sync()
-            t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-            smax = torch.tensor([stage["solve"]], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                all_solve = [torch.zeros_like(smax) for _ in range(world)]
-                dist.all_gather(all_solve, smax)
-                stage["solve_per_rank"] = [float(x.item()) for x in all_solve]
-            return float(t.item()), stage
+            ms, stage, _ = timed_pool([self], tile_skip, K, W, sampler)
+            return ms, stage
 
         def e2e(self, K, W):
-            """K calls of the host-buffer C ABI entry point: pinned host inputs, H2D + kernels + D2H inside the timed region."""
-            out_h = None
-            sync()
-            for _ in range(max(1, min(W, 3))):
-                out_h = eng.align_batch_host(self.D1p, self.D2p, self.u0p, out=out_h)
-            sync()
-            t0 = time.perf_counter()
-            for _ in range(K):
-                out_h = eng.align_batch_host(self.D1p, self.D2p, self.u0p, out=out_h)
-            wall = time.perf_counter() - t0
-            te = torch.tensor([wall], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            h2d, d2h = eng.host_copy_bytes()
-            return world * self.wl.B * K / float(te.item()), out_h, h2d, d2h
+            v, last, h2d, d2h = e2e_pool([self], K, W)
+            return v, last.out_h, h2d, d2h
 
-    wl = build_workload(args.config, rank, world, args.batch, args.desc_common, args.rank_offset)
-    bw = Bound(wl)
-    B, m = wl.B, wl.m
+    def timed_pool(pool, tile_skip, K, W, sampler=None):
+        """W warm-ups (of every member), then exactly K steps between device events; max over ranks.  Step s of rank r
+        runs member (r + s) mod len(pool): with one member that is the same batch every step, with several (cfg5) every
+        rank works through the same rotation of workloads."""
+        for b in pool:
+            b.plan(tile_skip)
+            for _ in range(W):
+                b.step()
+            b.drain()
+        sync()
+        if sampler is not None:
+            sampler.mark()  # only samples taken from here on (the timed region) are reported
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stage = {"prep": 0.0, "affinity": 0.0, "solve": 0.0, "arun": 0.0}
+        counts = [0] * len(pool)
+        sync()
+        ev0.record()
+        for s_ in range(K):
+            k = (rank + s_) % len(pool)
+            b = pool[k]
+            b.step()
+            counts[k] += 1
+            for kk, v in b.eng.stage_ms().items():  # CUDA events on the launch stream (syncs on the step's last event)
+                stage[kk] += v / K
+        for b in pool:
+            b.drain()      # the timed region ends when the last all-gather has landed
+        ev1.record()
+        sync()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        smax = torch.tensor([stage["solve"]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            all_solve = [torch.zeros_like(smax) for _ in range(world)]
+            dist.all_gather(all_solve, smax)
+            stage["solve_per_rank"] = [float(x.item()) for x in all_solve]
+        return float(t.item()), stage, counts
+
+    def e2e_pool(pool, K, W):
+        """K calls of the host-buffer C ABI entry point: pinned host inputs, H2D + kernels + D2H inside the timed region."""
+        sync()
+        for b in pool:
+            for _ in range(max(1, min(W, 3))):
+                b.host_step()
+        sync()
+        last = pool[0]
+        t0 = time.perf_counter()
+        for s_ in range(K):
+            last = pool[(rank + s_) % len(pool)]
+            last.host_step()
+        wall = time.perf_counter() - t0
+        te = torch.tensor([wall], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        h2d, d2h = last.eng.host_copy_bytes()
+        return world * last.wl.B * K / float(te.item()), last, h2d, d2h
+
+    # cfg5: a stream of robot-pair searches dealt round-robin over the GPUs — a pool of CFG5_POOL robot pairs (one engine
+    # each, planned up front), step s of rank r searches pair (r + s) mod pool.  Every rank, at every N, works through
+    # the same rotation, so the N-GPU efficiency measures the machine and not which robot pair a rank happened to get
+    # (the work of a search depends on its data: K2 of one 400-problem search ranges from 5.9 to 8.9 ms over seeds).
+    if args.config == "cfg5":
+        pool = [Bound(build_workload("cfg5", k, world, args.batch, args.desc_common, args.rank_offset), eng if k == 0 else make_engine())
+                for k in range(CFG5_POOL)]
+    else:
+        pool = [Bound(build_workload(args.config, rank, world, args.batch, args.desc_common, args.rank_offset))]
+    wl = pool[0].wl
+    B = wl.B
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         sampler.wait_ready()
+
+    def cat(counts, f):
+        """Per-problem arrays of the K timed steps, concatenated (member k appears counts[k] times)."""
+        return np.concatenate([np.tile(np.asarray(f(b)), c) for b, c in zip(pool, counts) if c])
+
     # ---- main measurement: the library's default (dense) format — every tile of the packed upper triangle is written
     #      by K1 and streamed by K2 each pass: the kernels and byte counts of BASELINE.json's north_star / SURVEY 8d
-    ms, stage = bw.timed(False, K, W, sampler if rank == 0 else None)
+    ms, stage, counts = timed_pool(pool, False, K, W, sampler if rank == 0 else None)
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * K / (ms * 1e-3)
-    passes = bw.res.n_passes.cpu().numpy().astype(np.int64)
-    streamed = eng.solver_streamed_passes().cpu().numpy().astype(np.int64)   # passes that read M from HBM
-    promoted = int((eng.solver_resident().cpu().numpy()[:B] >= 3).sum())
-    live = eng.live_counts().cpu().numpy().astype(np.int64)
+    m = cat(counts, lambda b: b.wl.m)
+    passes = cat(counts, lambda b: b.res.n_passes.cpu().numpy().astype(np.int64))
+    streamed = cat(counts, lambda b: b.eng.solver_streamed_passes().cpu().numpy().astype(np.int64)[:B])   # passes that read M from HBM
+    promoted = int(round(float((cat(counts, lambda b: b.eng.solver_resident().cpu().numpy()[:B]) >= 3).sum()) / K))
+    live = cat(counts, lambda b: b.eng.live_counts().cpu().numpy().astype(np.int64)[:B])
     cluster_dense = eng.solver_cluster
     packed_bytes = eng.packed_bytes
-    e2e_value, out_h, h2d, d2h = bw.e2e(K, W)
+    e2e_value, last, h2d, d2h = e2e_pool(pool, K, W)
+    out_h, wl_chk = last.out_h, last.wl
 
     # ---- same batch through the opt-in sparse fast path (rb_set_tile_skip): only tiles holding a non-zero are stored,
     #      K1 lists the edges, K2 solves from a shared-memory CSR.  N = 1 only: the N-GPU sweep stays short.
     do_fast = (args.format == "both") and world == 1
     if do_fast:
-        ms_f, stage_f = bw.timed(True, K, W)
-        passes_f = bw.res.n_passes.cpu().numpy().astype(np.int64)
-        stored = eng.stored_tiles().cpu().numpy().astype(np.int64)[:B]
-        resident = eng.solver_resident().cpu().numpy().astype(np.int64)[:B]
-        edges = eng.edge_counts().cpu().numpy().astype(np.int64)[:B]
+        ms_f, stage_f, counts_f = timed_pool(pool, True, K, W)
+        passes_f = cat(counts_f, lambda b: b.res.n_passes.cpu().numpy().astype(np.int64))
+        stored = cat(counts_f, lambda b: b.eng.stored_tiles().cpu().numpy().astype(np.int64)[:B])
+        resident = cat(counts_f, lambda b: b.eng.solver_resident().cpu().numpy().astype(np.int64)[:B])
+        edges = cat(counts_f, lambda b: b.eng.edge_counts().cpu().numpy().astype(np.int64)[:B])
+        m_f = cat(counts_f, lambda b: b.wl.m)
         cluster_fast = eng.solver_cluster
-        e2e_fast, _, _, _ = bw.e2e(K, W)
-        eng.set_tile_skip(False)
+        e2e_fast, _, _, _ = e2e_pool(pool, K, W)
+        for b in pool:
+            b.eng.set_tile_skip(False)
 
     if rank == 0:
         peaks, which = measured_peaks()
         peak = float(peaks["hbm_gbs"])
         gbs = lambda nbytes, t_ms: nbytes / (t_ms * 1e-3) / 1e9
-        # algorithmic bytes, dense format (SURVEY 8d with the packed-upper layout, s = 8): K1 writes and K2 reads per
-        # pass s*m(m-1)/2; K1 also reads the feature tables (shared tables once) and writes the single scores.
+        # algorithmic bytes PER LAUNCH (the arrays hold all K timed steps), dense format (SURVEY 8d with the packed-upper
+        # layout, s = 8): K1 writes and K2 reads per pass s*m(m-1)/2; K1 also reads the feature tables (shared tables
+        # once) and writes the single scores.
         tri = 8.0 * m * (m - 1) / 2
-        in_bytes = (wl.table_bytes if wl.indexed else float((8.0 * D_ROW * (wl.n1 + wl.n2)).sum())) + 8.0 * float(m.sum())
+        tbl = lambda w: (w.table_bytes if w.indexed else float((8.0 * D_ROW * (w.n1 + w.n2)).sum())) + 8.0 * float(w.m.sum())
+        in_bytes = sum(c * tbl(b.wl) for b, c in zip(pool, counts)) / K
         # K2: only passes that stream the matrix count (a problem still iterating after 8 streamed passes is extracted
         # into shared memory — rb_set_solver_promote — and its remaining passes move no HBM bytes)
-        k2_bytes = float((streamed * (tri + 24.0 * m)).sum())
-        k1_bytes = float(tri.sum()) + in_bytes
+        k2_bytes = float((streamed * (tri + 24.0 * m)).sum()) / K
+        k1_bytes = float(tri.sum()) / K + in_bytes
         k1_ms = stage["prep"] + stage["affinity"]
         nbt = (m + 31) // 32
         n_tiles = nbt * (nbt + 1) // 2
@@ -529,7 +598,7 @@ def run_b200(args):
         if args.no_parity:
             bad, okind, idx = [], None, []
         else:
-            bad, okind = check_parity(wl, out_h, idx)
+            bad, okind = check_parity(wl_chk, out_h, idx)
             if bad:
                 print(f"PARITY MISMATCH on problems {bad[:20]} of the timed batch", file=sys.stderr)
         line = {
@@ -538,7 +607,8 @@ def run_b200(args):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl.text, "name": wl.name, "pairs_per_gpu_per_step": B,
-                       "parallelism": (f"one robot pair (20 x 20 submaps = {B} problems, longest first) per GPU, {world} GPU(s)" if wl.name == "cfg5"
+                       "parallelism": (f"one robot pair (20 x 20 submaps = {B} problems, longest first) per GPU per step, {world} GPU(s); "
+                                       f"step s of rank r searches pair (r + s) mod {CFG5_POOL} of a pool of {CFG5_POOL}" if wl.name == "cfg5"
                                        else f"round-robin pairs over {world} GPU(s)"),
                        "l2": f"inputs larger than L2: packed affinity working set {packed_bytes / 1e9:.2f} GB per GPU per step",
                        "layout": "packed upper triangle, 32x32 fp64 tiles, dense format (every tile written by K1 and streamed by K2 each pass)",
@@ -573,9 +643,11 @@ def run_b200(args):
         if do_fast:
             # fast path bytes: a problem solved from K1's edge list reads 12 B per edge once; one built from its tiles reads
             # them once; a streamed one reads them every pass; plus u0 in, scratch and outputs (~24 m) and the tile flags
+            nbt_f = (m_f + 31) // 32
+            n_tiles_f = nbt_f * (nbt_f + 1) // 2
             per_prob = np.where(resident == 2, edges * 12, np.where(resident == 1, stored * 8192, passes_f * stored * 8192))
-            k2f = float((per_prob + 24 * m).sum()) + float(n_tiles.sum())
-            k1f = float(stored.sum()) * 8192 + float(n_tiles.sum()) + float(np.minimum(edges, 32 * nbt).sum()) * 12 + in_bytes
+            k2f = (float((per_prob + 24 * m_f).sum()) + float(n_tiles_f.sum())) / K
+            k1f = (float(stored.sum()) * 8192 + float(n_tiles_f.sum()) + float(np.minimum(edges, 32 * nbt_f).sum()) * 12) / K + in_bytes
             k1f_ms = stage_f["prep"] + stage_f["affinity"]
             line["fast_path"] = {
                 "what": "same batch with rb_set_tile_skip(1), the opt-in sparse fast path (SURVEY 8f rank 2): K1 stores only tiles "
@@ -587,14 +659,14 @@ def run_b200(args):
                 "kernels": {"K1_affinity": {"ms_per_launch": k1f_ms, "K1a_prep_ms": stage_f["prep"], "bytes_per_launch": k1f, "achieved": gbs(k1f, k1f_ms)},
                             "K2_solver": {"ms_per_launch": stage_f["solve"], "bytes_per_launch": k2f, "achieved": gbs(k2f, stage_f["solve"])},
                             "K3_arun_ms": stage_f["arun"]},
-                "resident_problems": int((resident > 0).sum()), "from_edge_list": int((resident == 2).sum()),
-                "streamed_problems": int((resident == 0).sum()),
+                "resident_problems": int(round((resident > 0).sum() / K)), "from_edge_list": int(round((resident == 2).sum() / K)),
+                "streamed_problems": int(round((resident == 0).sum() / K)),
                 "mean_edges": float(edges.mean()), "max_edges": int(edges.max()), "mean_stored_tiles": float(stored.mean()),
-                "mean_tiles_per_problem": float(n_tiles.mean()), "solver_cluster": int(cluster_fast)}
+                "mean_tiles_per_problem": float(n_tiles_f.mean()), "solver_cluster": int(cluster_fast)}
         if world == 1 and wl.name == "metric" and args.desc_common is None and not args.no_variants:
             line["config"]["variants"] = {"cone": cone_variant(Bound, eng, K, W, peak)}
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline(wl)
+            line["cpu_baseline"] = cpu_baseline(pool[0].wl)
         emit(line)
     if world > 1:
         dist.destroy_process_group()
