@@ -508,8 +508,9 @@ __global__ void __launch_bounds__(256) rb_block_mask_kernel(const RbProblem* __r
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1: one warp per 32x32 tile, lane = tile column; 32 coalesced 256-byte row stores per tile
-// (each row is written as a permutation of itself: the XOR swizzle of rb_common.cuh).
+// K1: one warp per 32x32 tile.  The tile is written as zeros (coalesced 16-byte stores; each row is a permutation of
+// itself: the XOR swizzle of rb_common.cuh); the (live row, live column) pairs are screened, the survivors scored on
+// full warps and their non-zero words written over the zeros (affinity_tile below).
 // Grid = (CTAs per problem, problems).  A CTA first condenses the problem's block live masks into the
 // list of LIVE blocks (blocks holding at least one association that can carry an edge); only tiles
 // whose row block and column block are both live are evaluated.
