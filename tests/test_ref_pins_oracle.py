@@ -227,3 +227,41 @@ def test_roman_invariant_through_score_pairwise_consistency(R, coracle):
         assert np.abs(Mo - Mn).max() < 1e-14
         Mfull, _ = R.score(ip, sp, p.D1, p.D2)          # and it is NOT what the pairwise-and-single entry computes
         assert not np.array_equal(Mr, Mfull)
+
+
+def k1_screen(ip, ai, aj, bi, bj):
+    """numpy restatement of K1's z-gate screen (rb_affinity.cu: make_zgate / zgate_pass): False <=> K1 skips the pair."""
+    if not (ip.gravity_guided and not ip.drift_aware):
+        return True
+    K13 = 0.57735026919                                  # roman.cpp:12, truncated literal
+    daz, dbz = ai[2] - aj[2], bi[2] - bj[2]
+    eps_z = ip.epsilon
+    if ip.gravity_unc_ang_rad > 0.0:
+        eps_z = eps_z + abs(0.5 * (abs(daz) + abs(dbz)) * np.sin(ip.gravity_unc_ang_rad))
+    return not (abs(daz - dbz) > K13 * eps_z)
+
+
+def test_k1_z_gate_screen_is_implied_by_the_reference_pairwise_score(R):
+    """K1 evaluates the reference's z test (roman.cpp:54-77) BEFORE everything else and skips a pair that fails it.  Against
+    the reference's own pairwise_similarity: a skipped pair scores exactly 0 there, in either operand order, and near the
+    gate's threshold the screen and the reference agree on which side a pair falls (same fp64 expressions)."""
+    rng = np.random.default_rng(23)
+    n_skipped = n_kept_nonzero = 0
+    for trial in range(3000):
+        ip = random_invariant(rng, 8)
+        pts = [np.ascontiguousarray(np.concatenate([rng.uniform(-3, 3, 2), rng.uniform(-1.5, 1.5, 1)])) for _ in range(4)]
+        if trial % 3 == 0 and ip.gravity_guided and not ip.drift_aware:
+            # put the pair within a few ulp of the z threshold
+            dz = 0.57735026919 * ip.epsilon
+            if ip.gravity_unc_ang_rad == 0.0:
+                pts[3][2] = pts[2][2] - ((pts[0][2] - pts[1][2]) - dz) + float(rng.integers(-3, 4)) * np.spacing(dz)
+        rows = [np.ascontiguousarray(np.concatenate([p, np.ones(ip.ratio_feature_dim), np.ones(ip.cos_feature_dim)])) for p in pts]
+        keep = k1_screen(ip, pts[0], pts[1], pts[2], pts[3])
+        assert keep == k1_screen(ip, pts[1], pts[0], pts[3], pts[2])        # operand order does not matter
+        p = R.pairwise_similarity(ip, *rows)
+        if not keep:
+            n_skipped += 1
+            assert p == 0.0 and R.pairwise_similarity(ip, rows[1], rows[0], rows[3], rows[2]) == 0.0, (trial, p)
+        elif p > 0.0:
+            n_kept_nonzero += 1
+    assert n_skipped > 200 and n_kept_nonzero > 100
