@@ -329,7 +329,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC if wl.name == "metric" else f"submap-pair alignments/sec ({wl.name})", "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl.text, "pairs_per_step": n,
+            "config": {"workload": wl.text, "name": wl.name, "pairs_per_gpu_per_step": wl.B,   # same keys / values as the GPU arm's
+                       "sample_pairs_per_step": n,                                               # what one CPU step processes of it
                        "note": ("the reference's own C++ sources (dependencies/clipper: clipper.cpp, utils.cpp, invariants/roman.cpp) "
                                 "compiled against the committed Eigen stand-in (oracle/_ref), plus the numpy Arun of T_align restated in C"
                                 if arm.kind == "reference" else
