@@ -215,7 +215,7 @@ def align_submap_pairs(sm_params: SubmapAlignParams, submaps0: Sequence[List], s
     # all-pairs preset: most submap pairs of a search do not overlap, and a problem without a consistent clique
     # iterates for hundreds of passes — out of the shared-memory CSR after the first few.  One CTA per problem then
     # beats the library's default of two (which exists to shorten the tail of a batch whose problems STREAM their
-    # matrix): measured on the 20 x 20 search of bench.py --config cfg5, 12.0 ms against 15.8 ms per search.
+    # matrix): measured on the 20 x 20 search of bench.py --config cfg5, 7.8 ms against 11.2 ms of solver time per search.
     eng.set_solver_cluster(ALL_PAIRS_SOLVER_CLUSTER)
     m = [len(a) for a in A_list] if exclude_common_ids else None
     eng.plan(D1.shape[1], n1_all[pi], n2_all[pj], m=m, obj1_offsets=off1[pi], obj2_offsets=off2[pj],
